@@ -1,0 +1,165 @@
+/* include/ldpc_b200.h — C ABI of libldpc_b200.so (sm_100a).
+ *
+ * The drop-in boundary for ONE hot path of thadikari/ldpc_decoders: the
+ * iterative message-passing decoders
+ *     bpa.SPA / bpa.MSA      (/root/reference/src/bpa.py:6-102)
+ *     bec.SPA (= bec.MSA)    (/root/reference/src/bec.py:70-125)
+ * and their channel LLR front ends (src/bsc.py:19-25, src/biawgn.py:10,21-28,
+ * src/bec.py:76,85), decoding a BATCH of frames per call on one B200.
+ *
+ * The reference has no FFI on this path (it is numpy/scipy Python); its only
+ * FFI precedent is src/parity_polytope/exact.py:12-26,41-60 (ctypes,
+ * caller-allocated outputs, void returns).  This header is what a ctypes
+ * binding on the reference side would load instead of calling
+ * bpa.BPA.decode / bec.SPA.decode frame by frame — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (a CUDA stream
+ *     is passed as void*, NULL = the legacy default stream).
+ *   - every function returns LDPC_OK (0) or a negative error code and never
+ *     throws or exits; ldpc_last_error() gives the message.
+ *   - "device" pointers are CUDA device pointers on the handle's device and
+ *     are CALLER-OWNED (e.g. torch.empty(...).data_ptr()); the handle owns
+ *     only the graph tables (and, for ldpc_decode_host, its staging buffers).
+ *   - ldpc_decode / ldpc_llr_* / ldpc_debug_step are asynchronous on the
+ *     given stream and never synchronise; ldpc_create / ldpc_destroy /
+ *     ldpc_decode_host synchronise.
+ *   - one handle per (process, device); a handle is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device ldpc_create fails.
+ */
+#ifndef LDPC_B200_H
+#define LDPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDPC_ABI_VERSION 1
+
+/* algo: which reference decoder is replaced */
+#define LDPC_MSA 0   /* bpa.MSA.decode_      src/bpa.py:86-102  */
+#define LDPC_SPA 1   /* bpa.SPA.decode_      src/bpa.py:71-75   */
+#define LDPC_BEC 2   /* bec.SPA.decode       src/bec.py:83-122  */
+
+/* dtype: arithmetic type of the messages (the reference is dtype-polymorphic
+ * through priors.dtype).
+ *   MSA: F32 / F64 are both bit-exact restatements at that dtype.
+ *   SPA: F64 mirrors the reference formula (tanh / log / exp / atanh);
+ *        F32 is the production form (phi-domain, numerically stable).
+ *   BEC: dtype is ignored (bit-plane integer arithmetic). */
+#define LDPC_F32 0
+#define LDPC_F64 1
+
+/* per-frame exit reason written by ldpc_decode (the reference's ret('...')
+ * strings, src/bpa.py:28-29, src/bec.py:96-97,120) */
+#define LDPC_REASON_DECODED  0
+#define LDPC_REASON_MAXIMUM  1
+#define LDPC_REASON_STOPPING 2   /* BEC only */
+#define LDPC_REASON_CAP      4   /* stopped by iter_cap while max_iter <= 0 (reference: unlimited) */
+
+/* error codes */
+#define LDPC_OK           0
+#define LDPC_EINVAL      -1
+#define LDPC_ECUDA       -2
+#define LDPC_ENOMEM      -3
+#define LDPC_EWORKSPACE  -4   /* workspace too small / misaligned */
+#define LDPC_EUNSUPPORTED -5
+
+/* flags for ldpc_decode */
+#define LDPC_PATH_AUTO      0u   /* resident kernel when the code fits on chip, else streaming */
+#define LDPC_PATH_STREAMING 1u   /* edge-major [E][B] messages in HBM, one CN + one VN sweep per iteration */
+#define LDPC_PATH_RESIDENT  2u   /* whole frames kept in shared memory for all iterations (short codes) */
+#define LDPC_PATH_MASK      3u
+
+/* channel kinds for ldpc_decode_host / ldpc_channel_llr */
+#define LDPC_CH_PRIORS 0   /* input already is the prior LLR (bpa.*.decode(y, priors)) */
+#define LDPC_CH_BSC    1   /* input y in {0,1};  priors = llr * (1 - 2y),  param = llr = log(1-p) - log(p)  (bsc.py:21,25) */
+#define LDPC_CH_BIAWGN 2   /* input y real;      priors = (-2y) / param,   param = noise_var = 10**(-snr/10) (biawgn.py:10,28) */
+#define LDPC_CH_BEC    3   /* input y in {0,1,2 = erasure} (bec.py:76,85) */
+
+typedef struct ldpc_handle ldpc_t;
+
+int ldpc_abi_version(void);
+
+/* Build a decoder handle for one parity-check matrix H (replaces
+ * bpa.BPA.__init__, src/bpa.py:9-15, and bec.SPA.__init__, src/bec.py:73-81).
+ * Tables are HOST pointers (copied):
+ *   edge e = position in np.where(H) order (check-major, ascending variable)
+ *   chk_ptr[m+1], edge_var[E]     check-major CSR of H
+ *   var_ptr[n+1], var_edges[E]    per variable, its edge ids in ascending order
+ * Validates the tables (monotone pointers, sorted, in range). */
+int ldpc_create(ldpc_t **out, int device, int n, int m, int E,
+                const int32_t *chk_ptr, const int32_t *edge_var,
+                const int32_t *var_ptr, const int32_t *var_edges);
+
+void ldpc_destroy(ldpc_t *h);
+
+/* Last error message of this handle (h == NULL: of the last failed ldpc_create). */
+const char *ldpc_last_error(const ldpc_t *h);
+
+/* Bytes of device workspace ldpc_decode needs for B frames (0 on bad arguments). */
+size_t ldpc_workspace_bytes(const ldpc_t *h, int algo, int dtype, int B, unsigned flags);
+
+/* Decode B frames (replaces B calls of bpa.BPA.decode(y, priors), src/bpa.py:17-63,
+ * or bec.SPA.decode(y), src/bec.py:83-122).
+ *   input    device [B,n] row-major: MSA/SPA priors of `dtype`; BEC uint8 symbols {0,1,2}
+ *   y_hard   device [B,n] uint8 hard received bits, or NULL.  MSA/SPA only: the
+ *            iteration-0 syndrome test (src/bpa.py:29 on x_hat = y) is run on it;
+ *            NULL skips that test (BIAWGN: real-valued y never passes it).
+ *   max_iter reference semantics: `0 < max_iter <= it` stops; max_iter <= 0 is
+ *            unlimited in the reference, here it runs until iter_cap (> 0 required).
+ *   x_hat    device [B,n] uint8: decoded bits (BEC: symbols, 2 = still erased).
+ *            A frame that exits at iteration 0 returns y_hard / the input symbols.
+ *   iters    device [B] int32: the reference's iter_count at return.
+ *   reason   device [B] uint8 LDPC_REASON_*, or NULL.
+ *   marg_out device [B,n] of `dtype`, or NULL: last marginal of every frame
+ *            (before the NaN scrub, src/bpa.py:35), for verification.  MSA/SPA only.
+ */
+int ldpc_decode(ldpc_t *h, int algo, int dtype,
+                const void *input, const uint8_t *y_hard, int B,
+                int max_iter, int iter_cap,
+                uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *marg_out,
+                void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
+
+/* Channel LLR front ends on device buffers (elementwise, any shape, `count` elements).
+ *   BSC:    y uint8 {0,1}             -> priors(dtype) = llr * (1 - 2y)       src/bsc.py:25
+ *   BIAWGN: y of y_dtype (F32 | F64)  -> priors(dtype) = (-2 y) / noise_var   src/biawgn.py:28
+ * computed in float64 and rounded once to `dtype` (== reference priors.astype(dtype)). */
+int ldpc_llr_bsc(ldpc_t *h, int dtype, double llr, const uint8_t *y, void *priors, size_t count, void *stream);
+int ldpc_llr_biawgn(ldpc_t *h, int y_dtype, int dtype, double noise_var, const void *y, void *priors,
+                    size_t count, void *stream);
+
+/* One isolated sweep on caller-supplied messages in the reference's own layout
+ * (teacher-forced parity): device [B,E] row-major, edge order of np.where(H).
+ *   which = 0: check-node sweep   c2v = CN(v2c)            (src/bpa.py:71-75 / 86-102)
+ *   which = 1: variable-node sweep: marg = prior + sum c2v, v2c = marg[yy] - c2v (src/bpa.py:35-37)
+ * Runs the same device math as the streaming kernels.  Synchronous-free, on `stream`. */
+int ldpc_debug_step(ldpc_t *h, int algo, int dtype, int which, int B,
+                    const void *prior /* [B,n], which=1 */, const void *msg_in /* [B,E] */,
+                    void *msg_out /* [B,E] */, void *marg /* [B,n], which=1, may be NULL */,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* End-to-end call with HOST buffers (what the Python decode_batch uses for numpy
+ * input): chunks the batch, overlaps H2D copy / LLR + decode / D2H copy on internal
+ * streams, and returns when x_hat / iters are complete in host memory.
+ *   channel  LDPC_CH_*; param = llr (BSC) or noise_var (BIAWGN), ignored otherwise
+ *   y        host [B,n] row-major; y_dtype: LDPC_F32 / LDPC_F64 for PRIORS and BIAWGN,
+ *            ignored (uint8) for BSC and BEC.  Pinned memory makes the copies asynchronous.
+ *   x_hat    host [B,n] uint8;  iters host [B] int32;  reason host [B] uint8 or NULL
+ *   chunk    frames per pipeline stage (0 = default)
+ * Device staging buffers are owned by the handle and reused across calls. */
+int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
+                     const void *y, int y_dtype, int B, int max_iter, int iter_cap,
+                     uint8_t *x_hat, int32_t *iters, uint8_t *reason,
+                     int chunk, unsigned flags);
+
+/* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
+unsigned long long ldpc_launch_count(const ldpc_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_B200_H */
