@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — decoded frames/s of the LDPC hot path on B200 (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json metric, config 3): LDPC(1200,3,6) `1200_3_6_rand_ldpc_1`, BIAWGN at 2.0 dB,
+min-sum, float32 messages, max_iter 10, all-ones codeword (src/simulations.py:32-33), synthetic noise.
+A step = one pass of the hot path over one batch of FRAMES frames per GPU: LLR front end + transpose,
+10 x (check-node sweep, book-keeping, variable-node sweep) with per-frame early exit, hard decisions out.
+
+  value     frames/s with the received block already resident in HBM (CUDA events on the launching stream)
+  e2e       the same through the host-buffer entry point (ldpc_decode_host behind decode_batch): pinned
+            host y in, x_hat / iteration counts out, copies inside the timed region
+  roofline  the dominant sweep kernel: algorithmic bytes / its event-timed launch durations vs measured HBM peak
+  cpu_baseline / --impl reference: the oracle port (oracle/ldpc_oracle.c, scalar C restatement of src/bpa.py)
+            on the host cores — the reference itself is Python and does not travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CODE = "1200_3_6_rand_ldpc_1"
+SNR_DB = 2.0
+MAX_ITER = 10
+METRIC = "decoded_frames_per_s"
+UNIT = "frames/s"
+
+
+def load_code(name=CODE):
+    import _golden as G
+    return G.code_tables(name)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fp:
+            return float(json.load(fp)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_per_launch(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fp:
+            return json.load(fp).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val == "Active":
+                    reasons.add(nm)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def oracle_rate(tables, snr_db, frames, seconds, threads, dtype=np.float32):
+    """frames/s of the oracle port (scalar C min-sum, one frame per thread at a time) on `threads` host threads."""
+    from oracle import oracle as O
+    m, n, rows, cols = tables
+    g = O.Graph(m, n, rows, cols)
+    rng = np.random.RandomState(7)
+    std = np.sqrt(10 ** (-snr_db / 10))
+    Y = 1.0 + rng.normal(0, std, (frames, n))
+    pri = O.llr_biawgn(snr_db, Y).astype(dtype)
+    O.bp_decode(g, O.MSA, pri[:max(64, threads)], max_iter=MAX_ITER, nthreads=threads)       # warm
+    done, t0, its = 0, time.perf_counter(), 0
+    while True:
+        r = O.bp_decode(g, O.MSA, pri, max_iter=MAX_ITER, nthreads=threads)
+        done += frames
+        its += int(r["iters"].sum())
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return done / el, done, el, its / done
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    tables = load_code()
+    threads = os.cpu_count() or 1
+    frames = max(2048, 128 * threads)
+    from oracle import oracle as O
+    m, n, rows, cols = tables
+    g = O.Graph(m, n, rows, cols)
+    rng = np.random.RandomState(7)
+    Y = 1.0 + rng.normal(0, np.sqrt(10 ** (-SNR_DB / 10)), (frames, n))
+    pri = O.llr_biawgn(SNR_DB, Y).astype(np.float32)
+    its = 0
+    for _ in range(args.warmup):
+        O.bp_decode(g, O.MSA, pri, max_iter=MAX_ITER, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        its += int(O.bp_decode(g, O.MSA, pri, max_iter=MAX_ITER, nthreads=threads)["iters"].sum())
+    el = time.perf_counter() - t0
+    val = frames * args.steps / el
+    sample = "%d frames/step x %d steps of the same workload (float32 min-sum, max_iter %d)" % (frames, args.steps, MAX_ITER)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(frames, world=1),
+        "edge_updates_per_s": 2 * len(rows) * its / el,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(frames, world):
+    return {"workload": "LDPC(1200,3,6) %s, BIAWGN %.1f dB, min-sum, max_iter %d, codeword=1, %d frames/step/GPU"
+                        % (CODE, SNR_DB, MAX_ITER, frames),
+            "code": CODE, "n": 1200, "m": 600, "E": 3600, "channel": "biawgn", "snr_db": SNR_DB, "decoder": "MSA",
+            "max_iter": MAX_ITER, "frames_per_step_per_gpu": frames, "sharding": "frames x%d" % world,
+            "l2": "inputs larger than L2 (message array %.0f MB per GPU vs 126 MB L2)" % (3600 * frames * 4 / 1e6)}
+
+
+def algorithmic_bytes(E, n, s, iters, max_iter):
+    """Per SURVEY.md 8(d): CN sweep 2*E*s + E/8, VN sweep 2*E*s + n*s + n/8 bytes per frame it processes.
+    CN(it) runs for frames with iter_count >= it, VN(it) for frames with iter_count > it."""
+    iters = np.asarray(iters, np.int64)
+    cn_frames = int(np.minimum(iters + 1, max_iter).sum())
+    vn_frames = int(iters.sum())
+    return cn_frames * (2 * E * s + E / 8.0), vn_frames * (2 * E * s + n * s + n / 8.0)
+
+
+def timed_steps(torch, fn, steps, warmup, dist):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        fn()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    if dist is not None:
+        dist.barrier()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def extra_workloads(torch, lib, eng_mod, Tables, peak):
+    """Short side measurements (3 steps each) of the other §8 configurations; rank 0, N = 1 only."""
+    out = []
+    from ldpc_decoders_b200 import codes
+
+    def bp_case(label, tab, algo, dtype, snr, frames, cw=1):
+        eng = eng_mod.engine_for(tab)
+        tdt = torch.float32
+        nv = 10 ** (-snr / 10)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        y = (2 * cw - 1) + nv ** .5 * torch.randn((frames, tab.n), generator=g, device="cuda", dtype=tdt)
+        res = {}
+        def fn():
+            res["o"] = eng.decode_device_channel(lib.CH_BIAWGN, algo, dtype, nv, y, max_iter=MAX_ITER, out=res.get("o"))
+        ms = timed_steps(torch, fn, 3, 2, None)
+        iters = res["o"]["iters"].cpu().numpy()
+        s = 4 if dtype == lib.F32 else 8
+        cn_b, vn_b = algorithmic_bytes(tab.E, tab.n, s, iters, MAX_ITER)
+        fps = frames * 3 / (ms / 1e3)
+        out.append({"workload": label, "value": fps, "unit": UNIT, "mean_iters": float(iters.mean()),
+                    "edge_updates_per_s": 2 * tab.E * float(iters.sum()) * 3 / (ms / 1e3),
+                    "step_hbm_frac": (cn_b + vn_b) * 3 / (ms / 1e3) / 1e9 / peak})
+
+    tab = Tables(*load_code())
+    bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB SPA f32 (phi form), max_iter 10, cw=0", tab, lib.SPA, lib.F32, 2.0, 32768, cw=0)
+    bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB MSA f64, max_iter 10", tab, lib.MSA, lib.F64, 2.0, 16384)
+    bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB SPA f64 (formula mirror), max_iter 10, cw=0", tab, lib.SPA, lib.F64, 2.0, 16384, cw=0)
+    big = codes.random_regular(64800, 3, 6, seed=0).tables
+    bp_case("synthetic (3,6) n=64800 BIAWGN 1.0 dB MSA f32, max_iter 10 (no convergence)", big, lib.MSA, lib.F32, 1.0, 2048)
+    bp_case("synthetic (3,6) n=64800 BIAWGN 2.5 dB MSA f32, max_iter 10", big, lib.MSA, lib.F32, 2.5, 2048)
+    # BEC, config 2
+    eng = eng_mod.engine_for(tab)
+    frames = 131072
+    g = torch.Generator(device="cuda").manual_seed(4)
+    yb = torch.where(torch.rand((frames, tab.n), generator=g, device="cuda") < 0.4, 2, 0).to(torch.uint8)
+    res = {}
+    def fb():
+        res["o"] = eng.decode_device_channel(lib.CH_BEC, lib.BEC, lib.F32, 0.0, yb, max_iter=MAX_ITER, out=res.get("o"))
+    ms = timed_steps(torch, fb, 3, 2, None)
+    iters = res["o"]["iters"].cpu().numpy()
+    out.append({"workload": "LDPC(1200,3,6) BEC p=0.40 erasure decoding (bit planes), max_iter 10, cw=0",
+                "value": frames * 3 / (ms / 1e3), "unit": UNIT, "mean_iters": float(iters.mean()),
+                "edge_updates_per_s": 2 * tab.E * float(iters.sum()) * 3 / (ms / 1e3)})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=32768, help="frames per step per GPU")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from ldpc_decoders_b200 import Tables, _lib as lib
+    from ldpc_decoders_b200 import engine as eng_mod
+    from ldpc_decoders_b200.engine import pinned_empty
+
+    tables = load_code()
+    tab = Tables(*tables)
+    eng = eng_mod.engine_for(tab)
+    B = args.frames
+    nv = 10 ** (-SNR_DB / 10)
+    peak, peak_src = measured_peak()
+
+    # ---- synthetic received block, resident in HBM: y = (2x-1) + sigma * N(0,1), x = all ones; seed by global rank
+    g = torch.Generator(device="cuda").manual_seed(1000 + rank)
+    y = 1.0 + nv ** .5 * torch.randn((B, tab.n), generator=g, device="cuda", dtype=torch.float32)
+    res = {}
+
+    def step():
+        res["o"] = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, y, max_iter=MAX_ITER, out=res.get("o"))
+
+    launches0 = None
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    eng.profile(True)
+    eng.profile_read()
+    launches0 = eng.launch_count
+    ms = timed_steps(torch, step, args.steps, 0, dist)
+    launches = eng.launch_count - launches0
+    prof = eng.profile_read()
+    eng.profile(False)
+    iters = res["o"]["iters"].cpu().numpy()
+    x_hat = res["o"]["x_hat"]
+    wer = float((x_hat != 1).any(dim=1).float().mean().item())
+
+    total_frames = B * args.steps * world
+    value = total_frames / (ms / 1e3)
+    it_sum = float(iters.sum())
+    if dist is not None:
+        t = torch.tensor([it_sum], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        it_sum_all = float(t.item())
+    else:
+        it_sum_all = it_sum
+    edge_updates = 2 * tab.E * it_sum_all * args.steps / (ms / 1e3)
+
+    # ---- roofline of the dominant sweep kernel (this rank), from the events recorded inside the timed steps
+    cn_bytes, vn_bytes = algorithmic_bytes(tab.E, tab.n, 4, iters, MAX_ITER)
+    cn_gbs = cn_bytes * args.steps / (prof["cn_ms"] / 1e3) / 1e9 if prof["cn_ms"] > 0 else 0.0
+    vn_gbs = vn_bytes * args.steps / (prof["vn_ms"] / 1e3) / 1e9 if prof["vn_ms"] > 0 else 0.0
+    dom = "vn_sweep" if prof["vn_ms"] >= prof["cn_ms"] else "cn_sweep"
+    achieved = vn_gbs if dom == "vn_sweep" else cn_gbs
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": peak_src, "traffic": traffic_per_launch(dom),
+        "algorithmic_bytes_per_launch": ((vn_bytes if dom == "vn_sweep" else cn_bytes) * args.steps
+                                         / max(1, prof["vn_launches"] if dom == "vn_sweep" else prof["cn_launches"])),
+        "avg_launch_ms": (prof["vn_ms"] / max(1, prof["vn_launches"])) if dom == "vn_sweep" else (prof["cn_ms"] / max(1, prof["cn_launches"])),
+        "cn_sweep": {"ms_total": prof["cn_ms"], "launches": prof["cn_launches"], "GBps": cn_gbs, "frac": cn_gbs / peak},
+        "vn_sweep": {"ms_total": prof["vn_ms"], "launches": prof["vn_launches"], "GBps": vn_gbs, "frac": vn_gbs / peak},
+        "sweeps_share_of_step": (prof["cn_ms"] + prof["vn_ms"]) / ms,
+        "step_frac": (cn_bytes + vn_bytes) * args.steps / (ms / 1e3) / 1e9 / peak,
+        "bytes_per_edge_iteration": 17.5,
+    }
+
+    # ---- e2e: host buffers through the host entry point (what decode_batch calls), copies inside the timed region
+    Yh = pinned_empty((B, tab.n), np.float32)
+    Yh[...] = y.cpu().numpy()
+    xh, ith, rsh = pinned_empty((B, tab.n), np.uint8), pinned_empty((B,), np.int32), pinned_empty((B,), np.uint8)
+
+    def e2e_step():
+        eng.decode_host(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, Yh, max_iter=MAX_ITER, x_hat=xh, iters=ith, reason=rsh)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e_launch0 = eng.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e_el = time.perf_counter() - t0
+    e_launches = eng.launch_count - e_launch0
+    if dist is not None:
+        t = torch.tensor([e_el], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_el = float(t.item())
+    assert (ith == iters).all() and bool((torch.from_numpy(xh).cuda() == x_hat).all()), "e2e result differs from device path"
+    e2e = {"value": total_frames / e_el, "unit": UNIT, "h2d_bytes_per_step": int(Yh.nbytes),
+           "d2h_bytes_per_step": int(xh.nbytes + ith.nbytes + rsh.nbytes), "ms_per_step": 1e3 * e_el / args.steps,
+           "api": "Engine.decode_host -> ldpc_decode_host (pinned float32 y in; x_hat, iters, reason out)",
+           "timer": "host perf_counter around blocking calls, max over ranks"}
+
+    clocks = sampler.stop() if sampler is not None else None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(B, world),
+            "edge_updates_per_s": edge_updates, "mean_iters": it_sum / B, "wer": wer,
+            "roofline": roofline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches), "gpu_launches_e2e": int(e_launches),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, done, el, mean_it = oracle_rate(tables, SNR_DB, max(2048, 64 * threads), 10.0, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d frames of the same workload in %.1f s, oracle/ldpc_oracle.c float32 "
+                                              "min-sum on %d threads (mean %.2f iterations)" % (done, el, threads, mean_it)}
+            r1, d1, e1, _ = oracle_rate(tables, SNR_DB, 512, 3.0, 1)
+            line["cpu_baseline"]["single_thread_value"] = r1
+        if world == 1 and not args.no_extras:
+            try:
+                line["extra"] = extra_workloads(torch, lib, eng_mod, Tables, peak)
+            except Exception as exc:        # side measurements must not lose the headline line
+                line["extra_error"] = repr(exc)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

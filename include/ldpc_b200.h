@@ -124,6 +124,16 @@ int ldpc_decode(ldpc_t *h, int algo, int dtype,
                 uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *marg_out,
                 void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
 
+/* Same as ldpc_decode, with the channel front end fused into the load: `y` is the RECEIVED block on
+ * the device ([B,n] row-major; uint8 for BSC / BEC, y_dtype F32 | F64 for BIAWGN / PRIORS) and the
+ * LLR map of the reference's adapters (src/bsc.py:25, src/biawgn.py:28, src/bec.py:85) is applied while
+ * it is transposed into the kernels' layout.  channel = LDPC_CH_*, param = llr (BSC) / noise_var
+ * (BIAWGN).  BSC uses y as the hard input of the iteration-0 syndrome test. */
+int ldpc_decode_channel(ldpc_t *h, int channel, int algo, int dtype, double param,
+                        const void *y, int y_dtype, int B, int max_iter, int iter_cap,
+                        uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *marg_out,
+                        void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
+
 /* Channel LLR front ends on device buffers (elementwise, any shape, `count` elements).
  *   BSC:    y uint8 {0,1}             -> priors(dtype) = llr * (1 - 2y)       src/bsc.py:25
  *   BIAWGN: y of y_dtype (F32 | F64)  -> priors(dtype) = (-2 y) / noise_var   src/biawgn.py:28
@@ -155,6 +165,14 @@ int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
                      const void *y, int y_dtype, int B, int max_iter, int iter_cap,
                      uint8_t *x_hat, int32_t *iters, uint8_t *reason,
                      int chunk, unsigned flags);
+
+/* Per-launch timing of the two sweeps, for bench.py's roofline.  While enabled, ldpc_decode records CUDA
+ * events around every check-node and variable-node sweep launch on the stream it runs on;
+ * ldpc_profile_read waits for them and returns the accumulated milliseconds and launch counts
+ * since the previous read (kind 0 = check-node sweep, 1 = variable-node sweep). */
+int ldpc_profile_enable(ldpc_t *h, int on);
+int ldpc_profile_read(ldpc_t *h, double *cn_ms, unsigned long long *cn_launches,
+                      double *vn_ms, unsigned long long *vn_launches);
 
 /* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
 unsigned long long ldpc_launch_count(const ldpc_t *h);

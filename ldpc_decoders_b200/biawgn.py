@@ -1,0 +1,55 @@
+"""BIAWGN channel and decoder adapters — GPU drop-ins for /root/reference/src/biawgn.py:10-42."""
+import numpy as np
+
+from . import _lib, bpa
+
+noise_var = lambda snr_in_db: 10 ** (-snr_in_db / 10)      # src/biawgn.py:10
+
+
+class Channel:
+    """biawgn.Channel (src/biawgn.py:13-18): {0,1} -> {-1,+1} plus N(0, sigma^2), legacy global numpy RNG."""
+
+    def __init__(self, snr_in_db):
+        self.std_dev = np.sqrt(noise_var(snr_in_db))
+
+    def send(self, x):
+        return (2 * x - 1) + np.random.normal(0, self.std_dev, x.shape)
+
+
+class LLR:
+    """biawgn.LLR (src/biawgn.py:21-28): priors = -2 y / noise_var."""
+
+    def __init__(self, snr_in_db, dec, dtype=None):
+        self.noise_var, self.dec = noise_var(snr_in_db), dec
+        self.dtype = np.dtype(np.float64 if dtype is None else dtype)
+        self.stats = self.dec.stats
+
+    def decode(self, y):
+        y = np.asarray(y)
+        return self.dec.decode(y, (-2 * y / self.noise_var).astype(self.dtype, copy=False))
+
+    def decode_batch(self, Y, return_reason=False):
+        """Y [B,n] float64 or float32 received values; priors = dtype((-2 * float64(y)) / noise_var) on the GPU."""
+        Y = np.ascontiguousarray(Y)
+        if Y.dtype not in (np.float32, np.float64):
+            Y = Y.astype(np.float64)
+        dt = _lib.F32 if self.dtype == np.float32 else _lib.F64
+        x_hat, iters, reason = self.dec.engine.decode_host(_lib.CH_BIAWGN, self.dec._algo, dt, self.noise_var, Y,
+                                                           max_iter=self.dec.max_iter, iter_cap=self.dec.iter_cap)
+        self.dec._count(iters)
+        x_hat = x_hat.astype(np.int64)
+        return (x_hat, iters, reason) if return_reason else (x_hat, iters)
+
+
+class SPA(LLR):
+    id_keys = bpa.SPA.id_keys
+
+    def __init__(self, snr_in_db, _code, **kwargs):
+        super().__init__(snr_in_db, bpa.SPA(_code, **kwargs), kwargs.get('dtype'))
+
+
+class MSA(LLR):
+    id_keys = bpa.MSA.id_keys
+
+    def __init__(self, snr_in_db, _code, **kwargs):
+        super().__init__(snr_in_db, bpa.MSA(_code, **kwargs), kwargs.get('dtype'))

@@ -1,0 +1,113 @@
+// common.cuh — handle, launch bookkeeping, 128-bit frame packs, flag-word helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ldpc_b200.h"
+#include "ldpc_math.cuh"
+
+namespace ldpc {
+
+constexpr int kCtaWarps = 8;                 // CN / VN sweeps: 8 warps = 8 frame groups per CTA
+constexpr int kCtaThreads = kCtaWarps * 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Device copies of the graph tables (edge order = np.where(H), /root/reference/src/bpa.py:12).
+struct Tables {
+    int n = 0, m = 0, E = 0;
+    int *chk_ptr = nullptr, *edge_var = nullptr, *var_ptr = nullptr, *var_edges = nullptr;
+    int max_dc = 0, max_dv = 0;
+    int uni_dc = 0, uni_dv = 0;              // > 0: every check / variable has exactly this degree
+};
+
+}  // namespace ldpc
+
+struct HostStage;                            // ldpc_decode_host staging (api file)
+
+struct ProfEvent {                           // one timed launch (ldpc_profile_*)
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    int kind = 0;                            // 0 = check-node sweep, 1 = variable-node sweep
+};
+
+struct ldpc_handle {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    ldpc::Tables t;
+    std::string err;
+    unsigned long long launches = 0;
+    HostStage *stage = nullptr;
+    bool prof = false;
+    std::vector<ProfEvent> prof_ev;
+    size_t prof_used = 0;
+};
+
+namespace ldpc {
+
+// ---- 16-byte pack of FPT consecutive frames (4 x f32 or 2 x f64): one 128-bit load / store per edge row ----
+template <typename T, int FPT> struct alignas(16) Pack {
+    T x[FPT];
+};
+
+template <typename P> __device__ __forceinline__ P ld_stream(const void *ptr)       // read once: evict-first
+{
+    static_assert(sizeof(P) == 16, "pack must be 128 bits");
+    const uint4 r = __ldcs(reinterpret_cast<const uint4 *>(ptr));
+    P out;
+    *reinterpret_cast<uint4 *>(&out) = r;
+    return out;
+}
+template <typename P> __device__ __forceinline__ P ld_ro(const void *ptr)           // read-only path (priors)
+{
+    static_assert(sizeof(P) == 16, "pack must be 128 bits");
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(ptr));
+    P out;
+    *reinterpret_cast<uint4 *>(&out) = r;
+    return out;
+}
+template <typename P> __device__ __forceinline__ void st_stream(void *ptr, const P &v)
+{
+    static_assert(sizeof(P) == 16, "pack must be 128 bits");
+    __stcs(reinterpret_cast<uint4 *>(ptr), *reinterpret_cast<const uint4 *>(&v));
+}
+
+// Frame flags are bit-packed naturally: bit l of word w <-> frame 32*w + l.  A thread that owns FPT
+// consecutive frames owns an FPT-bit field of one word; 32/FPT adjacent lanes share that word.
+template <int FPT> struct Field {
+    static constexpr int LPW = 32 / FPT;                 // lanes per word
+    static constexpr uint32_t MASK = (1u << FPT) - 1u;
+    static __device__ __forceinline__ int word_of(int group, int lane) { return group * FPT + lane / LPW; }
+    static __device__ __forceinline__ int shift_of(int lane) { return (lane % LPW) * FPT; }
+    static __device__ __forceinline__ uint32_t get(uint32_t word, int lane) { return (word >> shift_of(lane)) & MASK; }
+    // OR the fields of the LPW lanes that share a word; every one of them gets the assembled word.
+    static __device__ __forceinline__ uint32_t assemble(uint32_t field, int lane)
+    {
+        uint32_t w = field << shift_of(lane);
+#pragma unroll
+        for (int d = 1; d < LPW; d <<= 1) w |= __shfl_xor_sync(kFull, w, d);
+        return w;
+    }
+    static __device__ __forceinline__ bool leader(int lane) { return (lane % LPW) == 0; }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *p) : base(static_cast<char *>(p)) {}
+    template <typename U> U *take(size_t count)
+    {
+        off = align_up(off, 256);
+        U *r = reinterpret_cast<U *>(base + off);
+        off += count * sizeof(U);
+        return r;
+    }
+    size_t used() const { return align_up(off, 256); }
+};
+
+}  // namespace ldpc

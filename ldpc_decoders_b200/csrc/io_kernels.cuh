@@ -1,0 +1,180 @@
+// io_kernels.cuh — layout changes at the boundary and the channel LLR front ends.
+//
+// The reference-facing layout is frame-major [B][n] (one numpy row per frame); the kernels want
+// variable-major [n][Bp] with frames contiguous.  These kernels transpose through a 32x32 shared
+// tile (both sides coalesced) and fuse the LLR map of the channel adapters into the load:
+//   BSC     priors = llr * (1 - 2y)            /root/reference/src/bsc.py:25
+//   BIAWGN  priors = (-2 y) / noise_var        /root/reference/src/biawgn.py:28
+//   BEC     messages[y] = [-1, +1, 0][y]       /root/reference/src/bec.py:76,85
+// evaluated in float64 and rounded once to the message type (== reference priors.astype(dtype)).
+#pragma once
+#include "common.cuh"
+
+namespace ldpc {
+
+enum { IN_COPY = 0, IN_BSC = 1, IN_BIAWGN = 2 };
+
+template <typename Tin, typename T, int MODE> __device__ __forceinline__ T llr_map(Tin y, double param)
+{
+    if (MODE == IN_BSC) return (T)(param * (double)(1 - 2 * (int)y));
+    if (MODE == IN_BIAWGN) return (T)((-2.0 * (double)y) / param);
+    return (T)y;
+}
+
+// src [B][n] (frame-major) -> prior [n][Bp]; frames >= B are zero-filled.
+// MODE == IN_BSC additionally packs the hard bits y into xbits [n][wpr].
+// grid (ceil(n/32), Bp/32), block (32, 8).
+template <typename Tin, typename T, int MODE>
+__global__ void ingest_priors(const Tin *__restrict__ src, T *__restrict__ prior, uint32_t *__restrict__ xbits,
+                              int B, int n, int Bp, int wpr, double param)
+{
+    __shared__ T tile[32][33];
+    __shared__ uint8_t hard[32][33];
+    const int v0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int f = f0 + r, v = v0 + threadIdx.x;
+        T val = (T)0;
+        uint8_t hb = 0;
+        if (f < B && v < n) {
+            const Tin y = src[(size_t)f * n + v];
+            val = llr_map<Tin, T, MODE>(y, param);
+            if (MODE == IN_BSC) hb = (uint8_t)(y != (Tin)0);
+        }
+        tile[r][threadIdx.x] = val;
+        if (MODE == IN_BSC) hard[r][threadIdx.x] = hb;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int v = v0 + r, f = f0 + threadIdx.x;
+        if (v < n) {                                                 // warp-uniform
+            prior[(size_t)v * Bp + f] = tile[threadIdx.x][r];
+            if (MODE == IN_BSC) {
+                const uint32_t w = __ballot_sync(kFull, hard[threadIdx.x][r] != 0);
+                if (threadIdx.x == 0) xbits[(size_t)v * wpr + (f0 >> 5)] = w;
+            }
+        }
+    }
+}
+
+// y_hard [B][n] uint8 -> xbits [n][wpr]   (the x_hat = y of src/bpa.py:20)
+__global__ void pack_hard(const uint8_t *__restrict__ y, uint32_t *__restrict__ xbits, int B, int n, int wpr)
+{
+    __shared__ uint8_t hard[32][33];
+    const int v0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int f = f0 + r, v = v0 + threadIdx.x;
+        hard[r][threadIdx.x] = (f < B && v < n) ? (uint8_t)(y[(size_t)f * n + v] != 0) : (uint8_t)0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int v = v0 + r;
+        if (v < n) {
+            const uint32_t w = __ballot_sync(kFull, hard[threadIdx.x][r] != 0);
+            if (threadIdx.x == 0) xbits[(size_t)v * wpr + (f0 >> 5)] = w;
+        }
+    }
+}
+
+// BEC symbols [B][n] uint8 {0,1,2} -> prior planes, x_hat planes and the per-frame "has erasures" flag.
+__global__ void ingest_bec(const uint8_t *__restrict__ y, uint32_t *__restrict__ pnz, uint32_t *__restrict__ ppos,
+                           uint32_t *__restrict__ xe, uint32_t *__restrict__ xv, uint32_t *__restrict__ haser,
+                           int B, int n, int wpr)
+{
+    __shared__ uint8_t sym[32][33];
+    const int v0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int f = f0 + r, v = v0 + threadIdx.x;
+        sym[r][threadIdx.x] = (f < B && v < n) ? y[(size_t)f * n + v] : (uint8_t)0;
+    }
+    __syncthreads();
+    const bool valid = (f0 + (int)threadIdx.x) < B;
+    uint32_t er_any = 0u;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int v = v0 + r;
+        if (v < n) {
+            const uint8_t s = sym[threadIdx.x][r];
+            const uint32_t e = __ballot_sync(kFull, valid && s >= 2);
+            const uint32_t one = __ballot_sync(kFull, valid && s == 1);
+            const uint32_t ok = __ballot_sync(kFull, valid);
+            if (threadIdx.x == 0) {
+                const size_t i = (size_t)v * wpr + (f0 >> 5);
+                pnz[i] = ok & ~e; ppos[i] = one;
+                xe[i] = e; xv[i] = one;
+            }
+            er_any |= e;
+        }
+    }
+    if (threadIdx.x == 0 && er_any != 0u) atomicOr(haser + (f0 >> 5), er_any);
+}
+
+// act = frames < B; unsat = act (iteration-0 syndrome skipped) or 0; iters = 0.
+__global__ void init_flags(uint32_t *act, uint32_t *unsat, int *iters, int B, int Bp, int wpr, int unsat_all)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Bp) iters[i] = 0;
+    if (i < wpr) {
+        const int lo = i * 32;
+        const uint32_t m = (B >= lo + 32) ? 0xffffffffu : (B <= lo ? 0u : ((1u << (B - lo)) - 1u));
+        act[i] = m;
+        if (unsat != nullptr) unsat[i] = unsat_all ? m : 0u;
+    }
+}
+
+// xbits [n][wpr] (and, for BEC, the erased plane) -> x_hat [B][n] uint8.  grid (ceil(n/32), wpr), block (32, 8).
+__global__ void emit_words(const uint32_t *__restrict__ xval, const uint32_t *__restrict__ xer,
+                           uint8_t *__restrict__ x_hat, int B, int n, int wpr)
+{
+    const int v = blockIdx.x * 32 + threadIdx.x, w = blockIdx.y;
+    uint32_t val = 0u, er = 0u;
+    if (v < n) {
+        val = xval[(size_t)v * wpr + w];
+        if (xer != nullptr) er = xer[(size_t)v * wpr + w];
+    }
+    for (int l = threadIdx.y; l < 32; l += 8) {
+        const int f = w * 32 + l;
+        if (f < B && v < n) x_hat[(size_t)f * n + v] = ((er >> l) & 1u) ? (uint8_t)2 : (uint8_t)((val >> l) & 1u);
+    }
+}
+
+// iters / exit reason per frame.  still-active frames hit the loop bound: MAXIMUM (or CAP when unlimited).
+__global__ void emit_status(const int *__restrict__ iters_ws, const uint32_t *__restrict__ act,
+                            const uint32_t *__restrict__ stopped, int *__restrict__ iters, uint8_t *__restrict__ reason,
+                            int B, int bound_reason)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= B) return;
+    iters[f] = iters_ws[f];
+    if (reason != nullptr) {
+        uint8_t r = LDPC_REASON_DECODED;
+        if (stopped != nullptr && ((stopped[f >> 5] >> (f & 31)) & 1u)) r = LDPC_REASON_STOPPING;
+        else if ((act[f >> 5] >> (f & 31)) & 1u) r = (uint8_t)bound_reason;
+        reason[f] = r;
+    }
+}
+
+// Plain tiled transposes (debug step, marginals): a [R][C] row-major -> b [C][ldb] row-major.
+template <typename T>
+__global__ void transpose_tile(const T *__restrict__ a, T *__restrict__ b, int R, int C, int lda, int ldb)
+{
+    __shared__ T tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int rr = r0 + r, cc = c0 + threadIdx.x;
+        tile[r][threadIdx.x] = (rr < R && cc < C) ? a[(size_t)rr * lda + cc] : (T)0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int cc = c0 + r, rr = r0 + threadIdx.x;
+        if (cc < C && rr < R) b[(size_t)cc * ldb + rr] = tile[threadIdx.x][r];
+    }
+}
+
+// Elementwise LLR front ends on flat buffers (ldpc_llr_bsc / ldpc_llr_biawgn).
+template <typename Tin, typename T, int MODE>
+__global__ void llr_flat(const Tin *__restrict__ y, T *__restrict__ out, size_t count, double param)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = llr_map<Tin, T, MODE>(y[i], param);
+}
+
+}  // namespace ldpc

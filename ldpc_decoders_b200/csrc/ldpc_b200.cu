@@ -1,0 +1,829 @@
+// ldpc_b200.cu — C ABI of libldpc_b200.so (see include/ldpc_b200.h) and the host-side
+// orchestration of the decode: ingest -> [cn_sweep, book, vn_sweep] x iterations -> emit.
+// Built for sm_100a only; there is no CPU path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "io_kernels.cuh"
+#include "stream_bec.cuh"
+#include "stream_bp.cuh"
+
+using namespace ldpc;
+
+namespace {
+
+std::string g_create_error;
+
+int fail(ldpc_t *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                           \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail((h), LDPC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+#define LAUNCH(h, kern, grid, block, stream, ...)                                                   \
+    do {                                                                                            \
+        kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                        \
+        (h)->launches++;                                                                            \
+    } while (0)
+
+int check_launch(ldpc_t *h, const char *what)
+{
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(h, LDPC_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return LDPC_OK;
+}
+
+// Optional per-launch timing of the two sweeps (bench.py's roofline): events on the launching stream.
+ProfEvent *prof_begin(ldpc_t *h, int kind, cudaStream_t s)
+{
+    if (!h->prof) return nullptr;
+    if (h->prof_used == h->prof_ev.size()) {
+        ProfEvent ev;
+        if (cudaEventCreate(&ev.t0) != cudaSuccess || cudaEventCreate(&ev.t1) != cudaSuccess) return nullptr;
+        h->prof_ev.push_back(ev);
+    }
+    ProfEvent *ev = &h->prof_ev[h->prof_used++];
+    ev->kind = kind;
+    cudaEventRecord(ev->t0, s);
+    return ev;
+}
+void prof_end(ProfEvent *ev, cudaStream_t s)
+{
+    if (ev) cudaEventRecord(ev->t1, s);
+}
+
+template <typename T> struct Fpt;
+template <> struct Fpt<float> { static constexpr int value = 4; };
+template <> struct Fpt<double> { static constexpr int value = 2; };
+
+inline int frames_per_group(int dtype) { return dtype == LDPC_F64 ? 64 : 128; }
+inline size_t elem_size(int dtype) { return dtype == LDPC_F64 ? 8 : 4; }
+
+// Grid for a sweep: x = frame tiles of 8 groups, y = chunks of checks / variables, >= ~16 CTAs per SM.
+dim3 sweep_grid(const ldpc_t *h, int ngroups, int items, int *per_cta)
+{
+    const int gx = (ngroups + kCtaWarps - 1) / kCtaWarps;
+    const int target = h->sm_count * 16;
+    int gy = std::max(1, std::min(items, target / std::max(1, gx)));
+    gy = std::min(gy, 65535);
+    int per = (items + gy - 1) / gy;
+    gy = (items + per - 1) / per;
+    *per_cta = per;
+    return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace layouts
+// ------------------------------------------------------------------------------------------------
+struct BpLayout {
+    int Bp, wpr, ngroups;
+    size_t bytes;
+};
+
+BpLayout bp_layout(const Tables &t, int dtype, int B, bool want_marg)
+{
+    BpLayout L;
+    const int G = frames_per_group(dtype);
+    L.Bp = (B + G - 1) / G * G;
+    L.wpr = L.Bp / 32;
+    L.ngroups = L.Bp / G;
+    const size_t es = elem_size(dtype);
+    size_t b = 0;
+    b += align_up((size_t)t.E * L.Bp * es, 256);                // msg
+    b += align_up((size_t)t.n * L.Bp * es, 256);                // prior
+    if (want_marg) b += align_up((size_t)t.n * L.Bp * es, 256); // marg
+    b += align_up((size_t)t.n * L.wpr * 4, 256);                // xbits
+    b += 2 * align_up((size_t)L.wpr * 4, 256);                  // act, unsat
+    b += align_up((size_t)L.Bp * 4, 256);                       // iters
+    b += 256;                                                   // any_active
+    L.bytes = b + 256;
+    return L;
+}
+
+struct BecLayout {
+    int Bp, wpr;
+    size_t bytes;
+};
+
+BecLayout bec_layout(const Tables &t, int B)
+{
+    BecLayout L;
+    L.Bp = (B + 31) / 32 * 32;
+    L.wpr = L.Bp / 32;
+    size_t b = 0;
+    b += 2 * align_up((size_t)t.E * L.wpr * 4, 256);            // mnz, mpos
+    b += 4 * align_up((size_t)t.n * L.wpr * 4, 256);            // pnz, ppos, xe, xv
+    b += 4 * align_up((size_t)L.wpr * 4, 256);                  // act, changed, haser, stopped
+    b += align_up((size_t)L.Bp * 4, 256);                       // iters
+    b += 256;
+    L.bytes = b + 256;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch by degree profile
+// ------------------------------------------------------------------------------------------------
+template <typename T, int ALGO>
+int launch_cn(ldpc_t *h, const BpParams<T> &p, dim3 grid, cudaStream_t s)
+{
+    constexpr int FPT = Fpt<T>::value;
+    const Tables &t = h->t;
+#define CN_CASE(DC, UNI) LAUNCH(h, (cn_sweep<T, FPT, ALGO, DC, UNI>), grid, kCtaThreads, s, p)
+    if (t.uni_dc == 4) CN_CASE(4, true);
+    else if (t.uni_dc == 6) CN_CASE(6, true);
+    else if (t.uni_dc == 8) CN_CASE(8, true);
+    else if (t.max_dc <= 8) CN_CASE(8, false);
+    else if (t.max_dc <= 16) CN_CASE(16, false);
+    else if (t.max_dc <= 32) CN_CASE(32, false);
+    else return fail(h, LDPC_EUNSUPPORTED, "check degree > 32 is not supported by the streaming kernels");
+#undef CN_CASE
+    return LDPC_OK;
+}
+
+template <typename T>
+int launch_vn(ldpc_t *h, const BpParams<T> &p, dim3 grid, cudaStream_t s)
+{
+    constexpr int FPT = Fpt<T>::value;
+    const Tables &t = h->t;
+#define VN_CASE(DV, UNI) LAUNCH(h, (vn_sweep<T, FPT, DV, UNI>), grid, kCtaThreads, s, p)
+    if (t.uni_dv == 3) VN_CASE(3, true);
+    else if (t.uni_dv == 4) VN_CASE(4, true);
+    else if (t.max_dv <= 4) VN_CASE(4, false);
+    else if (t.max_dv <= 8) VN_CASE(8, false);
+    else if (t.max_dv <= 16) VN_CASE(16, false);
+    else if (t.max_dv <= 32) VN_CASE(32, false);
+    else return fail(h, LDPC_EUNSUPPORTED, "variable degree > 32 is not supported by the streaming kernels");
+#undef VN_CASE
+    return LDPC_OK;
+}
+
+template <typename T>
+int launch_cn_algo(ldpc_t *h, int algo, const BpParams<T> &p, dim3 grid, cudaStream_t s);
+template <>
+int launch_cn_algo<float>(ldpc_t *h, int algo, const BpParams<float> &p, dim3 grid, cudaStream_t s)
+{
+    return algo == LDPC_MSA ? launch_cn<float, ALGO_MSA>(h, p, grid, s) : launch_cn<float, ALGO_SPA_PHI>(h, p, grid, s);
+}
+template <>
+int launch_cn_algo<double>(ldpc_t *h, int algo, const BpParams<double> &p, dim3 grid, cudaStream_t s)
+{
+    return algo == LDPC_MSA ? launch_cn<double, ALGO_MSA>(h, p, grid, s) : launch_cn<double, ALGO_SPA_REF>(h, p, grid, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// input description shared by ldpc_decode and ldpc_decode_host
+// ------------------------------------------------------------------------------------------------
+struct InSpec {
+    int channel;            // LDPC_CH_*
+    int in_dtype;           // element type of src for PRIORS / BIAWGN
+    const void *src;        // device [B][n]
+    const uint8_t *y_hard;  // device [B][n] or NULL (PRIORS only)
+    double param;
+};
+
+template <typename T>
+int ingest_bp(ldpc_t *h, const InSpec &in, T *prior, uint32_t *xbits, int B, const BpLayout &L, cudaStream_t s,
+              bool *have_hard)
+{
+    const Tables &t = h->t;
+    const dim3 grid((t.n + 31) / 32, L.Bp / 32), block(32, 8);
+    *have_hard = false;
+    switch (in.channel) {
+    case LDPC_CH_PRIORS:
+        if (in.in_dtype == LDPC_F64)
+            LAUNCH(h, (ingest_priors<double, T, IN_COPY>), grid, block, s, (const double *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, 0.0);
+        else
+            LAUNCH(h, (ingest_priors<float, T, IN_COPY>), grid, block, s, (const float *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, 0.0);
+        if (in.y_hard) {
+            LAUNCH(h, pack_hard, grid, block, s, in.y_hard, xbits, B, t.n, L.wpr);
+            *have_hard = true;
+        }
+        break;
+    case LDPC_CH_BSC:
+        LAUNCH(h, (ingest_priors<uint8_t, T, IN_BSC>), grid, block, s, (const uint8_t *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, in.param);
+        *have_hard = true;
+        break;
+    case LDPC_CH_BIAWGN:
+        if (in.in_dtype == LDPC_F64)
+            LAUNCH(h, (ingest_priors<double, T, IN_BIAWGN>), grid, block, s, (const double *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, in.param);
+        else
+            LAUNCH(h, (ingest_priors<float, T, IN_BIAWGN>), grid, block, s, (const float *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, in.param);
+        break;
+    default:
+        return fail(h, LDPC_EINVAL, "bad channel for MSA/SPA");
+    }
+    if (!*have_hard) {
+        cudaError_t e = cudaMemsetAsync(xbits, 0, (size_t)t.n * L.wpr * 4, s);
+        if (e != cudaSuccess) return fail(h, LDPC_ECUDA, std::string("memset xbits: ") + cudaGetErrorString(e));
+    }
+    return check_launch(h, "ingest");
+}
+
+struct PollState {
+    int *d_flag;            // device
+    int *h_flag;            // pinned host
+};
+
+int poll_any_active(ldpc_t *h, const PollState &ps, cudaStream_t s, bool *active)
+{
+    CUDA_TRY(h, cudaMemcpyAsync(ps.h_flag, ps.d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    *active = (*ps.h_flag != 0);
+    return LDPC_OK;
+}
+
+}  // namespace
+
+struct HostSlot {
+    cudaStream_t stream = nullptr;
+    void *d_y = nullptr; size_t y_bytes = 0;
+    uint8_t *d_x = nullptr; size_t x_bytes = 0;
+    int32_t *d_it = nullptr; uint8_t *d_rs = nullptr; size_t f_cap = 0;
+    void *ws = nullptr; size_t ws_bytes = 0;
+};
+
+struct HostStage {
+    static constexpr int kSlots = 3;
+    HostSlot slot[kSlots];
+    int *h_flag = nullptr;      // pinned, used by the unlimited-iteration poll
+};
+
+namespace {
+
+int ensure_stage(ldpc_t *h)
+{
+    if (h->stage) return LDPC_OK;
+    HostStage *st = new (std::nothrow) HostStage();
+    if (!st) return fail(h, LDPC_ENOMEM, "host stage");
+    for (auto &sl : st->slot) {
+        cudaError_t e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete st; return fail(h, LDPC_ECUDA, std::string("stream create: ") + cudaGetErrorString(e)); }
+    }
+    cudaError_t e = cudaMallocHost((void **)&st->h_flag, 64);
+    if (e != cudaSuccess) { delete st; return fail(h, LDPC_ECUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
+    h->stage = st;
+    return LDPC_OK;
+}
+
+template <typename U> int grow(ldpc_t *h, U **ptr, size_t *cap, size_t need)
+{
+    if (*cap >= need) return LDPC_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc((void **)ptr, need);
+    if (e != cudaSuccess) return fail(h, LDPC_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    *cap = need;
+    return LDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming BP decode
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int decode_bp_stream(ldpc_t *h, int algo, const InSpec &in, int B, int max_iter, int iter_cap,
+                     uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *marg_out,
+                     void *ws, size_t ws_bytes, cudaStream_t s)
+{
+    const Tables &t = h->t;
+    const int dtype = sizeof(T) == 8 ? LDPC_F64 : LDPC_F32;
+    const BpLayout L = bp_layout(t, dtype, B, marg_out != nullptr);
+    if (ws_bytes < L.bytes) return fail(h, LDPC_EWORKSPACE, "workspace too small");
+    if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0) return fail(h, LDPC_EWORKSPACE, "workspace must be 256-byte aligned");
+    const int limit = max_iter > 0 ? max_iter : iter_cap;
+    if (limit <= 0) return fail(h, LDPC_EINVAL, "max_iter <= 0 (unlimited in the reference) needs iter_cap > 0");
+
+    Carver cv(ws);
+    BpParams<T> p;
+    p.n = t.n; p.m = t.m; p.E = t.E;
+    p.Bp = L.Bp; p.wpr = L.wpr; p.ngroups = L.ngroups;
+    p.chk_ptr = t.chk_ptr; p.edge_var = t.edge_var; p.var_ptr = t.var_ptr; p.var_edges = t.var_edges;
+    p.msg = cv.take<T>((size_t)t.E * L.Bp);
+    T *prior = cv.take<T>((size_t)t.n * L.Bp);
+    p.prior = prior;
+    p.marg = marg_out ? cv.take<T>((size_t)t.n * L.Bp) : nullptr;
+    p.xbits = cv.take<uint32_t>((size_t)t.n * L.wpr);
+    p.act = cv.take<uint32_t>(L.wpr);
+    p.unsat = cv.take<uint32_t>(L.wpr);
+    p.iters = cv.take<int>(L.Bp);
+    int *any_active = cv.take<int>(1);
+
+    bool have_hard = false;
+    int rc = ingest_bp<T>(h, in, prior, p.xbits, B, L, s, &have_hard);
+    if (rc) return rc;
+    if (p.marg) {                                                   // a frame that never runs reports marginal = prior
+        CUDA_TRY(h, cudaMemcpyAsync(p.marg, prior, (size_t)t.n * L.Bp * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    }
+    LAUNCH(h, init_flags, (L.Bp + 255) / 256, 256, s, p.act, p.unsat, p.iters, B, L.Bp, L.wpr, have_hard ? 0 : 1);
+
+    int cpc = 1, vpc = 1;
+    const dim3 cgrid = sweep_grid(h, L.ngroups, t.m, &cpc);
+    const dim3 vgrid = sweep_grid(h, L.ngroups, t.n, &vpc);
+    const int book_blocks = (L.wpr * 32 + 255) / 256;
+    const bool poll = (max_iter <= 0) || (limit > 32);
+    PollState ps{any_active, nullptr};
+    if (poll) {
+        rc = ensure_stage(h);
+        if (rc) return rc;
+        ps.h_flag = h->stage->h_flag;
+    }
+
+    for (int it = 0; it < limit; ++it) {
+        p.first = (it == 0);
+        p.skip_syn = (it == 0 && !have_hard);
+        p.per_cta = cpc;
+        ProfEvent *pe = prof_begin(h, 0, s);
+        rc = launch_cn_algo<T>(h, algo, p, cgrid, s);
+        prof_end(pe, s);
+        if (rc) return rc;
+        const bool poll_now = poll && it >= 8 && (it % 8) == 0;
+        if (poll_now) CUDA_TRY(h, cudaMemsetAsync(any_active, 0, sizeof(int), s));
+        LAUNCH(h, bp_book, book_blocks, 256, s, p.act, p.unsat, p.iters, L.wpr, any_active);
+        if (poll_now) {
+            bool active = true;
+            rc = poll_any_active(h, ps, s, &active);
+            if (rc) return rc;
+            if (!active) break;
+        }
+        p.per_cta = vpc;
+        pe = prof_begin(h, 1, s);
+        rc = launch_vn<T>(h, p, vgrid, s);
+        prof_end(pe, s);
+        if (rc) return rc;
+    }
+
+    const dim3 egrid((t.n + 31) / 32, L.wpr), eblock(32, 8);
+    LAUNCH(h, emit_words, egrid, eblock, s, p.xbits, (const uint32_t *)nullptr, x_hat, B, t.n, L.wpr);
+    LAUNCH(h, emit_status, (B + 255) / 256, 256, s, p.iters, p.act, (const uint32_t *)nullptr, iters, reason, B,
+           max_iter > 0 ? LDPC_REASON_MAXIMUM : LDPC_REASON_CAP);
+    if (marg_out) {
+        const dim3 tgrid((B + 31) / 32, (t.n + 31) / 32);
+        LAUNCH(h, (transpose_tile<T>), tgrid, eblock, s, p.marg, (T *)marg_out, t.n, B, L.Bp, t.n);
+    }
+    return check_launch(h, "decode_bp_stream");
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming BEC decode
+// ------------------------------------------------------------------------------------------------
+int decode_bec_stream(ldpc_t *h, const uint8_t *y, int B, int max_iter, int iter_cap,
+                      uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *ws, size_t ws_bytes, cudaStream_t s)
+{
+    const Tables &t = h->t;
+    const BecLayout L = bec_layout(t, B);
+    if (ws_bytes < L.bytes) return fail(h, LDPC_EWORKSPACE, "workspace too small");
+    if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0) return fail(h, LDPC_EWORKSPACE, "workspace must be 256-byte aligned");
+    if (t.max_dv > 126) return fail(h, LDPC_EUNSUPPORTED, "variable degree > 126 is not supported by the BEC kernels");
+    // Peeling ends by itself ('decoded' or 'stopping') after at most n rounds; that bounds "unlimited".
+    const int limit = max_iter > 0 ? max_iter : (iter_cap > 0 ? iter_cap : t.n + 1);
+
+    Carver cv(ws);
+    BecParams p;
+    p.n = t.n; p.m = t.m; p.E = t.E; p.wpr = L.wpr;
+    p.chk_ptr = t.chk_ptr; p.edge_var = t.edge_var; p.var_ptr = t.var_ptr; p.var_edges = t.var_edges;
+    p.mnz = cv.take<uint32_t>((size_t)t.E * L.wpr);
+    p.mpos = cv.take<uint32_t>((size_t)t.E * L.wpr);
+    uint32_t *pnz = cv.take<uint32_t>((size_t)t.n * L.wpr);
+    uint32_t *ppos = cv.take<uint32_t>((size_t)t.n * L.wpr);
+    p.pnz = pnz; p.ppos = ppos;
+    p.xe = cv.take<uint32_t>((size_t)t.n * L.wpr);
+    p.xv = cv.take<uint32_t>((size_t)t.n * L.wpr);
+    p.act = cv.take<uint32_t>(L.wpr);
+    p.changed = cv.take<uint32_t>(L.wpr);
+    p.haser = cv.take<uint32_t>(L.wpr);
+    p.stopped = cv.take<uint32_t>(L.wpr);
+    p.iters = cv.take<int>(L.Bp);
+    int *any_active = cv.take<int>(1);
+
+    CUDA_TRY(h, cudaMemsetAsync(p.changed, 0, (size_t)((char *)p.iters - (char *)p.changed), s));   // changed, haser, stopped
+    const dim3 igrid((t.n + 31) / 32, L.wpr), iblock(32, 8);
+    LAUNCH(h, ingest_bec, igrid, iblock, s, y, pnz, ppos, p.xe, p.xv, p.haser, B, t.n, L.wpr);
+    LAUNCH(h, init_flags, (L.Bp + 255) / 256, 256, s, p.act, (uint32_t *)nullptr, p.iters, B, L.Bp, L.wpr, 0);
+
+    const int gx = (L.wpr + 127) / 128;
+    const int target = h->sm_count * 32;
+    auto grid_for = [&](int items, int *per) {
+        int gy = std::max(1, std::min(items, target / gx));
+        gy = std::min(gy, 65535);
+        *per = (items + gy - 1) / gy;
+        gy = (items + *per - 1) / *per;
+        return dim3((unsigned)gx, (unsigned)gy, 1);
+    };
+    int cpc = 1, vpc = 1;
+    const dim3 cgrid = grid_for(t.m, &cpc), vgrid = grid_for(t.n, &vpc);
+    const int book_blocks = (L.wpr * 32 + 255) / 256;
+    const bool poll = (max_iter <= 0) || (limit > 32);
+    PollState ps{any_active, nullptr};
+    if (poll) {
+        int rc = ensure_stage(h);
+        if (rc) return rc;
+        ps.h_flag = h->stage->h_flag;
+    }
+
+    int it = 0;
+    for (; it < limit; ++it) {
+        const bool poll_now = poll && it >= 8 && (it % 8) == 0;
+        if (poll_now) CUDA_TRY(h, cudaMemsetAsync(any_active, 0, sizeof(int), s));
+        LAUNCH(h, bec_book, book_blocks, 256, s, p.act, p.changed, p.haser, p.stopped, p.iters, L.wpr, it == 0 ? 1 : 0, 0, any_active);
+        if (poll_now) {
+            bool active = true;
+            int rc = poll_any_active(h, ps, s, &active);
+            if (rc) return rc;
+            if (!active) break;
+        }
+        p.first = (it == 0);
+        p.per_cta = cpc;
+        ProfEvent *pe = prof_begin(h, 0, s);
+        LAUNCH(h, bec_cn, cgrid, 128, s, p);
+        prof_end(pe, s);
+        p.per_cta = vpc;
+        pe = prof_begin(h, 1, s);
+        if (t.max_dv <= 14) LAUNCH(h, (bec_vn<5>), vgrid, 128, s, p);
+        else LAUNCH(h, (bec_vn<8>), vgrid, 128, s, p);
+        prof_end(pe, s);
+    }
+    if (it == limit)    // account the last round; frames still active after it hit the bound
+        LAUNCH(h, bec_book, book_blocks, 256, s, p.act, p.changed, p.haser, p.stopped, p.iters, L.wpr, 0, 1, any_active);
+
+    LAUNCH(h, emit_words, igrid, iblock, s, p.xv, p.xe, x_hat, B, t.n, L.wpr);
+    LAUNCH(h, emit_status, (B + 255) / 256, 256, s, p.iters, p.act, p.stopped, iters, reason, B,
+           max_iter > 0 ? LDPC_REASON_MAXIMUM : LDPC_REASON_CAP);
+    return check_launch(h, "decode_bec_stream");
+}
+
+int decode_any(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_iter, int iter_cap,
+               uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *marg_out,
+               void *ws, size_t ws_bytes, unsigned flags, cudaStream_t s)
+{
+    if (!h) return LDPC_EINVAL;
+    if (B <= 0) return fail(h, LDPC_EINVAL, "B must be positive");
+    if (!in.src || !x_hat || !iters || !ws) return fail(h, LDPC_EINVAL, "null buffer");
+    if ((flags & LDPC_PATH_MASK) == LDPC_PATH_RESIDENT)
+        return fail(h, LDPC_EUNSUPPORTED, "resident path is not built into this version");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (algo == LDPC_BEC) {
+        if (in.channel != LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "BEC decoder needs symbol input");
+        if (marg_out) return fail(h, LDPC_EINVAL, "marg_out is MSA/SPA only");
+        return decode_bec_stream(h, (const uint8_t *)in.src, B, max_iter, iter_cap, x_hat, iters, reason, ws, ws_bytes, s);
+    }
+    if (algo != LDPC_MSA && algo != LDPC_SPA) return fail(h, LDPC_EINVAL, "bad algo");
+    if (in.channel == LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "MSA/SPA cannot take BEC symbols");
+    if (dtype == LDPC_F32)
+        return decode_bp_stream<float>(h, algo, in, B, max_iter, iter_cap, x_hat, iters, reason, marg_out, ws, ws_bytes, s);
+    if (dtype == LDPC_F64)
+        return decode_bp_stream<double>(h, algo, in, B, max_iter, iter_cap, x_hat, iters, reason, marg_out, ws, ws_bytes, s);
+    return fail(h, LDPC_EINVAL, "bad dtype");
+}
+
+size_t workspace_bytes_impl(const ldpc_t *h, int algo, int dtype, int B, bool want_marg)
+{
+    if (!h || B <= 0) return 0;
+    if (algo == LDPC_BEC) return bec_layout(h->t, B).bytes;
+    if (algo != LDPC_MSA && algo != LDPC_SPA) return 0;
+    if (dtype != LDPC_F32 && dtype != LDPC_F64) return 0;
+    return bp_layout(h->t, dtype, B, want_marg).bytes;
+}
+
+}  // namespace
+
+// One isolated sweep in the reference layout [B][E] (teacher-forced parity).
+template <typename T>
+static int debug_step_t(ldpc_t *h, int algo, int which, int B, const void *prior_in, const void *msg_in,
+                        void *msg_out, void *marg_out, void *ws, size_t ws_bytes, cudaStream_t s)
+{
+    const Tables &t = h->t;
+    const int dtype = sizeof(T) == 8 ? LDPC_F64 : LDPC_F32;
+    const BpLayout L = bp_layout(t, dtype, B, true);
+    if (ws_bytes < L.bytes) return fail(h, LDPC_EWORKSPACE, "workspace too small");
+    if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0) return fail(h, LDPC_EWORKSPACE, "workspace must be 256-byte aligned");
+    Carver cv(ws);
+    BpParams<T> p;
+    p.n = t.n; p.m = t.m; p.E = t.E;
+    p.Bp = L.Bp; p.wpr = L.wpr; p.ngroups = L.ngroups;
+    p.chk_ptr = t.chk_ptr; p.edge_var = t.edge_var; p.var_ptr = t.var_ptr; p.var_edges = t.var_edges;
+    p.msg = cv.take<T>((size_t)t.E * L.Bp);
+    T *prior = cv.take<T>((size_t)t.n * L.Bp);
+    p.prior = prior;
+    p.marg = cv.take<T>((size_t)t.n * L.Bp);
+    p.xbits = cv.take<uint32_t>((size_t)t.n * L.wpr);
+    p.act = cv.take<uint32_t>(L.wpr);
+    p.unsat = cv.take<uint32_t>(L.wpr);
+    p.iters = cv.take<int>(L.Bp);
+    p.first = 0; p.skip_syn = 1;
+
+    const dim3 block(32, 8);
+    CUDA_TRY(h, cudaMemsetAsync(ws, 0, L.bytes, s));
+    LAUNCH(h, (transpose_tile<T>), dim3((t.E + 31) / 32, (B + 31) / 32), block, s, (const T *)msg_in, p.msg, B, t.E, t.E, L.Bp);
+    LAUNCH(h, init_flags, (L.Bp + 255) / 256, 256, s, p.act, p.unsat, p.iters, B, L.Bp, L.wpr, 1);
+    int rc;
+    if (which == 0) {
+        const dim3 grid = sweep_grid(h, L.ngroups, t.m, &p.per_cta);
+        rc = launch_cn_algo<T>(h, algo, p, grid, s);
+        if (rc) return rc;
+    } else {
+        if (!prior_in) return fail(h, LDPC_EINVAL, "variable-node step needs priors");
+        LAUNCH(h, (transpose_tile<T>), dim3((t.n + 31) / 32, (B + 31) / 32), block, s, (const T *)prior_in, prior, B, t.n, t.n, L.Bp);
+        const dim3 grid = sweep_grid(h, L.ngroups, t.n, &p.per_cta);
+        rc = launch_vn<T>(h, p, grid, s);
+        if (rc) return rc;
+        if (marg_out)
+            LAUNCH(h, (transpose_tile<T>), dim3((B + 31) / 32, (t.n + 31) / 32), block, s, p.marg, (T *)marg_out, t.n, B, L.Bp, t.n);
+    }
+    LAUNCH(h, (transpose_tile<T>), dim3((B + 31) / 32, (t.E + 31) / 32), block, s, p.msg, (T *)msg_out, t.E, B, L.Bp, t.E);
+    return check_launch(h, "debug_step");
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int ldpc_abi_version(void) { return LDPC_ABI_VERSION; }
+
+const char *ldpc_last_error(const ldpc_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+unsigned long long ldpc_launch_count(const ldpc_t *h) { return h ? h->launches : 0ull; }
+
+int ldpc_create(ldpc_t **out, int device, int n, int m, int E,
+                const int32_t *chk_ptr, const int32_t *edge_var,
+                const int32_t *var_ptr, const int32_t *var_edges)
+{
+    if (!out) return fail(nullptr, LDPC_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n <= 0 || m <= 0 || E <= 0 || !chk_ptr || !edge_var || !var_ptr || !var_edges)
+        return fail(nullptr, LDPC_EINVAL, "bad table arguments");
+    // ---- validate: np.where(H) order = check-major, ascending variable; var_edges ascending per variable
+    if (chk_ptr[0] != 0 || chk_ptr[m] != E || var_ptr[0] != 0 || var_ptr[n] != E)
+        return fail(nullptr, LDPC_EINVAL, "pointer tables must start at 0 and end at E");
+    int max_dc = 0, max_dv = 0, min_dc = E, min_dv = E;
+    for (int c = 0; c < m; ++c) {
+        const int d = chk_ptr[c + 1] - chk_ptr[c];
+        if (d < 0) return fail(nullptr, LDPC_EINVAL, "chk_ptr not monotone");
+        max_dc = std::max(max_dc, d); min_dc = std::min(min_dc, d);
+        for (int e = chk_ptr[c]; e < chk_ptr[c + 1]; ++e) {
+            if (edge_var[e] < 0 || edge_var[e] >= n) return fail(nullptr, LDPC_EINVAL, "edge_var out of range");
+            if (e > chk_ptr[c] && edge_var[e] <= edge_var[e - 1]) return fail(nullptr, LDPC_EINVAL, "edge_var not ascending within a check");
+        }
+    }
+    std::vector<char> seen((size_t)E, 0);
+    for (int v = 0; v < n; ++v) {
+        const int d = var_ptr[v + 1] - var_ptr[v];
+        if (d < 0) return fail(nullptr, LDPC_EINVAL, "var_ptr not monotone");
+        max_dv = std::max(max_dv, d); min_dv = std::min(min_dv, d);
+        for (int k = var_ptr[v]; k < var_ptr[v + 1]; ++k) {
+            const int e = var_edges[k];
+            if (e < 0 || e >= E || edge_var[e] != v || seen[e]) return fail(nullptr, LDPC_EINVAL, "var_edges inconsistent with edge_var");
+            if (k > var_ptr[v] && e <= var_edges[k - 1]) return fail(nullptr, LDPC_EINVAL, "var_edges not ascending within a variable");
+            seen[e] = 1;
+        }
+    }
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, LDPC_ECUDA, std::string("no CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, LDPC_EINVAL, "bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, LDPC_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+
+    ldpc_t *h = new (std::nothrow) ldpc_t();
+    if (!h) return fail(nullptr, LDPC_ENOMEM, "handle");
+    h->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        h->sm_count = prop.multiProcessorCount;
+        h->smem_optin = prop.sharedMemPerBlockOptin;
+    }
+    Tables &t = h->t;
+    t.n = n; t.m = m; t.E = E;
+    t.max_dc = max_dc; t.max_dv = max_dv;
+    t.uni_dc = (max_dc == min_dc) ? max_dc : 0;
+    t.uni_dv = (max_dv == min_dv) ? max_dv : 0;
+    auto up = [&](int **dst, const int32_t *src, size_t cnt) -> cudaError_t {
+        cudaError_t r = cudaMalloc((void **)dst, cnt * sizeof(int));
+        if (r != cudaSuccess) return r;
+        return cudaMemcpy(*dst, src, cnt * sizeof(int), cudaMemcpyHostToDevice);
+    };
+    if ((e = up(&t.chk_ptr, chk_ptr, (size_t)m + 1)) != cudaSuccess || (e = up(&t.edge_var, edge_var, (size_t)E)) != cudaSuccess ||
+        (e = up(&t.var_ptr, var_ptr, (size_t)n + 1)) != cudaSuccess || (e = up(&t.var_edges, var_edges, (size_t)E)) != cudaSuccess) {
+        const std::string msg = std::string("table upload: ") + cudaGetErrorString(e);
+        ldpc_destroy(h);
+        return fail(nullptr, LDPC_ECUDA, msg);
+    }
+    *out = h;
+    return LDPC_OK;
+}
+
+int ldpc_profile_enable(ldpc_t *h, int on)
+{
+    if (!h) return LDPC_EINVAL;
+    h->prof = on != 0;
+    return LDPC_OK;
+}
+
+int ldpc_profile_read(ldpc_t *h, double *cn_ms, unsigned long long *cn_launches, double *vn_ms,
+                      unsigned long long *vn_launches)
+{
+    if (!h) return LDPC_EINVAL;
+    double ms[2] = {0.0, 0.0};
+    unsigned long long cnt[2] = {0ull, 0ull};
+    for (size_t i = 0; i < h->prof_used; ++i) {
+        ProfEvent &ev = h->prof_ev[i];
+        CUDA_TRY(h, cudaEventSynchronize(ev.t1));
+        float t = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&t, ev.t0, ev.t1));
+        ms[ev.kind & 1] += (double)t;
+        cnt[ev.kind & 1] += 1ull;
+    }
+    h->prof_used = 0;
+    if (cn_ms) *cn_ms = ms[0];
+    if (vn_ms) *vn_ms = ms[1];
+    if (cn_launches) *cn_launches = cnt[0];
+    if (vn_launches) *vn_launches = cnt[1];
+    return LDPC_OK;
+}
+
+void ldpc_destroy(ldpc_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto &ev : h->prof_ev) {
+        if (ev.t0) cudaEventDestroy(ev.t0);
+        if (ev.t1) cudaEventDestroy(ev.t1);
+    }
+    if (h->stage) {
+        for (auto &sl : h->stage->slot) {
+            if (sl.d_y) cudaFree(sl.d_y);
+            if (sl.d_x) cudaFree(sl.d_x);
+            if (sl.d_it) cudaFree(sl.d_it);
+            if (sl.d_rs) cudaFree(sl.d_rs);
+            if (sl.ws) cudaFree(sl.ws);
+            if (sl.stream) cudaStreamDestroy(sl.stream);
+        }
+        if (h->stage->h_flag) cudaFreeHost(h->stage->h_flag);
+        delete h->stage;
+    }
+    if (h->t.chk_ptr) cudaFree(h->t.chk_ptr);
+    if (h->t.edge_var) cudaFree(h->t.edge_var);
+    if (h->t.var_ptr) cudaFree(h->t.var_ptr);
+    if (h->t.var_edges) cudaFree(h->t.var_edges);
+    delete h;
+}
+
+size_t ldpc_workspace_bytes(const ldpc_t *h, int algo, int dtype, int B, unsigned flags)
+{
+    (void)flags;
+    return workspace_bytes_impl(h, algo, dtype, B, true);
+}
+
+int ldpc_decode(ldpc_t *h, int algo, int dtype, const void *input, const uint8_t *y_hard, int B,
+                int max_iter, int iter_cap, uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *marg_out,
+                void *workspace, size_t workspace_bytes, unsigned flags, void *stream)
+{
+    InSpec in;
+    in.channel = (algo == LDPC_BEC) ? LDPC_CH_BEC : LDPC_CH_PRIORS;
+    in.in_dtype = dtype;
+    in.src = input;
+    in.y_hard = y_hard;
+    in.param = 0.0;
+    return decode_any(h, algo, dtype, in, B, max_iter, iter_cap, x_hat, iters, reason, marg_out,
+                      workspace, workspace_bytes, flags, (cudaStream_t)stream);
+}
+
+int ldpc_decode_channel(ldpc_t *h, int channel, int algo, int dtype, double param,
+                        const void *y, int y_dtype, int B, int max_iter, int iter_cap,
+                        uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *marg_out,
+                        void *workspace, size_t workspace_bytes, unsigned flags, void *stream)
+{
+    if (!h) return LDPC_EINVAL;
+    if (algo == LDPC_BEC) channel = LDPC_CH_BEC;
+    if (channel < LDPC_CH_PRIORS || channel > LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "bad channel");
+    if ((channel == LDPC_CH_PRIORS || channel == LDPC_CH_BIAWGN) && y_dtype != LDPC_F32 && y_dtype != LDPC_F64)
+        return fail(h, LDPC_EINVAL, "bad y_dtype");
+    InSpec in;
+    in.channel = channel;
+    in.in_dtype = y_dtype;
+    in.src = y;
+    in.y_hard = nullptr;
+    in.param = param;
+    return decode_any(h, algo, dtype, in, B, max_iter, iter_cap, x_hat, iters, reason, marg_out,
+                      workspace, workspace_bytes, flags, (cudaStream_t)stream);
+}
+
+int ldpc_llr_bsc(ldpc_t *h, int dtype, double llr, const uint8_t *y, void *priors, size_t count, void *stream)
+{
+    if (!h || !y || !priors) return fail(h, LDPC_EINVAL, "null buffer");
+    if (count == 0) return LDPC_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int blocks = (int)std::min<size_t>((count + 255) / 256, (size_t)h->sm_count * 32);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == LDPC_F32) LAUNCH(h, (llr_flat<uint8_t, float, IN_BSC>), blocks, 256, s, y, (float *)priors, count, llr);
+    else if (dtype == LDPC_F64) LAUNCH(h, (llr_flat<uint8_t, double, IN_BSC>), blocks, 256, s, y, (double *)priors, count, llr);
+    else return fail(h, LDPC_EINVAL, "bad dtype");
+    return check_launch(h, "llr_bsc");
+}
+
+int ldpc_llr_biawgn(ldpc_t *h, int y_dtype, int dtype, double noise_var, const void *y, void *priors, size_t count, void *stream)
+{
+    if (!h || !y || !priors) return fail(h, LDPC_EINVAL, "null buffer");
+    if (count == 0) return LDPC_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int blocks = (int)std::min<size_t>((count + 255) / 256, (size_t)h->sm_count * 32);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (y_dtype == LDPC_F64 && dtype == LDPC_F64) LAUNCH(h, (llr_flat<double, double, IN_BIAWGN>), blocks, 256, s, (const double *)y, (double *)priors, count, noise_var);
+    else if (y_dtype == LDPC_F64 && dtype == LDPC_F32) LAUNCH(h, (llr_flat<double, float, IN_BIAWGN>), blocks, 256, s, (const double *)y, (float *)priors, count, noise_var);
+    else if (y_dtype == LDPC_F32 && dtype == LDPC_F64) LAUNCH(h, (llr_flat<float, double, IN_BIAWGN>), blocks, 256, s, (const float *)y, (double *)priors, count, noise_var);
+    else if (y_dtype == LDPC_F32 && dtype == LDPC_F32) LAUNCH(h, (llr_flat<float, float, IN_BIAWGN>), blocks, 256, s, (const float *)y, (float *)priors, count, noise_var);
+    else return fail(h, LDPC_EINVAL, "bad dtype");
+    return check_launch(h, "llr_biawgn");
+}
+
+int ldpc_debug_step(ldpc_t *h, int algo, int dtype, int which, int B, const void *prior, const void *msg_in,
+                    void *msg_out, void *marg, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!h) return LDPC_EINVAL;
+    if (B <= 0 || !msg_in || !msg_out || !workspace) return fail(h, LDPC_EINVAL, "bad arguments");
+    if (algo != LDPC_MSA && algo != LDPC_SPA) return fail(h, LDPC_EINVAL, "debug step is MSA/SPA only");
+    if (which != 0 && which != 1) return fail(h, LDPC_EINVAL, "which must be 0 (CN) or 1 (VN)");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (dtype == LDPC_F32)
+        return debug_step_t<float>(h, algo, which, B, prior, msg_in, msg_out, marg, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (dtype == LDPC_F64)
+        return debug_step_t<double>(h, algo, which, B, prior, msg_in, msg_out, marg, workspace, workspace_bytes, (cudaStream_t)stream);
+    return fail(h, LDPC_EINVAL, "bad dtype");
+}
+
+int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
+                     const void *y, int y_dtype, int B, int max_iter, int iter_cap,
+                     uint8_t *x_hat, int32_t *iters, uint8_t *reason, int chunk, unsigned flags)
+{
+    if (!h) return LDPC_EINVAL;
+    if (B <= 0 || !y || !x_hat || !iters) return fail(h, LDPC_EINVAL, "bad arguments");
+    if (algo == LDPC_BEC) channel = LDPC_CH_BEC;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_stage(h);
+    if (rc) return rc;
+    const Tables &t = h->t;
+    size_t in_es;
+    switch (channel) {
+    case LDPC_CH_PRIORS: in_es = elem_size(y_dtype); if (y_dtype != dtype) return fail(h, LDPC_EINVAL, "priors must have the message dtype"); break;
+    case LDPC_CH_BIAWGN: in_es = elem_size(y_dtype); break;
+    case LDPC_CH_BSC: case LDPC_CH_BEC: in_es = 1; break;
+    default: return fail(h, LDPC_EINVAL, "bad channel");
+    }
+    if (chunk <= 0) {
+        // ~1 GiB of message workspace per pipeline slot, at least one full wave of frame groups
+        const size_t per_frame = (size_t)t.E * elem_size(dtype) + (size_t)t.n * elem_size(dtype) * 2;
+        size_t c = ((size_t)1 << 30) / std::max<size_t>(per_frame, 1);
+        c = std::max<size_t>(1024, std::min<size_t>(c, 32768));
+        chunk = (int)(c / 128 * 128);
+    }
+    chunk = std::min(chunk, B);
+
+    HostStage *st = h->stage;
+    int idx = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, ++idx) {
+        const int nb = std::min(chunk, B - b0);
+        HostSlot &sl = st->slot[idx % HostStage::kSlots];
+        const size_t wsb = workspace_bytes_impl(h, algo, dtype, nb, false);
+        if (wsb == 0) return fail(h, LDPC_EINVAL, "bad algo/dtype");
+        if ((rc = grow(h, &sl.d_y, &sl.y_bytes, (size_t)nb * t.n * in_es)) != 0) return rc;
+        if ((rc = grow(h, &sl.d_x, &sl.x_bytes, (size_t)nb * t.n)) != 0) return rc;
+        if (sl.f_cap < (size_t)nb) {
+            if (sl.d_it) cudaFree(sl.d_it);
+            if (sl.d_rs) cudaFree(sl.d_rs);
+            sl.d_it = nullptr; sl.d_rs = nullptr; sl.f_cap = 0;
+            CUDA_TRY(h, cudaMalloc((void **)&sl.d_it, (size_t)nb * sizeof(int32_t)));
+            CUDA_TRY(h, cudaMalloc((void **)&sl.d_rs, (size_t)nb));
+            sl.f_cap = (size_t)nb;
+        }
+        if ((rc = grow(h, &sl.ws, &sl.ws_bytes, wsb)) != 0) return rc;
+
+        const char *src = (const char *)y + (size_t)b0 * t.n * in_es;
+        CUDA_TRY(h, cudaMemcpyAsync(sl.d_y, src, (size_t)nb * t.n * in_es, cudaMemcpyHostToDevice, sl.stream));
+        InSpec in;
+        in.channel = channel; in.in_dtype = y_dtype; in.src = sl.d_y; in.y_hard = nullptr; in.param = param;
+        rc = decode_any(h, algo, dtype, in, nb, max_iter, iter_cap, sl.d_x, sl.d_it, sl.d_rs, nullptr,
+                        sl.ws, sl.ws_bytes, flags, sl.stream);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMemcpyAsync(x_hat + (size_t)b0 * t.n, sl.d_x, (size_t)nb * t.n, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(h, cudaMemcpyAsync(iters + b0, sl.d_it, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+        if (reason) CUDA_TRY(h, cudaMemcpyAsync(reason + b0, sl.d_rs, (size_t)nb, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    for (auto &sl : st->slot) CUDA_TRY(h, cudaStreamSynchronize(sl.stream));
+    return LDPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+"""Engine — one libldpc_b200 handle per (parity-check matrix, device), plus the device buffers.
+
+PyTorch is used for exactly three things here: allocating device / pinned memory
+(``torch.empty``), naming the current CUDA stream, and (in dist.py) the NCCL process group.
+All arithmetic happens in the hand-written kernels behind the C ABI (include/ldpc_b200.h).
+"""
+import ctypes
+import hashlib
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import LdpcError
+from .graph import Tables
+
+_NP2DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise LdpcError("no CUDA device: ldpc_decoders_b200 has no CPU fallback")
+    return torch
+
+
+class Engine:
+    """Decoder handle for one H on one GPU."""
+
+    def __init__(self, tables, device=None):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.tables = tables
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        t = tables
+        h = ctypes.c_void_p()
+        rc = self.lib.ldpc_create(ctypes.byref(h), self.device, t.n, t.m, t.E,
+                                  t.chk_ptr.ctypes.data, t.edge_var.ctypes.data,
+                                  t.var_ptr.ctypes.data, t.var_edges.ctypes.data)
+        if rc != 0:
+            raise LdpcError("ldpc_create failed (%d): %s" % (rc, self.lib.ldpc_last_error(None).decode()))
+        self.handle = h
+        self._ws = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ldpc_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def launch_count(self):
+        return int(self.lib.ldpc_launch_count(self.handle))
+
+    def profile(self, on):
+        """Record CUDA events around every CN / VN sweep launch (see ldpc_profile_enable)."""
+        _lib.check(self.handle, self.lib.ldpc_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self):
+        """dict(cn_ms, cn_launches, vn_ms, vn_launches) accumulated since the last read; synchronises."""
+        cn, vn = ctypes.c_double(), ctypes.c_double()
+        ncn, nvn = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        _lib.check(self.handle, self.lib.ldpc_profile_read(self.handle, ctypes.byref(cn), ctypes.byref(ncn),
+                                                           ctypes.byref(vn), ctypes.byref(nvn)))
+        return dict(cn_ms=cn.value, cn_launches=ncn.value, vn_ms=vn.value, vn_launches=nvn.value)
+
+    def _dev(self):
+        return _torch().device("cuda", self.device)
+
+    def workspace(self, algo, dtype, B, flags=0):
+        """A cached torch uint8 buffer of at least ldpc_workspace_bytes (grow-only)."""
+        torch = _torch()
+        need = int(self.lib.ldpc_workspace_bytes(self.handle, algo, dtype, int(B), flags))
+        if need == 0:
+            raise LdpcError("ldpc_workspace_bytes: bad arguments")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self._dev())
+        return self._ws
+
+    @staticmethod
+    def _stream_ptr(stream):
+        torch = _torch()
+        s = torch.cuda.current_stream() if stream is None else stream
+        return ctypes.c_void_p(s.cuda_stream)
+
+    # ------------------------------------------------------------------ device-resident decode
+    def decode_device(self, algo, inp, y_hard=None, max_iter=10, iter_cap=0, want_marg=False,
+                      want_reason=True, flags=0, stream=None, out=None):
+        """Decode a batch that already lives on the GPU.
+
+        inp: torch CUDA tensor [B, n]; float32/float64 priors for MSA/SPA (dtype selects the
+        arithmetic, like the reference's priors.dtype), uint8 symbols for BEC.
+        Returns dict(x_hat uint8 [B,n], iters int32 [B], reason uint8 [B] | None, marg | None).
+        Asynchronous on the current stream.
+        """
+        torch = _torch()
+        t = self.tables
+        if inp.dim() != 2 or inp.shape[1] != t.n or not inp.is_cuda or not inp.is_contiguous():
+            raise ValueError("input must be a contiguous CUDA tensor [B, n]")
+        B = int(inp.shape[0])
+        if algo == _lib.BEC:
+            if inp.dtype != torch.uint8:
+                raise TypeError("BEC input must be uint8 symbols {0,1,2}")
+            dtype = _lib.F32
+        else:
+            if inp.dtype == torch.float32:
+                dtype = _lib.F32
+            elif inp.dtype == torch.float64:
+                dtype = _lib.F64
+            else:
+                raise TypeError("priors must be float32 or float64")
+        if y_hard is not None and (y_hard.dtype != torch.uint8 or tuple(y_hard.shape) != (B, t.n)
+                                   or not y_hard.is_contiguous()):
+            raise ValueError("y_hard must be a contiguous uint8 CUDA tensor [B, n]")
+        dev = self._dev()
+        if out is None:
+            out = {}
+        x_hat = out.get("x_hat")
+        if x_hat is None:
+            x_hat = torch.empty((B, t.n), dtype=torch.uint8, device=dev)
+        iters = out.get("iters")
+        if iters is None:
+            iters = torch.empty(B, dtype=torch.int32, device=dev)
+        reason = torch.empty(B, dtype=torch.uint8, device=dev) if want_reason else None
+        marg = torch.empty((B, t.n), dtype=inp.dtype, device=dev) if (want_marg and algo != _lib.BEC) else None
+        ws = self.workspace(algo, dtype, B, flags)
+        rc = self.lib.ldpc_decode(self.handle, algo, dtype, inp.data_ptr(),
+                                  None if y_hard is None else y_hard.data_ptr(), B,
+                                  int(max_iter), int(iter_cap), x_hat.data_ptr(), iters.data_ptr(),
+                                  None if reason is None else reason.data_ptr(),
+                                  None if marg is None else marg.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), flags, self._stream_ptr(stream))
+        _lib.check(self.handle, rc)
+        return dict(x_hat=x_hat, iters=iters, reason=reason, marg=marg)
+
+    def decode_device_channel(self, channel, algo, dtype, param, y, max_iter=10, iter_cap=0, want_reason=True,
+                              flags=0, stream=None, out=None):
+        """Like decode_device, but takes the RECEIVED block y [B,n] (CUDA tensor: uint8 for BSC/BEC, float32 or
+        float64 for BIAWGN) and applies the channel's LLR map inside the load kernel (ldpc_decode_channel)."""
+        torch = _torch()
+        t = self.tables
+        if y.dim() != 2 or y.shape[1] != t.n or not y.is_cuda or not y.is_contiguous():
+            raise ValueError("y must be a contiguous CUDA tensor [B, n]")
+        B = int(y.shape[0])
+        if channel in (_lib.CH_BSC, _lib.CH_BEC):
+            if y.dtype != torch.uint8:
+                raise TypeError("BSC/BEC input must be uint8")
+            y_dtype = _lib.F32
+        else:
+            y_dtype = {torch.float32: _lib.F32, torch.float64: _lib.F64}[y.dtype]
+        dev = self._dev()
+        out = {} if out is None else out
+        x_hat = out.get("x_hat")
+        if x_hat is None:
+            x_hat = torch.empty((B, t.n), dtype=torch.uint8, device=dev)
+        iters = out.get("iters")
+        if iters is None:
+            iters = torch.empty(B, dtype=torch.int32, device=dev)
+        reason = out.get("reason")
+        if reason is None and want_reason:
+            reason = torch.empty(B, dtype=torch.uint8, device=dev)
+        ws = self.workspace(algo, dtype, B, flags)
+        rc = self.lib.ldpc_decode_channel(self.handle, channel, algo, dtype, float(param), y.data_ptr(), y_dtype, B,
+                                          int(max_iter), int(iter_cap), x_hat.data_ptr(), iters.data_ptr(),
+                                          None if reason is None else reason.data_ptr(), None,
+                                          ws.data_ptr(), ws.numel(), flags, self._stream_ptr(stream))
+        _lib.check(self.handle, rc)
+        return dict(x_hat=x_hat, iters=iters, reason=reason, marg=None)
+
+    # ------------------------------------------------------------------ host-buffer decode (e2e path)
+    def decode_host(self, channel, algo, dtype, param, y, max_iter=10, iter_cap=0, chunk=0, flags=0,
+                    x_hat=None, iters=None, reason=None):
+        """Decode a batch held in host memory (numpy); H2D / decode / D2H are pipelined in the library.
+
+        y [B, n]: uint8 for BSC/BEC, float32/float64 for BIAWGN / PRIORS.  Pinned arrays
+        (``pinned_empty``) make the copies asynchronous.  Returns numpy (x_hat, iters, reason).
+        """
+        t = self.tables
+        y = np.ascontiguousarray(y)
+        if y.ndim != 2 or y.shape[1] != t.n:
+            raise ValueError("y must be [B, n]")
+        B = y.shape[0]
+        if channel in (_lib.CH_BSC, _lib.CH_BEC):
+            if y.dtype != np.uint8:
+                raise TypeError("BSC/BEC input must be uint8")
+            y_dtype = _lib.F32
+        else:
+            if y.dtype not in _NP2DT:
+                raise TypeError("input must be float32 or float64")
+            y_dtype = _NP2DT[y.dtype]
+        if x_hat is None:
+            x_hat = np.empty((B, t.n), np.uint8)
+        if iters is None:
+            iters = np.empty(B, np.int32)
+        if reason is None:
+            reason = np.empty(B, np.uint8)
+        rc = self.lib.ldpc_decode_host(self.handle, channel, algo, dtype, float(param), y.ctypes.data, y_dtype,
+                                       B, int(max_iter), int(iter_cap), x_hat.ctypes.data, iters.ctypes.data,
+                                       reason.ctypes.data, int(chunk), flags)
+        _lib.check(self.handle, rc)
+        return x_hat, iters, reason
+
+    # ------------------------------------------------------------------ front ends and the isolated sweep
+    def llr_bsc(self, p_llr, y, dtype, stream=None):
+        torch = _torch()
+        out = torch.empty(y.shape, dtype=torch.float32 if dtype == _lib.F32 else torch.float64, device=y.device)
+        rc = self.lib.ldpc_llr_bsc(self.handle, dtype, float(p_llr), y.data_ptr(), out.data_ptr(), y.numel(),
+                                   self._stream_ptr(stream))
+        _lib.check(self.handle, rc)
+        return out
+
+    def llr_biawgn(self, noise_var, y, dtype, stream=None):
+        torch = _torch()
+        y_dtype = _lib.F32 if y.dtype == torch.float32 else _lib.F64
+        out = torch.empty(y.shape, dtype=torch.float32 if dtype == _lib.F32 else torch.float64, device=y.device)
+        rc = self.lib.ldpc_llr_biawgn(self.handle, y_dtype, dtype, float(noise_var), y.data_ptr(), out.data_ptr(),
+                                      y.numel(), self._stream_ptr(stream))
+        _lib.check(self.handle, rc)
+        return out
+
+    def debug_step(self, algo, which, msg_in, prior=None, stream=None):
+        """One CN (which=0) or VN (which=1) sweep on messages [B, E] in np.where(H) edge order."""
+        torch = _torch()
+        t = self.tables
+        B = int(msg_in.shape[0])
+        dtype = _lib.F32 if msg_in.dtype == torch.float32 else _lib.F64
+        msg_out = torch.empty_like(msg_in)
+        marg = torch.empty((B, t.n), dtype=msg_in.dtype, device=msg_in.device) if which == 1 else None
+        ws = self.workspace(algo, dtype, B)
+        rc = self.lib.ldpc_debug_step(self.handle, algo, dtype, which, B,
+                                      None if prior is None else prior.data_ptr(), msg_in.data_ptr(),
+                                      msg_out.data_ptr(), None if marg is None else marg.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), self._stream_ptr(stream))
+        _lib.check(self.handle, rc)
+        return msg_out, marg
+
+
+def pinned_empty(shape, dtype):
+    """A numpy array backed by pinned (page-locked) host memory, for asynchronous copies."""
+    torch = _torch()
+    tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32,
+           np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+    t = torch.empty(tuple(shape) if not np.isscalar(shape) else (shape,), dtype=tdt, pin_memory=True)
+    return t.numpy()          # the array keeps the tensor (and its pinned allocation) alive
+
+
+_engines = {}
+_engines_lock = threading.Lock()
+
+
+def tables_of(code_or_mtx):
+    """Tables from a reference-style Code object (``.parity_mtx``), a dense H, or ready-made Tables."""
+    if isinstance(code_or_mtx, Tables):
+        return code_or_mtx
+    tab = getattr(code_or_mtx, "tables", None)
+    if isinstance(tab, Tables):
+        return tab
+    H = getattr(code_or_mtx, "parity_mtx", code_or_mtx)
+    return Tables.from_dense(H)
+
+
+def engine_for(tables, device=None):
+    """Engines are cached per (edge list, device): src/main.py builds a new decoder per channel parameter."""
+    torch = _torch()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    key = (tables.m, tables.n, hashlib.sha1(tables.edge_var.tobytes() + tables.chk_ptr.tobytes()).hexdigest(), dev)
+    with _engines_lock:
+        eng = _engines.get(key)
+        if eng is None:
+            eng = Engine(tables, dev)
+            _engines[key] = eng
+        return eng

@@ -1,0 +1,210 @@
+// tests/host_emu/emu.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the product's node arithmetic (ldpc_decoders_b200/csrc/ldpc_math.cuh, the
+// __host__ __device__ functions every CUDA kernel calls) with g++ and drives it with plain
+// loops, so that tests/test_host_emu.py can compare it with the oracle on the CPU box before any
+// GPU time is spent.  It is not a decoder anybody ships or times: the package never loads it.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../ldpc_decoders_b200/csrc/ldpc_math.cuh"
+
+using namespace ldpc;
+
+namespace {
+struct G { int n, m, E; const int32_t *chk_ptr, *edge_var, *var_ptr, *var_edges; };
+constexpr int DMAX = 32;
+
+template <typename T, int ALGO> void cn(const G &g, const T *v2c, T *c2v);
+template <typename T> void cn_msa_all(const G &g, const T *v2c, T *c2v)
+{
+    for (int c = 0; c < g.m; ++c) {
+        const int e0 = g.chk_ptr[c], dc = g.chk_ptr[c + 1] - e0;
+        T a[DMAX], o[DMAX];
+        for (int k = 0; k < dc; ++k) a[k] = v2c[e0 + k];
+        cn_msa<T, DMAX>(a, dc, o);
+        for (int k = 0; k < dc; ++k) c2v[e0 + k] = o[k];
+    }
+}
+void cn_spa_ref_all(const G &g, const double *v2c, double *c2v)
+{
+    for (int c = 0; c < g.m; ++c) {
+        const int e0 = g.chk_ptr[c], dc = g.chk_ptr[c + 1] - e0;
+        double a[DMAX], o[DMAX];
+        for (int k = 0; k < dc; ++k) a[k] = v2c[e0 + k];
+        cn_spa_ref<DMAX>(a, dc, o);
+        for (int k = 0; k < dc; ++k) c2v[e0 + k] = o[k];
+    }
+}
+void cn_spa_phi_all(const G &g, const float *v2c, float *c2v)
+{
+    for (int c = 0; c < g.m; ++c) {
+        const int e0 = g.chk_ptr[c], dc = g.chk_ptr[c + 1] - e0;
+        float a[DMAX], o[DMAX];
+        for (int k = 0; k < dc; ++k) a[k] = v2c[e0 + k];
+        cn_spa_phi<DMAX>(a, dc, o);
+        for (int k = 0; k < dc; ++k) c2v[e0 + k] = o[k];
+    }
+}
+
+template <typename T>
+void decode_bp(const G &g, int algo, const T *prior, const uint8_t *y_hard, int max_iter,
+               uint8_t *x_hat, int32_t *iters, T *marg_out)
+{
+    std::vector<T> msg((size_t)g.E), tmp((size_t)g.E), marg(prior, prior + g.n);
+    for (int e = 0; e < g.E; ++e) msg[e] = prior[g.edge_var[e]];
+    bool have_x = y_hard != nullptr;
+    if (have_x) memcpy(x_hat, y_hard, (size_t)g.n); else memset(x_hat, 0, (size_t)g.n);
+    int it = 0;
+    for (; it < max_iter; ++it) {
+        if (have_x) {
+            bool unsat = false;
+            for (int c = 0; c < g.m && !unsat; ++c) {
+                unsigned p = 0;
+                for (int e = g.chk_ptr[c]; e < g.chk_ptr[c + 1]; ++e) p ^= x_hat[g.edge_var[e]];
+                unsat = p & 1u;
+            }
+            if (!unsat) break;
+        }
+        if (algo == 0) cn_msa_all<T>(g, msg.data(), tmp.data());
+        else if (sizeof(T) == 8) cn_spa_ref_all(g, (const double *)msg.data(), (double *)tmp.data());
+        else cn_spa_phi_all(g, (const float *)msg.data(), (float *)tmp.data());
+        for (int v = 0; v < g.n; ++v) {
+            const int p0 = g.var_ptr[v], dv = g.var_ptr[v + 1] - p0;
+            T a[DMAX], o[DMAX];
+            for (int k = 0; k < dv; ++k) a[k] = tmp[g.var_edges[p0 + k]];
+            const T mg = vn_update<T, DMAX>(prior[v], a, dv, o);
+            for (int k = 0; k < dv; ++k) msg[g.var_edges[p0 + k]] = o[k];
+            marg[v] = mg;
+            x_hat[v] = (uint8_t)(mg < (T)0);
+        }
+        have_x = true;
+    }
+    *iters = it;
+    if (marg_out) memcpy(marg_out, marg.data(), sizeof(T) * (size_t)g.n);
+}
+}  // namespace
+
+extern "C" {
+
+int emu_bp_f64(int algo, int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+               int B, const double *priors, const uint8_t *y_hard, int max_iter, uint8_t *x_hat, int32_t *iters, double *marg)
+{
+    G g{n, m, E, cp, ev, vp, ve};
+    for (int b = 0; b < B; ++b)
+        decode_bp<double>(g, algo, priors + (size_t)b * n, y_hard ? y_hard + (size_t)b * n : nullptr, max_iter,
+                          x_hat + (size_t)b * n, iters + b, marg ? marg + (size_t)b * n : nullptr);
+    return 0;
+}
+
+int emu_bp_f32(int algo, int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+               int B, const float *priors, const uint8_t *y_hard, int max_iter, uint8_t *x_hat, int32_t *iters, float *marg)
+{
+    G g{n, m, E, cp, ev, vp, ve};
+    for (int b = 0; b < B; ++b)
+        decode_bp<float>(g, algo, priors + (size_t)b * n, y_hard ? y_hard + (size_t)b * n : nullptr, max_iter,
+                         x_hat + (size_t)b * n, iters + b, marg ? marg + (size_t)b * n : nullptr);
+    return 0;
+}
+
+int emu_cn_phi(int n, int m, int E, const int32_t *cp, const int32_t *ev, const float *v2c, float *c2v)
+{
+    G g{n, m, E, cp, ev, nullptr, nullptr};
+    cn_spa_phi_all(g, v2c, c2v);
+    return 0;
+}
+
+// BEC on bit planes, 32 frames per word, with the same book-keeping as bec_book / bec_cn / bec_vn.
+int emu_bec(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+            int B, const uint8_t *y, int max_iter, int nb_bits, uint8_t *x_hat, int32_t *iters, uint8_t *reason)
+{
+    const int wpr = (B + 31) / 32;
+    const int limit = max_iter > 0 ? max_iter : n + 1;
+    std::vector<uint32_t> mnz((size_t)E * wpr), mpos((size_t)E * wpr), pnz((size_t)n * wpr, 0), ppos((size_t)n * wpr, 0),
+        xe((size_t)n * wpr, 0), xv((size_t)n * wpr, 0), act(wpr, 0), changed(wpr, 0), haser(wpr, 0), stopped(wpr, 0);
+    std::vector<int32_t> its((size_t)wpr * 32, 0);
+    for (int f = 0; f < B; ++f) {
+        act[f >> 5] |= 1u << (f & 31);
+        for (int v = 0; v < n; ++v) {
+            const uint8_t s = y[(size_t)f * n + v];
+            const uint32_t bit = 1u << (f & 31);
+            const size_t i = (size_t)v * wpr + (f >> 5);
+            if (s >= 2) { xe[i] |= bit; haser[f >> 5] |= bit; }
+            else { pnz[i] |= bit; if (s == 1) { ppos[i] |= bit; xv[i] |= bit; } }
+        }
+    }
+    auto book = [&](bool first, bool last) {
+        for (int w = 0; w < wpr; ++w) {
+            uint32_t a = act[w];
+            const uint32_t ch = changed[w], h = haser[w];
+            if (!first) {
+                stopped[w] |= a & ~ch;
+                a &= ch;
+                for (int l = 0; l < 32; ++l) if ((a >> l) & 1u) its[(size_t)w * 32 + l] += 1;
+            }
+            if (!last) { a &= h; haser[w] = 0; }
+            act[w] = a; changed[w] = 0;
+        }
+    };
+    int it = 0;
+    for (; it < limit; ++it) {
+        book(it == 0, false);
+        const bool first = it == 0;
+        for (int w = 0; w < wpr; ++w) {
+            if (!act[w]) continue;
+            for (int c = 0; c < m; ++c) {
+                BecCnAcc acc; acc.init();
+                for (int e = cp[c]; e < cp[c + 1]; ++e) {
+                    const size_t r = first ? (size_t)ev[e] * wpr + w : (size_t)e * wpr + w;
+                    acc.push(first ? pnz[r] : mnz[r], first ? ppos[r] : mpos[r]);
+                }
+                for (int e = cp[c]; e < cp[c + 1]; ++e) {
+                    const size_t r = (size_t)e * wpr + w, rp = (size_t)ev[e] * wpr + w;
+                    uint32_t onz, opos;
+                    acc.out(first ? pnz[rp] : mnz[r], first ? ppos[rp] : mpos[r], onz, opos);
+                    mnz[r] = onz; mpos[r] = opos;
+                }
+            }
+        }
+        for (int w = 0; w < wpr; ++w) {
+            const uint32_t run = act[w];
+            if (!run) continue;
+            for (int v = 0; v < n; ++v) {
+                const size_t rv = (size_t)v * wpr + w;
+                uint32_t nz, pos;
+                auto body = [&](auto acc) {
+                    acc.set_ternary(pnz[rv], ppos[rv]);
+                    for (int k = vp[v]; k < vp[v + 1]; ++k) { const size_t r = (size_t)ve[k] * wpr + w; acc.add_ternary(mnz[r], mpos[r]); }
+                    for (int k = vp[v]; k < vp[v + 1]; ++k) {
+                        const size_t r = (size_t)ve[k] * wpr + w;
+                        auto t = acc;
+                        t.sub_ternary(mnz[r], mpos[r]);
+                        uint32_t a, b; t.sign(a, b);
+                        mnz[r] = a; mpos[r] = b;
+                    }
+                    acc.sign(nz, pos);
+                };
+                if (nb_bits == 5) body(BsInt<5>()); else body(BsInt<8>());
+                const uint32_t xe_new = ~nz, xv_new = pos, xe_old = xe[rv], xv_old = xv[rv];
+                changed[w] |= ((xe_new ^ xe_old) | (~xe_new & (xv_new ^ xv_old))) & run;
+                haser[w] |= xe_new & run;
+                xe[rv] = (xe_old & ~run) | (xe_new & run);
+                xv[rv] = (xv_old & ~run) | (xv_new & run & ~xe_new);
+            }
+        }
+    }
+    if (it == limit) book(false, true);
+    for (int f = 0; f < B; ++f) {
+        const uint32_t bit = 1u << (f & 31);
+        for (int v = 0; v < n; ++v) {
+            const size_t i = (size_t)v * wpr + (f >> 5);
+            x_hat[(size_t)f * n + v] = (xe[i] & bit) ? 2 : ((xv[i] & bit) ? 1 : 0);
+        }
+        iters[f] = its[f];
+        reason[f] = (stopped[f >> 5] & bit) ? 2 : ((act[f >> 5] & bit) ? (max_iter > 0 ? 1 : 4) : 0);
+    }
+    return 0;
+}
+}

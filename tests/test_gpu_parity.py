@@ -1,0 +1,353 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the oracle and the golden fixtures.
+
+Parity bars:
+  BEC          x_hat, iteration count and exit reason bit-exact
+  MSA          x_hat, iteration count (and marginals) bit-exact against the oracle AT THE SAME DTYPE
+  SPA float64  formula mirror: identical words / iteration counts on frames whose reference marginals stay
+               finite; messages within 1e-12*max(1,|ref|) + 1e-15*exp(|ref|) (2*atanh conditioning, H3)
+  SPA float32  phi form: |d| <= 1e-4*max(1,|ref|) for |ref| < 20 against the float64 formula on the same
+               inputs, sign agreement + |LLR| >= 15 beyond; identical words on frames away from a decision
+               boundary
+"""
+import numpy as np
+import pytest
+
+import _golden as G
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    from ldpc_decoders_b200 import Tables, _lib, bec, biawgn, bpa, bsc, engine, models
+    torch.cuda.set_device(0)
+    return dict(torch=torch, Tables=Tables, lib=_lib, bec=bec, biawgn=biawgn, bpa=bpa, bsc=bsc,
+                engine=engine, models=models)
+
+
+_tabs = {}
+
+
+def tables(mods, name):
+    if name not in _tabs:
+        _tabs[name] = mods["Tables"](*G.code_tables(name))
+    return _tabs[name]
+
+
+def ograph(name):
+    return O.Graph(*G.code_tables(name))
+
+
+def spa_tol(ref):
+    a = np.abs(ref)
+    return 1e-12 * np.maximum(1.0, a) + 1e-15 * np.exp(np.minimum(a, 40.0))
+
+
+class Code:
+    """What the reference hands to a decoder constructor: an object with a dense .parity_mtx (codes.Code)."""
+
+    def __init__(self, name):
+        self.parity_mtx = G.dense_H(name)
+
+
+# --------------------------------------------------------------------------------------------- KATs
+@pytest.mark.parametrize("k", G.kats(), ids=lambda k: "%s-%s-%s" % (k["channel"], k["code"], k["decoder"]))
+def test_kat_through_reference_protocol(mods, k):
+    """The six Test.sample vectors (src/bec.py:132-139, src/bsc.py:82-89, src/biawgn.py:85-92), decoded the
+    way utils.TestCase.sample does it: decoder(param, code, **kwargs).decode(y)  (src/utils.py:84)."""
+    model = mods["models"].models[k["channel"]]
+    dec = getattr(model, k["decoder"])(k["param"], Code(k["code"]), max_iter=k["max_iter"], mu=3., eps=1e-5)
+    y = np.array(k["y"]) if k["channel"] == "biawgn" else np.array(k["y"]).astype(int)
+    est = dec.decode(y)
+    assert (np.asarray(est) == np.array(k["x"])).all()
+    assert np.asarray(est).tolist() == k["x_hat"]
+    st = dec.stats()
+    assert st["iter"][k["iters"]] == 1 and sum(st["iter"]) == 1
+
+
+# --------------------------------------------------------------------------------------------- golden runs
+@pytest.mark.parametrize("rec", G.runs(), ids=lambda r: r["key"])
+def test_golden_run(mods, rec):
+    x, Y = G.run_inputs(rec)
+    gold = G.run_arrays(rec)
+    tab = tables(mods, rec["code"])
+    model = mods["models"].models[rec["channel"]]
+    if rec["channel"] == "bec":
+        dec = model.SPA(rec["param"], tab, max_iter=rec["max_iter"])
+        x_hat, iters, reason = dec.decode_batch(Y, return_reason=True)
+        assert (iters == gold["iters"]).all() and (reason == gold["reason"]).all() and (x_hat == gold["x_hat"]).all()
+        return
+    dt = np.float64 if rec["dtype"] == "f64" else np.float32
+    dec = getattr(model, rec["decoder"])(rec["param"], tab, max_iter=rec["max_iter"], dtype=dt)
+    x_hat, iters, reason = dec.decode_batch(Y.astype(np.uint8) if rec["channel"] == "bsc" else Y, return_reason=True)
+    if rec["decoder"] == "MSA":
+        assert (iters == gold["iters"]).all()
+        assert (x_hat == gold["x_hat"]).all()
+        assert (reason == gold["reason"]).all()
+    else:
+        nf = gold["nonfinite"]
+        ok = (iters == gold["iters"]) & (x_hat == gold["x_hat"]).all(axis=1)
+        assert ok[~nf].all(), "SPA f64 differs on finite frames %s" % np.flatnonzero(~ok & ~nf)[:8]
+        if nf.any():
+            assert (x_hat == gold["x_hat"]).all(axis=1)[nf].mean() >= 0.9
+
+
+@pytest.mark.parametrize("rec", [r for r in G.runs() if r["channel"] != "bec"], ids=lambda r: r["key"])
+def test_golden_marginals(mods, rec):
+    """Last marginal (src/bpa.py:35) of the first frames: bit-exact for MSA, conditioning-aware tolerance for SPA."""
+    torch = mods["torch"]
+    x, Y = G.run_inputs(rec)
+    gold = G.run_arrays(rec)
+    m4 = gold["marg4"]
+    k = len(m4)
+    og = ograph(rec["code"])
+    dt = np.float64 if rec["dtype"] == "f64" else np.float32
+    if rec["channel"] == "bsc":
+        pri, yh = O.llr_bsc(rec["param"], Y[:k].astype(np.uint8)).astype(dt), np.ascontiguousarray(Y[:k], np.uint8)
+    else:
+        pri, yh = O.llr_biawgn(rec["param"], Y[:k]).astype(dt), None
+    eng = mods["engine"].engine_for(tables(mods, rec["code"]))
+    algo = mods["lib"].MSA if rec["decoder"] == "MSA" else mods["lib"].SPA
+    out = eng.decode_device(algo, torch.from_numpy(pri).cuda(), None if yh is None else torch.from_numpy(yh).cuda(),
+                            max_iter=rec["max_iter"], want_marg=True)
+    marg = out["marg"].cpu().numpy()
+    if rec["decoder"] == "MSA":
+        assert marg.dtype == m4.dtype and (marg == m4).all()
+    else:
+        fin = np.isfinite(m4) & ~gold["nonfinite"][:k, None]
+        with np.errstate(invalid="ignore"):
+            d = np.abs(marg - m4)
+        assert (d[fin] <= 50 * spa_tol(m4[fin])).all()
+
+
+# --------------------------------------------------------------------------------------------- MSA / BEC at scale
+@pytest.mark.parametrize("channel,code,param,cw,dt", [
+    ("biawgn", "1200_3_6_rand_ldpc_1", 2.0, 1, np.float32),
+    ("biawgn", "1200_3_6_rand_ldpc_1", 2.6, 1, np.float64),
+    ("bsc", "1200_3_6_rand_ldpc_1", .05, 1, np.float32),
+    ("bsc", "1200_3_6_rand_ldpc_1", .041, 1, np.float64),
+    ("bsc", "1200_rho_x5_rand_ldpc_10", .045, 0, np.float32),
+    ("biawgn", "1200_rho_x5_rand_ldpc_3", 1.5, 0, np.float32),
+])
+def test_msa_bit_exact_1e4_frames(mods, channel, code, param, cw, dt):
+    frames = 10000
+    tab, og = tables(mods, code), ograph(code)
+    x = np.zeros(tab.n, np.int64) + cw
+    Y = G.channel_send(channel, param, np.tile(x, (frames, 1)), 4242)
+    dec = mods["models"].models[channel].MSA(param, tab, max_iter=10, dtype=dt)
+    if channel == "bsc":
+        Yh = Y.astype(np.uint8)
+        ref = O.bp_decode(og, O.MSA, O.llr_bsc(param, Yh).astype(dt), y_hard=Yh, max_iter=10, nthreads=8)
+        x_hat, iters = dec.decode_batch(Yh)
+    else:
+        ref = O.bp_decode(og, O.MSA, O.llr_biawgn(param, Y).astype(dt), max_iter=10, nthreads=8)
+        x_hat, iters = dec.decode_batch(Y)
+    assert (iters == ref["iters"]).all()
+    assert (x_hat == ref["x_hat"]).all()
+
+
+@pytest.mark.parametrize("code,p,mi", [("1200_3_6_rand_ldpc_1", .42, 10), ("1200_3_6_rand_ldpc_1", .38, 100),
+                                        ("1200_rho_x5_rand_ldpc_10", .42, 0), ("margulis", .41, 100)])
+def test_bec_bit_exact_many_frames(mods, code, p, mi):
+    frames = 20000
+    tab, og = tables(mods, code), ograph(code)
+    Y = G.channel_send("bec", p, np.zeros((frames, tab.n), np.int64), 99).astype(np.uint8)
+    ref = O.bec_decode(og, Y, max_iter=mi, nthreads=8)
+    x_hat, iters, reason = mods["bec"].SPA(p, tab, max_iter=mi).decode_batch(Y, return_reason=True)
+    assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all()
+
+
+def test_bec_arbitrary_symbols(mods):
+    rng = np.random.RandomState(3)
+    for code in ("7_4_hamming", "12_3_4_ldpc", "1200_rho_x5_rand_ldpc_10"):
+        tab, og = tables(mods, code), ograph(code)
+        Y = rng.choice(3, size=(333, tab.n), p=[.35, .35, .3]).astype(np.uint8)
+        for mi in (1, 4, 10, 0):
+            ref = O.bec_decode(og, Y, max_iter=mi)
+            x_hat, iters, reason = mods["bec"].SPA(.3, tab, max_iter=mi).decode_batch(Y, return_reason=True)
+            assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all()
+
+
+# --------------------------------------------------------------------------------------------- SPA
+@pytest.mark.parametrize("case", G.spa_tf(), ids=lambda c: c[0]["slot"])
+def test_spa_teacher_forced(mods, case):
+    """One check-node sweep from a shared input state (reference v2c snapshots), both SPA kernels."""
+    torch, lib = mods["torch"], mods["lib"]
+    rec, v2c, c2v_ref = case
+    eng = mods["engine"].engine_for(tables(mods, rec["code"]))
+    # float64 mirror against the reference's own c2v
+    out, _ = eng.debug_step(lib.SPA, 0, torch.from_numpy(np.tile(v2c, (3, 1))).cuda())
+    out = out.cpu().numpy()
+    assert (out[0] == out[2]).all() or np.isnan(out[0]).any()
+    fin = np.isfinite(c2v_ref) & np.isfinite(out[0])
+    assert (np.isfinite(c2v_ref) == np.isfinite(out[0])).all() or (np.abs(c2v_ref[np.isfinite(c2v_ref) != np.isfinite(out[0])]) > 30).all()
+    assert (np.abs(out[0][fin] - c2v_ref[fin]) <= spa_tol(c2v_ref[fin])).all()
+    # float32 phi form against the float64 formula evaluated on the same float32 inputs
+    v32 = np.ascontiguousarray(v2c, np.float32)
+    ref = O.cn_sweep(ograph(rec["code"]), O.SPA, v32.astype(np.float64))
+    out32, _ = eng.debug_step(lib.SPA, 0, torch.from_numpy(v32[None, :]).cuda())
+    out32 = out32.cpu().numpy()[0].astype(np.float64)
+    a = np.abs(ref)
+    m = a < 20
+    assert (np.abs(out32[m] - ref[m]) <= 1e-4 * np.maximum(1, a[m])).all()
+    big = ~m & np.isfinite(ref)
+    assert (np.sign(out32[big]) == np.sign(ref[big])).all() and (np.abs(out32[big]) >= 15).all()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_msa_and_vn_sweeps_bit_exact(mods, dt):
+    torch, lib = mods["torch"], mods["lib"]
+    for code in ("1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_10", "7_4_hamming"):
+        og = ograph(code)
+        eng = mods["engine"].engine_for(tables(mods, code))
+        rng = np.random.RandomState(1)
+        B = 5
+        v2c = (rng.normal(size=(B, og.E)) * 3).astype(dt)
+        v2c[0, :7] = [0.0, -0.0, 1.5, -1.5, 1.5, 2.0, -2.0]          # ties, zeros, negative zero
+        prior = rng.normal(size=(B, og.n)).astype(dt)
+        c2v, _ = eng.debug_step(lib.MSA, 0, torch.from_numpy(v2c).cuda())
+        c2v = c2v.cpu().numpy()
+        for b in range(B):
+            ref = O.cn_sweep(og, O.MSA, v2c[b])
+            assert (c2v[b] == ref).all() and (np.signbit(c2v[b]) == np.signbit(ref)).all()
+        nxt, marg = eng.debug_step(lib.MSA, 1, torch.from_numpy(c2v).cuda(), prior=torch.from_numpy(prior).cuda())
+        nxt, marg = nxt.cpu().numpy(), marg.cpu().numpy()
+        for b in range(B):
+            rv, rm, _ = O.vn_sweep(og, prior[b], c2v[b])
+            assert (nxt[b] == rv).all() and (marg[b] == rm).all()
+
+
+@pytest.mark.parametrize("channel,code,param,mi", [("biawgn", "1200_3_6_rand_ldpc_1", 2.0, 10),
+                                                    ("biawgn", "1200_3_6_rand_ldpc_1", 2.75, 10),
+                                                    ("bsc", "1200_rho_x5_rand_ldpc_1", .06, 40)])
+def test_spa_f32_words_agree_away_from_boundaries(mods, channel, code, param, mi):
+    """End to end: float32 phi-form SPA vs the float64 reference formula on the same float32 priors."""
+    frames = 1500
+    tab, og = tables(mods, code), ograph(code)
+    Y = G.channel_send(channel, param, np.zeros((frames, tab.n), np.int64), 31337)
+    if channel == "bsc":
+        Yh = Y.astype(np.uint8)
+        pri32 = O.llr_bsc(param, Yh).astype(np.float32)
+        ref = O.bp_decode(og, O.SPA, pri32.astype(np.float64), y_hard=Yh, max_iter=mi, want_marg=True, nthreads=8)
+        x_hat, iters = mods["bsc"].SPA(param, tab, max_iter=mi, dtype=np.float32).decode_batch(Yh)
+    else:
+        pri32 = O.llr_biawgn(param, Y).astype(np.float32)
+        ref = O.bp_decode(og, O.SPA, pri32.astype(np.float64), max_iter=mi, want_marg=True, nthreads=8)
+        x_hat, iters = mods["biawgn"].SPA(param, tab, max_iter=mi, dtype=np.float32).decode_batch(Y)
+    finite = np.isfinite(ref["marg"]).all(axis=1)
+    clear = finite & (np.abs(ref["marg"]).min(axis=1) > 1e-3) & (ref["iters"] < mi)      # converged, no bit near 0
+    assert clear.sum() > frames // 4
+    assert (x_hat[clear] == ref["x_hat"][clear]).all()
+    assert (np.abs(iters[clear] - ref["iters"][clear]) <= 1).all()
+    assert (iters[clear] == ref["iters"][clear]).mean() > 0.99
+    # error rates of the two arithmetic types agree statistically (same frames)
+    wer32 = (x_hat != 0).any(axis=1).mean()
+    wer64 = (ref["x_hat"] != 0).any(axis=1).mean()
+    assert abs(wer32 - wer64) <= 3 * np.sqrt(max(wer64 * (1 - wer64), 1e-4) / frames) + 2e-3
+
+
+# --------------------------------------------------------------------------------------------- edges of the batch API
+@pytest.mark.parametrize("B", [1, 2, 31, 33, 127, 129, 257])
+def test_ragged_batch_sizes(mods, B):
+    tab, og = tables(mods, "512_3_6_rand_ldpc_1"), ograph("512_3_6_rand_ldpc_1")
+    Y = G.channel_send("biawgn", 2.0, np.ones((B, tab.n), np.int64), 5)
+    for dt in (np.float32, np.float64):
+        ref = O.bp_decode(og, O.MSA, O.llr_biawgn(2.0, Y).astype(dt), max_iter=10)
+        x_hat, iters = mods["biawgn"].MSA(2.0, tab, max_iter=10, dtype=dt).decode_batch(Y)
+        assert (iters == ref["iters"]).all() and (x_hat == ref["x_hat"]).all()
+    Yb = G.channel_send("bec", .4, np.ones((B, tab.n), np.int64), 6).astype(np.uint8)
+    ref = O.bec_decode(og, Yb, max_iter=10)
+    x_hat, iters, reason = mods["bec"].SPA(.4, tab, max_iter=10).decode_batch(Yb, return_reason=True)
+    assert (iters == ref["iters"]).all() and (x_hat == ref["x_hat"]).all() and (reason == ref["reason"]).all()
+
+
+def test_zero_iteration_exits(mods):
+    """BSC: a received word that already satisfies H returns y itself after 0 iterations (bpa.py:20,29);
+    BIAWGN: integer-valued y passes the reference's (H @ y) % 2 test too; BEC without erasures: 'decoded' at 0."""
+    code = Code("1200_3_6_rand_ldpc_1")
+    n = code.parity_mtx.shape[1]
+    y = np.ones(n, int)
+    dec = mods["bsc"].MSA(.05, code, max_iter=10)
+    assert dec.decode(y) is y
+    yf = np.ones(n)                       # noise-free BIAWGN, all-ones codeword: H @ y is even everywhere
+    assert mods["biawgn"].MSA(2.0, code, max_iter=10).decode(yf) is yf
+    yb = np.zeros(n, int)
+    assert mods["bec"].SPA(.3, code, max_iter=10).decode(yb) is yb
+
+
+def test_unlimited_iterations_are_capped_and_flagged(mods):
+    tab, og = tables(mods, "1200_3_6_rand_ldpc_1"), ograph("1200_3_6_rand_ldpc_1")
+    Y = G.channel_send("biawgn", 0.5, np.ones((40, tab.n), np.int64), 7)
+    dec = mods["biawgn"].MSA(0.5, tab, max_iter=0, iter_cap=25, dtype=np.float32)
+    x_hat, iters, reason = dec.decode_batch(Y, return_reason=True)
+    ref = O.bp_decode(og, O.MSA, O.llr_biawgn(0.5, Y).astype(np.float32), max_iter=0, iter_cap=25)
+    assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all()
+    assert (reason == 4).any()
+
+
+def test_long_run_with_polling_matches(mods):
+    """max_iter = 100 takes the early-out polling path of ldpc_decode; results must not change."""
+    tab, og = tables(mods, "1200_3_6_rand_ldpc_1"), ograph("1200_3_6_rand_ldpc_1")
+    Y = G.channel_send("biawgn", 2.2, np.ones((300, tab.n), np.int64), 8)
+    ref = O.bp_decode(og, O.MSA, O.llr_biawgn(2.2, Y), max_iter=100, nthreads=8)
+    x_hat, iters = mods["biawgn"].MSA(2.2, tab, max_iter=100).decode_batch(Y)
+    assert (iters == ref["iters"]).all() and (x_hat == ref["x_hat"]).all()
+
+
+def test_device_and_host_entry_points_agree(mods):
+    torch, lib = mods["torch"], mods["lib"]
+    tab = tables(mods, "1200_3_6_rand_ldpc_1")
+    eng = mods["engine"].engine_for(tab)
+    Y = G.channel_send("biawgn", 2.0, np.ones((5000, tab.n), np.int64), 9).astype(np.float32)
+    nv = 10 ** (-2.0 / 10)
+    xh, it, rs = eng.decode_host(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, Y, max_iter=10, chunk=1024)
+    pri = eng.llr_biawgn(nv, torch.from_numpy(Y).cuda(), lib.F32)
+    out = eng.decode_device(lib.MSA, pri, max_iter=10)
+    assert (out["x_hat"].cpu().numpy() == xh).all() and (out["iters"].cpu().numpy() == it).all()
+    assert (out["reason"].cpu().numpy() == rs).all()
+    ref = (-2.0 * Y.astype(np.float64) / nv).astype(np.float32)
+    assert (pri.cpu().numpy() == ref).all()
+
+
+# --------------------------------------------------------------------------------------------- size-independent properties
+def test_sign_symmetry_at_full_batch(mods):
+    """All-ones is a codeword of a (3,6) code, so flipping the sign of every prior must flip every decoded
+    bit and leave every iteration count unchanged (min-sum is odd in its inputs).  Checked at a batch
+    larger than anything the oracle is run on."""
+    torch, lib = mods["torch"], mods["lib"]
+    tab = tables(mods, "1200_3_6_rand_ldpc_1")
+    eng = mods["engine"].engine_for(tab)
+    B = 32768
+    g = torch.Generator(device="cuda").manual_seed(1)
+    nv = 10 ** (-2.0 / 10)
+    y = 1.0 + nv ** .5 * torch.randn((B, tab.n), generator=g, device="cuda", dtype=torch.float32)
+    pri = eng.llr_biawgn(nv, y, lib.F32)
+    a = eng.decode_device(lib.MSA, pri, max_iter=10)
+    xa, ia = a["x_hat"].clone(), a["iters"].clone()
+    b = eng.decode_device(lib.MSA, -pri, max_iter=10)
+    assert bool((ia == b["iters"]).all())
+    assert bool(((xa ^ 1) == b["x_hat"]).all())
+    # decoded frames satisfy every check; frames at max_iter are exactly the undecoded ones
+    H = torch.from_numpy(tab.dense(np.float32)).cuda()
+    syn = (xa.float() @ H.T) % 2
+    ok = (syn == 0).all(dim=1)
+    assert bool(ok[a["reason"] == 0].all())
+    assert bool((ia[a["reason"] == 1] == 10).all())
+    assert 0.1 < float(ok.float().mean()) < 0.6            # WER ~0.7 at 2 dB
+
+
+def test_bec_round_trip_property(mods):
+    """Erase, decode: every symbol the decoder resolves equals the transmitted bit, unresolved ones stay 2,
+    and a frame reported 'decoded' has no erasures left."""
+    tab = tables(mods, "1200_3_6_rand_ldpc_1")
+    B = 50000
+    rng = np.random.RandomState(12)
+    Y = np.where(rng.random_sample((B, tab.n)) < .36, 2, 0).astype(np.uint8)
+    x_hat, iters, reason = mods["bec"].SPA(.36, tab, max_iter=100).decode_batch(Y, return_reason=True)
+    assert ((x_hat == 0) | (x_hat == 2)).all()
+    assert ((x_hat == 2) <= (Y == 2)).all()
+    assert ((x_hat == 2).sum(axis=1)[reason == 0] == 0).all()
+    assert ((x_hat == 2).sum(axis=1)[reason == 2] > 0).all()
+    assert (reason == 0).mean() > 0.8
