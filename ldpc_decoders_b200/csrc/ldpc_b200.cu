@@ -784,11 +784,14 @@ int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
     default: return fail(h, LDPC_EINVAL, "bad channel");
     }
     if (chunk <= 0) {
-        // ~1 GiB of message workspace per pipeline slot, at least one full wave of frame groups
+        // Enough chunks to overlap H2D / decode / D2H on the 3 slot streams, each chunk still filling the GPU
+        // (>= 4096 frames) and its message workspace bounded (~1 GiB per slot).
         const size_t per_frame = (size_t)t.E * elem_size(dtype) + (size_t)t.n * elem_size(dtype) * 2;
-        size_t c = ((size_t)1 << 30) / std::max<size_t>(per_frame, 1);
-        c = std::max<size_t>(1024, std::min<size_t>(c, 32768));
-        chunk = (int)(c / 128 * 128);
+        size_t cap = ((size_t)1 << 30) / std::max<size_t>(per_frame, 1);
+        cap = std::max<size_t>(256, std::min<size_t>(cap, 16384));
+        size_t c = std::max<size_t>((size_t)B / 6, 4096);
+        c = std::min(c, cap);
+        chunk = (int)std::max<size_t>(128, c / 128 * 128);
     }
     chunk = std::min(chunk, B);
 

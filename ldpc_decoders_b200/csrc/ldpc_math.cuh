@@ -135,6 +135,13 @@ LDPC_HD void cn_spa_ref(const double (&v)[DCMAX], int dc, double (&out)[DCMAX])
 // edges is built from prefix/suffix sums (total - own cancels catastrophically).
 // Degenerate inputs follow the reference: v_k == 0 gives NaN on that edge
 // (0/0, bpa.py:74) and 0 on the others; all others saturated gives +-inf.
+// Saturation is the reference's, not float32's: in float64 tanh(v/2) rounds to exactly 1 once
+// |v| > 55 ln 2 = 38.123 (2 e^-|v| < 2^-54), its log is then 0, and a check whose OTHER inputs are all
+// saturated emits +-inf (|q| == 1, math_utils.py:57-58) which turns the variable's "total minus own"
+// into inf - inf = NaN (bpa.py:37) and floods the frame.  With sat_llr = 38.123 a saturated input
+// contributes phi = 0 here too, so the float32 decoder leaves the well-conditioned regime at the same
+// point as the reference (its BER/WER curves depend on it: a flooded frame decodes to all-zero).
+// sat_llr = +inf switches the emulation off (numerically robust decoder).
 // Measured against the float64 reference formula: <= 6e-7 * max(1,|ref|) for |ref| < 20.
 // ---------------------------------------------------------------------------------------------
 LDPC_HD float phi_f32(float x)
@@ -156,8 +163,10 @@ LDPC_HD float phi_f32(float x)
     return (x > 3.0f) ? small : big;
 }
 
+constexpr float kSpaSatLlr = 38.1230f;       // 55 ln 2: float64 tanh(v/2) == 1 beyond this |v|
+
 template <int DCMAX>
-LDPC_HD void cn_spa_phi(const float (&v)[DCMAX], int dc, float (&out)[DCMAX])
+LDPC_HD void cn_spa_phi(const float (&v)[DCMAX], int dc, float (&out)[DCMAX], float sat_llr = kSpaSatLlr)
 {
     float a[DCMAX], pre[DCMAX];
     unsigned par = 0u;
@@ -165,7 +174,8 @@ LDPC_HD void cn_spa_phi(const float (&v)[DCMAX], int dc, float (&out)[DCMAX])
 #pragma unroll
     for (int k = 0; k < DCMAX; ++k)
         if (k < dc) {
-            a[k] = phi_f32(fabsf(v[k]));
+            const float av = fabsf(v[k]);
+            a[k] = (av > sat_llr) ? 0.0f : phi_f32(av);
             par ^= (v[k] < 0.0f) ? 1u : 0u;
             pre[k] = run;
             run += a[k];
