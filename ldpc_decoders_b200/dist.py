@@ -1,0 +1,84 @@
+"""Multi-GPU plumbing: one process per GPU, frames sharded, counters all-reduced.
+
+Frames are independent, so there is no data-path collective.  The only exchanges are
+  * all_gather of the per-frame (bit errors, iteration count) of a round, so that every rank can apply the
+    reference's sequential stopping rule `while wec < min_wec` (src/main.py:37) to the GLOBAL frame order, and
+  * all_reduce(SUM) of Monte-Carlo counters.
+Backend: NCCL over NVLink when the process group lives on GPUs, gloo in the CPU tests.
+"""
+import os
+
+import numpy as np
+
+
+class Comm:
+    """Thin wrapper over torch.distributed that also works as a 1-rank no-op."""
+
+    def __init__(self, backend=None):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        self.device = "cpu"
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            if backend is None:
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+            if not dist.is_initialized():
+                if backend == "nccl":
+                    torch.cuda.set_device(self.local_rank)
+                    dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+                else:
+                    dist.init_process_group(backend)
+            self.dist = dist
+            self.device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+
+    def allreduce_sum(self, counters):
+        """int64 numpy vector -> element-wise sum over ranks."""
+        counters = np.asarray(counters, np.int64)
+        if self.dist is None:
+            return counters.copy()
+        import torch
+        t = torch.from_numpy(counters.copy()).to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def allgather(self, arr):
+        """Equal-length numpy vector per rank -> [world, len] in rank order."""
+        arr = np.ascontiguousarray(arr)
+        if self.dist is None:
+            return arr[None, :].copy()
+        import torch
+        t = torch.from_numpy(arr.copy()).to(self.device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return np.stack([o.cpu().numpy() for o in out])
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def close(self):
+        if self.dist is not None and self.dist.is_initialized():
+            self.dist.destroy_process_group()
+            self.dist = None
+
+
+def round_slice(round_idx, rank, world, batch):
+    """Global frame indices of `rank` in round `round_idx`: rounds of world*batch frames, rank-major inside a
+    round: g in [k*R*B + r*B, k*R*B + (r+1)*B)."""
+    g0 = (round_idx * world + rank) * batch
+    return g0, g0 + batch
+
+
+def sequential_stop(bit_errs_global, wec_so_far, min_wec):
+    """The reference counts frames one by one and stops as soon as `wec >= min_wec` (src/main.py:37-45).
+    Given the bit-error counts of the next frames in GLOBAL order, return how many of them are consumed."""
+    we = np.asarray(bit_errs_global) > 0
+    need = min_wec - wec_so_far
+    if need <= 0:
+        return 0
+    c = np.cumsum(we)
+    hit = np.flatnonzero(c >= need)
+    return int(hit[0]) + 1 if hit.size else int(we.size)

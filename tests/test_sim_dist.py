@@ -1,0 +1,129 @@
+"""CPU tier: host-side logic of the batched driver and the multi-process path (gloo, world_size 2).
+
+The decode function injected here is the oracle (tests may use it as a stand-in checker); the product's
+decoders need a GPU and are covered by tests/test_gpu_parity.py / test_gpu_sim.py.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import _golden as G
+from ldpc_decoders_b200 import dist, sim
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_round_slices_tile_the_frame_axis():
+    seen = []
+    for rnd in range(3):
+        for r in range(4):
+            g0, g1 = dist.round_slice(rnd, r, 4, 5)
+            seen.extend(range(g0, g1))
+    assert seen == list(range(60))
+
+
+def test_sequential_stop_matches_frame_by_frame_loop():
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        errs = rng.binomial(3, .2, size=rng.randint(1, 40))
+        wec0, min_wec = rng.randint(0, 5), rng.randint(1, 8)
+        wec, used = wec0, 0
+        for e in errs:                      # the reference's loop, src/main.py:37-45
+            if wec >= min_wec:
+                break
+            wec += e > 0
+            used += 1
+        assert dist.sequential_stop(errs, wec0, min_wec) == used
+
+
+def oracle_decoder(name, snr):
+    g = O.Graph(*G.code_tables(name))
+    def decode_batch(Y):
+        r = O.bp_decode(g, O.MSA, O.llr_biawgn(snr, Y), max_iter=10, nthreads=2)
+        return r["x_hat"], r["iters"]
+    return g, decode_batch
+
+
+def test_run_param_reproduces_the_sequential_reference_loop():
+    """Batched + stopping rule == decoding the same RNG stream one frame at a time (what main.test does)."""
+    name, snr, min_wec = "512_3_6_rand_ldpc_1", 1.5, 7
+    g, decode_batch = oracle_decoder(name, snr)
+    x = np.ones(g.n, np.int64)
+    std = np.sqrt(10 ** (-snr / 10))
+    send = lambda X: (2 * X - 1) + np.random.normal(0, std, X.shape)
+    np.random.seed(3)
+    tot = wec = bec = 0
+    while wec < min_wec:                                  # src/main.py:37-45
+        y = send(x)
+        x_hat, _ = decode_batch(y[None, :])
+        e = int((x_hat[0] != x).sum())
+        wec += e > 0; bec += e; tot += 1
+    for batch in (1, 4, 16):
+        np.random.seed(3)
+        r = sim.run_param(decode_batch, send, x, dist.Comm(), batch, min_wec)
+        assert (r["tot"], r["wec"], r["bec"]) == (tot, wec, bec), batch
+        assert sum(r["dec"]["iter"]) == tot
+
+
+def test_saver_schema_matches_reference(tmp_path):
+    ids = [("channel", "biawgn"), ("code", "c"), ("decoder", "MSA"), ("codeword", 1), ("min_wec", 100), ("max_iter", 10)]
+    s = sim.Saver(str(tmp_path), ids)
+    s.add(2.0, dict(tot=10, wec=1, wer=.1, bec=3, ber=.001))
+    s.add(2.5, dict(tot=20, wec=1, wer=.05, bec=2, ber=.0005))
+    s.add(2.0, dict(tot=11, wec=2, wer=.2, bec=4, ber=.002))
+    assert os.path.basename(s.file_path) == "biawgn-c-MSA-1-100-10.json"
+    d = json.load(open(s.file_path))
+    assert list(d)[:6] == [k for k, _ in ids]
+    assert d["tot"] == {"2.0": 11, "2.5": 20} and d["wer"]["2.5"] == .05
+
+
+WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import _golden as G
+from ldpc_decoders_b200 import dist, sim
+from oracle import oracle as O
+comm = dist.Comm("gloo")
+g = O.Graph(*G.code_tables("512_3_6_rand_ldpc_1"))
+snr = 1.5
+def decode_batch(Y):
+    r = O.bp_decode(g, O.MSA, O.llr_biawgn(snr, Y), max_iter=10)
+    return r["x_hat"], r["iters"]
+x = np.ones(g.n, np.int64)
+std = np.sqrt(10 ** (-snr / 10))
+send = lambda X: (2 * X - 1) + np.random.normal(0, std, X.shape)
+np.random.seed(3)
+r = sim.run_param(decode_batch, send, x, comm, 4, 7)
+tot = comm.allreduce_sum(np.array([r["tot"], comm.rank]))
+if comm.rank == 0:
+    print("RESULT " + json.dumps(dict(tot=r["tot"], wec=r["wec"], bec=r["bec"], sum_tot=int(tot[0]), ranks=int(tot[1]))))
+comm.close()
+'''
+
+
+def test_two_process_gloo_run_matches_single_process(tmp_path):
+    name, snr, min_wec = "512_3_6_rand_ldpc_1", 1.5, 7
+    g, decode_batch = oracle_decoder(name, snr)
+    x = np.ones(g.n, np.int64)
+    std = np.sqrt(10 ** (-snr / 10))
+    send = lambda X: (2 * X - 1) + np.random.normal(0, std, X.shape)
+    np.random.seed(3)
+    ref = sim.run_param(decode_batch, send, x, dist.Comm(), 8, min_wec)
+
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][0]
+    r = json.loads(line[7:])
+    assert (r["tot"], r["wec"], r["bec"]) == (ref["tot"], ref["wec"], ref["bec"])
+    assert r["sum_tot"] == 2 * ref["tot"] and r["ranks"] == 1      # all_reduce(SUM) over 2 ranks
