@@ -254,6 +254,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=32768, help="frames per step per GPU")
+    ap.add_argument("--flags", type=int, default=0, help="ldpc_decode flags (8 = register-staged check-node sweep)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -293,7 +294,8 @@ def main():
     res = {}
 
     def step():
-        res["o"] = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, y, max_iter=MAX_ITER, out=res.get("o"))
+        res["o"] = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, y, max_iter=MAX_ITER, out=res.get("o"),
+                                             flags=args.flags)
 
     launches0 = None
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -347,7 +349,8 @@ def main():
     xh, ith, rsh = pinned_empty((B, tab.n), np.uint8), pinned_empty((B,), np.int32), pinned_empty((B,), np.uint8)
 
     def e2e_step():
-        eng.decode_host(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, Yh, max_iter=MAX_ITER, x_hat=xh, iters=ith, reason=rsh)
+        eng.decode_host(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, Yh, max_iter=MAX_ITER, x_hat=xh, iters=ith, reason=rsh,
+                        flags=args.flags)
 
     for _ in range(2):
         e2e_step()

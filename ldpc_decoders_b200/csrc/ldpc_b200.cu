@@ -12,6 +12,7 @@
 #include "io_kernels.cuh"
 #include "stream_bec.cuh"
 #include "stream_bp.cuh"
+#include "stream_bp_tma.cuh"
 
 using namespace ldpc;
 
@@ -68,7 +69,8 @@ template <typename T> struct Fpt;
 template <> struct Fpt<float> { static constexpr int value = 4; };
 template <> struct Fpt<double> { static constexpr int value = 2; };
 
-inline int frames_per_group(int dtype) { return dtype == LDPC_F64 ? 64 : 128; }
+inline int frames_per_group(int dtype) { return dtype == LDPC_F64 ? 64 : 128; }     // one warp of the register sweeps
+inline int frames_per_tile(int dtype) { return dtype == LDPC_F64 ? 256 : 512; }     // one CTA tile of cn_sweep_tma (2 KB rows)
 inline size_t elem_size(int dtype) { return dtype == LDPC_F64 ? 8 : 4; }
 
 // Grid for a sweep: x = frame tiles of 8 groups, y = chunks of checks / variables, >= ~16 CTAs per SM.
@@ -95,8 +97,8 @@ struct BpLayout {
 BpLayout bp_layout(const Tables &t, int dtype, int B, bool want_marg)
 {
     BpLayout L;
-    const int G = frames_per_group(dtype);
-    L.Bp = (B + G - 1) / G * G;
+    const int G = frames_per_group(dtype), TF = frames_per_tile(dtype);
+    L.Bp = (B + TF - 1) / TF * TF;
     L.wpr = L.Bp / 32;
     L.ngroups = L.Bp / G;
     const size_t es = elem_size(dtype);
@@ -135,11 +137,41 @@ BecLayout bec_layout(const Tables &t, int B)
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch by degree profile
 // ------------------------------------------------------------------------------------------------
+template <typename KernelT> int opt_in_smem(ldpc_t *h, KernelT kern, size_t bytes)
+{
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(h, LDPC_ECUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
+    return LDPC_OK;
+}
+
+// Check-node sweep: bulk-async staged kernel for check degrees <= 8, register kernel otherwise / on request.
 template <typename T, int ALGO>
-int launch_cn(ldpc_t *h, const BpParams<T> &p, dim3 grid, cudaStream_t s)
+int launch_cn(ldpc_t *h, BpParams<T> p, bool tma, cudaStream_t s)
 {
     constexpr int FPT = Fpt<T>::value;
     const Tables &t = h->t;
+    if (tma && t.max_dc <= 8) {
+        const int gx = p.Bp / (kTmaThreads * FPT);
+        int gy = std::max(1, std::min(t.m, (h->sm_count * 8) / std::max(1, gx)));
+        p.per_cta = (t.m + gy - 1) / gy;
+        gy = (t.m + p.per_cta - 1) / p.per_cta;
+        const dim3 grid((unsigned)gx, (unsigned)gy, 1);
+#define CN_TMA(DC, UNI)                                                                             \
+        do {                                                                                        \
+            auto kern = cn_sweep_tma<T, FPT, ALGO, DC, UNI>;                                        \
+            static bool ready = false;                                                              \
+            if (!ready) { int rc_ = opt_in_smem(h, kern, tma_smem_bytes<DC>()); if (rc_) return rc_; ready = true; } \
+            kern<<<grid, kTmaThreads, tma_smem_bytes<DC>(), s>>>(p);                                \
+            h->launches++;                                                                          \
+        } while (0)
+        if (t.uni_dc == 4) CN_TMA(4, true);
+        else if (t.uni_dc == 6) CN_TMA(6, true);
+        else if (t.uni_dc == 8) CN_TMA(8, true);
+        else CN_TMA(8, false);
+#undef CN_TMA
+        return LDPC_OK;
+    }
+    const dim3 grid = sweep_grid(h, p.ngroups, t.m, &p.per_cta);
 #define CN_CASE(DC, UNI) LAUNCH(h, (cn_sweep<T, FPT, ALGO, DC, UNI>), grid, kCtaThreads, s, p)
     if (t.uni_dc == 4) CN_CASE(4, true);
     else if (t.uni_dc == 6) CN_CASE(6, true);
@@ -170,16 +202,16 @@ int launch_vn(ldpc_t *h, const BpParams<T> &p, dim3 grid, cudaStream_t s)
 }
 
 template <typename T>
-int launch_cn_algo(ldpc_t *h, int algo, const BpParams<T> &p, dim3 grid, cudaStream_t s);
+int launch_cn_algo(ldpc_t *h, int algo, const BpParams<T> &p, bool tma, cudaStream_t s);
 template <>
-int launch_cn_algo<float>(ldpc_t *h, int algo, const BpParams<float> &p, dim3 grid, cudaStream_t s)
+int launch_cn_algo<float>(ldpc_t *h, int algo, const BpParams<float> &p, bool tma, cudaStream_t s)
 {
-    return algo == LDPC_MSA ? launch_cn<float, ALGO_MSA>(h, p, grid, s) : launch_cn<float, ALGO_SPA_PHI>(h, p, grid, s);
+    return algo == LDPC_MSA ? launch_cn<float, ALGO_MSA>(h, p, tma, s) : launch_cn<float, ALGO_SPA_PHI>(h, p, tma, s);
 }
 template <>
-int launch_cn_algo<double>(ldpc_t *h, int algo, const BpParams<double> &p, dim3 grid, cudaStream_t s)
+int launch_cn_algo<double>(ldpc_t *h, int algo, const BpParams<double> &p, bool tma, cudaStream_t s)
 {
-    return algo == LDPC_MSA ? launch_cn<double, ALGO_MSA>(h, p, grid, s) : launch_cn<double, ALGO_SPA_REF>(h, p, grid, s);
+    return algo == LDPC_MSA ? launch_cn<double, ALGO_MSA>(h, p, tma, s) : launch_cn<double, ALGO_SPA_REF>(h, p, tma, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -294,10 +326,11 @@ template <typename U> int grow(ldpc_t *h, U **ptr, size_t *cap, size_t need)
 template <typename T>
 int decode_bp_stream(ldpc_t *h, int algo, const InSpec &in, int B, int max_iter, int iter_cap,
                      uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *marg_out,
-                     void *ws, size_t ws_bytes, cudaStream_t s)
+                     void *ws, size_t ws_bytes, unsigned flags, cudaStream_t s)
 {
     const Tables &t = h->t;
     const int dtype = sizeof(T) == 8 ? LDPC_F64 : LDPC_F32;
+    const bool tma = (flags & LDPC_CN_REGISTER) == 0;
     const BpLayout L = bp_layout(t, dtype, B, marg_out != nullptr);
     if (ws_bytes < L.bytes) return fail(h, LDPC_EWORKSPACE, "workspace too small");
     if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0) return fail(h, LDPC_EWORKSPACE, "workspace must be 256-byte aligned");
@@ -327,8 +360,7 @@ int decode_bp_stream(ldpc_t *h, int algo, const InSpec &in, int B, int max_iter,
     }
     LAUNCH(h, init_flags, (L.Bp + 255) / 256, 256, s, p.act, p.unsat, p.iters, B, L.Bp, L.wpr, have_hard ? 0 : 1);
 
-    int cpc = 1, vpc = 1;
-    const dim3 cgrid = sweep_grid(h, L.ngroups, t.m, &cpc);
+    int vpc = 1;
     const dim3 vgrid = sweep_grid(h, L.ngroups, t.n, &vpc);
     const int book_blocks = (L.wpr * 32 + 255) / 256;
     const bool poll = (max_iter <= 0) || (limit > 32);
@@ -342,9 +374,8 @@ int decode_bp_stream(ldpc_t *h, int algo, const InSpec &in, int B, int max_iter,
     for (int it = 0; it < limit; ++it) {
         p.first = (it == 0);
         p.skip_syn = (it == 0 && !have_hard);
-        p.per_cta = cpc;
         ProfEvent *pe = prof_begin(h, 0, s);
-        rc = launch_cn_algo<T>(h, algo, p, cgrid, s);
+        rc = launch_cn_algo<T>(h, algo, p, tma, s);
         prof_end(pe, s);
         if (rc) return rc;
         const bool poll_now = poll && it >= 8 && (it % 8) == 0;
@@ -480,9 +511,9 @@ int decode_any(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_
     if (algo != LDPC_MSA && algo != LDPC_SPA) return fail(h, LDPC_EINVAL, "bad algo");
     if (in.channel == LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "MSA/SPA cannot take BEC symbols");
     if (dtype == LDPC_F32)
-        return decode_bp_stream<float>(h, algo, in, B, max_iter, iter_cap, x_hat, iters, reason, marg_out, ws, ws_bytes, s);
+        return decode_bp_stream<float>(h, algo, in, B, max_iter, iter_cap, x_hat, iters, reason, marg_out, ws, ws_bytes, flags, s);
     if (dtype == LDPC_F64)
-        return decode_bp_stream<double>(h, algo, in, B, max_iter, iter_cap, x_hat, iters, reason, marg_out, ws, ws_bytes, s);
+        return decode_bp_stream<double>(h, algo, in, B, max_iter, iter_cap, x_hat, iters, reason, marg_out, ws, ws_bytes, flags, s);
     return fail(h, LDPC_EINVAL, "bad dtype");
 }
 
@@ -528,8 +559,7 @@ static int debug_step_t(ldpc_t *h, int algo, int which, int B, const void *prior
     LAUNCH(h, init_flags, (L.Bp + 255) / 256, 256, s, p.act, p.unsat, p.iters, B, L.Bp, L.wpr, 1);
     int rc;
     if (which == 0) {
-        const dim3 grid = sweep_grid(h, L.ngroups, t.m, &p.per_cta);
-        rc = launch_cn_algo<T>(h, algo, p, grid, s);
+        rc = launch_cn_algo<T>(h, algo, p, true, s);
         if (rc) return rc;
     } else {
         if (!prior_in) return fail(h, LDPC_EINVAL, "variable-node step needs priors");

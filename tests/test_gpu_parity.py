@@ -311,6 +311,24 @@ def test_device_and_host_entry_points_agree(mods):
     assert (pri.cpu().numpy() == ref).all()
 
 
+def test_register_and_bulk_async_check_node_sweeps_agree(mods):
+    """Both stagings of the check-node sweep (cn_sweep_tma, default; cn_sweep, LDPC_CN_REGISTER) run the same
+    arithmetic: identical words, iteration counts and marginals, all decoders and dtypes."""
+    torch, lib = mods["torch"], mods["lib"]
+    for code in ("1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_10", "7_4_hamming"):
+        tab = tables(mods, code)
+        eng = mods["engine"].engine_for(tab)
+        Y = G.channel_send("biawgn", 2.0, np.zeros((700, tab.n), np.int64), 21)
+        for algo in (lib.MSA, lib.SPA):
+            for dt in (np.float32, np.float64):
+                pri = torch.from_numpy(O.llr_biawgn(2.0, Y).astype(dt)).cuda()
+                a = eng.decode_device(algo, pri, max_iter=10, want_marg=True)
+                a = {k: v.clone() for k, v in a.items()}
+                b = eng.decode_device(algo, pri, max_iter=10, want_marg=True, flags=lib.CN_REGISTER)
+                assert bool((a["iters"] == b["iters"]).all()) and bool((a["x_hat"] == b["x_hat"]).all())
+                assert bool(((a["marg"] == b["marg"]) | (a["marg"].isnan() & b["marg"].isnan())).all())
+
+
 # --------------------------------------------------------------------------------------------- size-independent properties
 def test_sign_symmetry_at_full_batch(mods):
     """All-ones is a codeword of a (3,6) code, so flipping the sign of every prior must flip every decoded
