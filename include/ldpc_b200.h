@@ -73,6 +73,9 @@ extern "C" {
 #define LDPC_PATH_STREAMING 1u   /* edge-major [E][B] messages in HBM, one CN + one VN sweep per iteration */
 #define LDPC_PATH_RESIDENT  2u   /* whole frames kept in shared memory for all iterations (short codes) */
 #define LDPC_PATH_MASK      3u
+#define LDPC_SPA_ROBUST     4u   /* float32 SPA: do not emulate the reference's float64 tanh saturation (|v| > 38.123
+                                    contributes exactly 0, which is what floods a frame with inf/NaN in the reference);
+                                    honoured by the resident path */
 #define LDPC_CN_REGISTER    8u   /* streaming path: use the register-staged check-node sweep instead of the
                                     bulk-async (TMA) staged one (A/B measurements; it is also the fallback for
                                     check degrees > 8) */

@@ -10,6 +10,7 @@ MSA, SPA, BEC = 0, 1, 2
 F32, F64 = 0, 1
 CH_PRIORS, CH_BSC, CH_BIAWGN, CH_BEC = 0, 1, 2, 3
 PATH_AUTO, PATH_STREAMING, PATH_RESIDENT = 0, 1, 2
+SPA_ROBUST = 4
 CN_REGISTER = 8
 REASONS = {0: "decoded", 1: "maximum", 2: "stopping", 4: "cap"}
 

@@ -15,6 +15,8 @@ constexpr int kCtaWarps = 8;                 // CN / VN sweeps: 8 warps = 8 fram
 constexpr int kCtaThreads = kCtaWarps * 32;
 constexpr unsigned kFull = 0xffffffffu;
 
+enum { ALGO_MSA = 0, ALGO_SPA_REF = 1, ALGO_SPA_PHI = 2 };      // check-node arithmetic variants (ldpc_math.cuh)
+
 // Device copies of the graph tables (edge order = np.where(H), /root/reference/src/bpa.py:12).
 struct Tables {
     int n = 0, m = 0, E = 0;
@@ -26,6 +28,14 @@ struct Tables {
 }  // namespace ldpc
 
 struct HostStage;                            // ldpc_decode_host staging (api file)
+
+struct ResidentInfo {                        // compact tables of the on-chip path (resident_bp.cuh)
+    bool ok = false;
+    uint16_t *cvar = nullptr, *vpos = nullptr;
+    uint8_t *cdeg = nullptr, *vdeg = nullptr;
+    int S = 0, DCP = 0, DVP = 0, F = 0, threads = 0;
+    size_t smem = 0;
+};
 
 struct ProfEvent {                           // one timed launch (ldpc_profile_*)
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -40,6 +50,7 @@ struct ldpc_handle {
     std::string err;
     unsigned long long launches = 0;
     HostStage *stage = nullptr;
+    ResidentInfo res;
     bool prof = false;
     std::vector<ProfEvent> prof_ev;
     size_t prof_used = 0;

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "io_kernels.cuh"
+#include "resident_bp.cuh"
 #include "stream_bec.cuh"
 #include "stream_bp.cuh"
 #include "stream_bp_tma.cuh"
@@ -493,6 +494,129 @@ int decode_bec_stream(ldpc_t *h, const uint8_t *y, int B, int max_iter, int iter
     return check_launch(h, "decode_bec_stream");
 }
 
+// ------------------------------------------------------------------------------------------------
+// resident (on-chip) BP decode for short codes
+// ------------------------------------------------------------------------------------------------
+template <int ALGO, int F, int DCP, int DVP>
+int launch_resident_t(ldpc_t *h, const ResParams &rp, int grid, cudaStream_t s)
+{
+    auto kern = resident_bp<ALGO, F, DCP, DVP>;
+    static bool ready = false;
+    if (!ready) {
+        int rc = opt_in_smem(h, kern, h->res.smem);
+        if (rc) return rc;
+        ready = true;
+    }
+    kern<<<grid, h->res.threads, h->res.smem, s>>>(rp);
+    h->launches++;
+    return LDPC_OK;
+}
+
+template <int ALGO>
+int launch_resident(ldpc_t *h, const ResParams &rp, int grid, cudaStream_t s)
+{
+    const ResidentInfo &r = h->res;
+#define RES_CASE(FF, DC, DV) if (r.F == FF && r.DCP == DC && r.DVP == DV) return launch_resident_t<ALGO, FF, DC, DV>(h, rp, grid, s)
+    RES_CASE(8, 8, 4); RES_CASE(8, 8, 8); RES_CASE(8, 4, 4); RES_CASE(8, 4, 8);
+    RES_CASE(4, 8, 4); RES_CASE(4, 8, 8); RES_CASE(4, 4, 4); RES_CASE(4, 4, 8);
+#undef RES_CASE
+    return fail(h, LDPC_EUNSUPPORTED, "no resident kernel for this degree profile");
+}
+
+bool resident_eligible(const ldpc_t *h, int algo, int dtype, const void *marg_out)
+{
+    return h->res.ok && dtype == LDPC_F32 && (algo == LDPC_MSA || algo == LDPC_SPA) && marg_out == nullptr;
+}
+
+int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_iter, int iter_cap,
+                       uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *ws, size_t ws_bytes,
+                       unsigned flags, cudaStream_t s)
+{
+    const Tables &t = h->t;
+    const ResidentInfo &r = h->res;
+    if (ws_bytes < 256) return fail(h, LDPC_EWORKSPACE, "workspace too small");
+    const int limit = max_iter > 0 ? max_iter : iter_cap;
+    if (limit <= 0) return fail(h, LDPC_EINVAL, "max_iter <= 0 (unlimited in the reference) needs iter_cap > 0");
+    ResParams rp;
+    rp.n = t.n; rp.m = t.m; rp.S = r.S;
+    rp.cvar = r.cvar; rp.vpos = r.vpos; rp.cdeg = r.cdeg; rp.vdeg = r.vdeg;
+    rp.src = in.src;
+    rp.y_hard = in.y_hard;
+    rp.param = in.param;
+    rp.in_f64 = (in.in_dtype == LDPC_F64) ? 1 : 0;
+    switch (in.channel) {
+    case LDPC_CH_PRIORS: rp.in_mode = IN_COPY; break;
+    case LDPC_CH_BSC: rp.in_mode = IN_BSC; break;
+    case LDPC_CH_BIAWGN: rp.in_mode = IN_BIAWGN; break;
+    default: return fail(h, LDPC_EINVAL, "bad channel for MSA/SPA");
+    }
+    rp.B = B; rp.limit = limit;
+    rp.bound_reason = max_iter > 0 ? LDPC_REASON_MAXIMUM : LDPC_REASON_CAP;
+    rp.sat_llr = (flags & LDPC_SPA_ROBUST) ? INFINITY : kSpaSatLlr;
+    rp.x_hat = x_hat; rp.iters = iters; rp.reason = reason;
+    rp.counter = static_cast<int *>(ws);
+    CUDA_TRY(h, cudaMemsetAsync(rp.counter, 0, sizeof(int), s));
+    const int batches = (B + r.F - 1) / r.F;
+    const int grid = std::min(h->sm_count, batches);
+    ProfEvent *pe = prof_begin(h, 0, s);
+    int rc = (algo == LDPC_MSA) ? launch_resident<ALGO_MSA>(h, rp, grid, s) : launch_resident<ALGO_SPA_PHI>(h, rp, grid, s);
+    prof_end(pe, s);
+    if (rc) return rc;
+    return check_launch(h, "decode_bp_resident");
+}
+
+// Compact uint16 tables + the geometry of the resident kernel; leaves res.ok = false when the code does not fit.
+int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, const int32_t *var_ptr, const int32_t *var_edges)
+{
+    const Tables &t = h->t;
+    ResidentInfo &r = h->res;
+    if (t.max_dc > 8 || t.max_dv > 8 || t.max_dc < 1 || t.n > 65535) return LDPC_OK;
+    r.S = t.max_dc | 1;
+    if ((long long)t.m * r.S > 65535) return LDPC_OK;
+    r.DCP = t.max_dc <= 4 ? 4 : 8;
+    r.DVP = t.max_dv <= 4 ? 4 : 8;
+    const size_t budget = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
+    r.F = 0;
+    for (int F : {8, 4}) {
+        const size_t need = resident_smem_bytes(t.n, t.m, r.S, F, r.DCP, r.DVP);
+        if (need <= budget) { r.F = F; r.smem = need; break; }
+    }
+    if (r.F == 0) return LDPC_OK;
+    const int Q = r.F / 4;
+    const int items = t.m * Q;
+    const int passes = (items + kResMaxThreads - 1) / kResMaxThreads;
+    int T = (items + passes - 1) / passes;
+    T = std::max(64, (T + 31) / 32 * 32);
+    r.threads = std::min(T, kResMaxThreads);
+
+    std::vector<uint16_t> cvar((size_t)t.m * r.DCP, 0), vpos((size_t)t.n * r.DVP, 0);
+    std::vector<uint8_t> cdeg((size_t)t.m), vdeg((size_t)t.n);
+    std::vector<int> row_of_edge((size_t)t.E);
+    for (int c = 0; c < t.m; ++c) {
+        cdeg[c] = (uint8_t)(chk_ptr[c + 1] - chk_ptr[c]);
+        for (int e = chk_ptr[c], k = 0; e < chk_ptr[c + 1]; ++e, ++k) {
+            cvar[(size_t)c * r.DCP + k] = (uint16_t)edge_var[e];
+            row_of_edge[e] = c * r.S + k;
+        }
+    }
+    for (int v = 0; v < t.n; ++v) {
+        vdeg[v] = (uint8_t)(var_ptr[v + 1] - var_ptr[v]);
+        for (int p0 = var_ptr[v], k = 0; p0 < var_ptr[v + 1]; ++p0, ++k)
+            vpos[(size_t)v * r.DVP + k] = (uint16_t)row_of_edge[var_edges[p0]];
+    }
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e;
+    if ((e = up((void **)&r.cvar, cvar.data(), cvar.size() * 2)) != cudaSuccess || (e = up((void **)&r.vpos, vpos.data(), vpos.size() * 2)) != cudaSuccess ||
+        (e = up((void **)&r.cdeg, cdeg.data(), cdeg.size())) != cudaSuccess || (e = up((void **)&r.vdeg, vdeg.data(), vdeg.size())) != cudaSuccess)
+        return fail(nullptr, LDPC_ECUDA, std::string("resident table upload: ") + cudaGetErrorString(e));
+    r.ok = true;
+    return LDPC_OK;
+}
+
 int decode_any(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_iter, int iter_cap,
                uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *marg_out,
                void *ws, size_t ws_bytes, unsigned flags, cudaStream_t s)
@@ -500,16 +624,21 @@ int decode_any(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_
     if (!h) return LDPC_EINVAL;
     if (B <= 0) return fail(h, LDPC_EINVAL, "B must be positive");
     if (!in.src || !x_hat || !iters || !ws) return fail(h, LDPC_EINVAL, "null buffer");
-    if ((flags & LDPC_PATH_MASK) == LDPC_PATH_RESIDENT)
-        return fail(h, LDPC_EUNSUPPORTED, "resident path is not built into this version");
+    const unsigned path = flags & LDPC_PATH_MASK;
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (algo == LDPC_BEC) {
         if (in.channel != LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "BEC decoder needs symbol input");
         if (marg_out) return fail(h, LDPC_EINVAL, "marg_out is MSA/SPA only");
+        if (path == LDPC_PATH_RESIDENT) return fail(h, LDPC_EUNSUPPORTED, "BEC has no resident path");
         return decode_bec_stream(h, (const uint8_t *)in.src, B, max_iter, iter_cap, x_hat, iters, reason, ws, ws_bytes, s);
     }
     if (algo != LDPC_MSA && algo != LDPC_SPA) return fail(h, LDPC_EINVAL, "bad algo");
     if (in.channel == LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "MSA/SPA cannot take BEC symbols");
+    const bool res_ok = resident_eligible(h, algo, dtype, marg_out);
+    if (path == LDPC_PATH_RESIDENT && !res_ok)
+        return fail(h, LDPC_EUNSUPPORTED, "resident path needs float32 MSA/SPA, no marg_out, degrees <= 8 and a code that fits in shared memory");
+    if (path == LDPC_PATH_RESIDENT || (path == LDPC_PATH_AUTO && res_ok))
+        return decode_bp_resident(h, algo, in, B, max_iter, iter_cap, x_hat, iters, reason, ws, ws_bytes, flags, s);
     if (dtype == LDPC_F32)
         return decode_bp_stream<float>(h, algo, in, B, max_iter, iter_cap, x_hat, iters, reason, marg_out, ws, ws_bytes, flags, s);
     if (dtype == LDPC_F64)
@@ -651,6 +780,11 @@ int ldpc_create(ldpc_t **out, int device, int n, int m, int E,
         ldpc_destroy(h);
         return fail(nullptr, LDPC_ECUDA, msg);
     }
+    if (build_resident(h, chk_ptr, edge_var, var_ptr, var_edges) != LDPC_OK) {
+        const std::string msg = g_create_error;
+        ldpc_destroy(h);
+        return fail(nullptr, LDPC_ECUDA, msg);
+    }
     *out = h;
     return LDPC_OK;
 }
@@ -705,6 +839,10 @@ void ldpc_destroy(ldpc_t *h)
         if (h->stage->h_flag) cudaFreeHost(h->stage->h_flag);
         delete h->stage;
     }
+    if (h->res.cvar) cudaFree(h->res.cvar);
+    if (h->res.vpos) cudaFree(h->res.vpos);
+    if (h->res.cdeg) cudaFree(h->res.cdeg);
+    if (h->res.vdeg) cudaFree(h->res.vdeg);
     if (h->t.chk_ptr) cudaFree(h->t.chk_ptr);
     if (h->t.edge_var) cudaFree(h->t.edge_var);
     if (h->t.var_ptr) cudaFree(h->t.var_ptr);

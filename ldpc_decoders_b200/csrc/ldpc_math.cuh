@@ -89,6 +89,53 @@ LDPC_HD void cn_msa(const T (&v)[DCMAX], int dc, T (&out)[DCMAX])
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same min-sum rule for float32 on the IEEE bit patterns (fewer issue slots: integer min/max instead
+// of compare+select pairs).  For non-NaN inputs it is bit-identical to cn_msa<float>: magnitudes of
+// non-negative floats order like their bit patterns, "v < 0" is "bits > 0x80000000" (so -0.0 counts as
+// "+", math_utils.py:10,40), and the result's sign bit is par ^ own.  Used by the resident kernel, where
+// the check-node arithmetic (not HBM) is the limiter.
+// ---------------------------------------------------------------------------------------------
+LDPC_HD uint32_t f32_bits(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+LDPC_HD float bits_f32(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+template <int DCMAX>
+LDPC_HD void cn_msa_bits(const float (&v)[DCMAX], int dc, float (&out)[DCMAX])
+{
+    uint32_t m1 = 0x7f800000u, m2 = 0x7f800000u, par = 0u;
+#pragma unroll
+    for (int k = 0; k < DCMAX; ++k)
+        if (k < dc) {
+            const uint32_t b = f32_bits(v[k]), a = b & 0x7fffffffu;
+            par ^= (b > 0x80000000u) ? 0x80000000u : 0u;
+            const uint32_t hi = a > m1 ? a : m1;
+            m2 = m2 < hi ? m2 : hi;
+            m1 = m1 < a ? m1 : a;
+        }
+#pragma unroll
+    for (int k = 0; k < DCMAX; ++k)
+        if (k < dc) {
+            const uint32_t b = f32_bits(v[k]), a = b & 0x7fffffffu;
+            const uint32_t mag = (a == m1) ? m2 : m1;
+            const uint32_t sgn = par ^ ((b > 0x80000000u) ? 0x80000000u : 0u);
+            out[k] = bits_f32(mag | sgn);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Sum-product check node, formula mirror (float64 verification mode).
 //   t = tanh(v / 2); S = sum_k log|t_k| (ordered, from 0); P = (-1)^{#(t<0)} exp(S)
 //   q = P / t_k;  out = 2 * (|q| == 1 ? inf * q : atanh(q))

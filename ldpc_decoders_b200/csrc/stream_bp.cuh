@@ -37,7 +37,6 @@ template <typename T> struct BpParams {
     int skip_syn;                            // CN: do not evaluate the syndrome (iteration 0 without hard input)
 };
 
-enum { ALGO_MSA = 0, ALGO_SPA_REF = 1, ALGO_SPA_PHI = 2 };
 
 template <typename T, int ALGO, int DCMAX> struct CnMath;
 template <typename T, int DCMAX> struct CnMath<T, ALGO_MSA, DCMAX> {

@@ -28,6 +28,16 @@ template <typename T> void cn_msa_all(const G &g, const T *v2c, T *c2v)
         for (int k = 0; k < dc; ++k) c2v[e0 + k] = o[k];
     }
 }
+void cn_msa_bits_all(const G &g, const float *v2c, float *c2v)
+{
+    for (int c = 0; c < g.m; ++c) {
+        const int e0 = g.chk_ptr[c], dc = g.chk_ptr[c + 1] - e0;
+        float a[DMAX], o[DMAX];
+        for (int k = 0; k < dc; ++k) a[k] = v2c[e0 + k];
+        cn_msa_bits<DMAX>(a, dc, o);
+        for (int k = 0; k < dc; ++k) c2v[e0 + k] = o[k];
+    }
+}
 void cn_spa_ref_all(const G &g, const double *v2c, double *c2v)
 {
     for (int c = 0; c < g.m; ++c) {
@@ -69,6 +79,7 @@ void decode_bp(const G &g, int algo, const T *prior, const uint8_t *y_hard, int 
             if (!unsat) break;
         }
         if (algo == 0) cn_msa_all<T>(g, msg.data(), tmp.data());
+        else if (algo == 2) cn_msa_bits_all(g, (const float *)msg.data(), (float *)tmp.data());
         else if (sizeof(T) == 8) cn_spa_ref_all(g, (const double *)msg.data(), (double *)tmp.data());
         else cn_spa_phi_all(g, (const float *)msg.data(), (float *)tmp.data());
         for (int v = 0; v < g.n; ++v) {
@@ -106,6 +117,13 @@ int emu_bp_f32(int algo, int n, int m, int E, const int32_t *cp, const int32_t *
     for (int b = 0; b < B; ++b)
         decode_bp<float>(g, algo, priors + (size_t)b * n, y_hard ? y_hard + (size_t)b * n : nullptr, max_iter,
                          x_hat + (size_t)b * n, iters + b, marg ? marg + (size_t)b * n : nullptr);
+    return 0;
+}
+
+int emu_cn_msa_bits(int n, int m, int E, const int32_t *cp, const int32_t *ev, const float *v2c, float *c2v)
+{
+    G g{n, m, E, cp, ev, nullptr, nullptr};
+    cn_msa_bits_all(g, v2c, c2v);
     return 0;
 }
 

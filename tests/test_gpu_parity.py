@@ -311,6 +311,47 @@ def test_device_and_host_entry_points_agree(mods):
     assert (pri.cpu().numpy() == ref).all()
 
 
+@pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_10", "7_4_hamming",
+                                  "512_3_6_rand_ldpc_1", "margulis", "12_3_4_ldpc"])
+def test_resident_and_streaming_paths_agree(mods, code):
+    """The on-chip path (resident_bp, what LDPC_PATH_AUTO picks for short codes in float32) and the streaming
+    sweeps run the same arithmetic: identical words, iteration counts and exit reasons, for every front end."""
+    torch, lib = mods["torch"], mods["lib"]
+    tab = tables(mods, code)
+    eng = mods["engine"].engine_for(tab)
+    for B in (1, 13, 700):
+        Yg = G.channel_send("biawgn", 2.0, np.zeros((B, tab.n), np.int64), 77)
+        Yb = G.channel_send("bsc", .05, np.zeros((B, tab.n), np.int64), 78).astype(np.uint8)
+        for algo in (lib.MSA, lib.SPA):
+            for mi in (10, 3):
+                cases = [(lib.CH_BIAWGN, 10 ** (-2.0 / 10), torch.from_numpy(Yg.astype(np.float32)).cuda()),
+                         (lib.CH_BIAWGN, 10 ** (-2.0 / 10), torch.from_numpy(Yg).cuda()),
+                         (lib.CH_BSC, float(np.log(1 - .05) - np.log(.05)), torch.from_numpy(Yb).cuda())]
+                for ch, prm, y in cases:
+                    a = eng.decode_device_channel(ch, algo, lib.F32, prm, y, max_iter=mi, flags=lib.PATH_STREAMING)
+                    a = {k: (v.clone() if v is not None else None) for k, v in a.items()}
+                    n0 = eng.launch_count
+                    b = eng.decode_device_channel(ch, algo, lib.F32, prm, y, max_iter=mi, flags=lib.PATH_RESIDENT)
+                    assert eng.launch_count - n0 == 1                     # one kernel for the whole decode
+                    assert bool((a["iters"] == b["iters"]).all()) and bool((a["reason"] == b["reason"]).all())
+                    assert bool((a["x_hat"] == b["x_hat"]).all())
+    # priors + hard input through ldpc_decode, and unlimited iterations with a cap
+    pri = torch.from_numpy(O.llr_bsc(.05, Yb).astype(np.float32)).cuda()
+    a = eng.decode_device(lib.MSA, pri, y_hard=torch.from_numpy(Yb).cuda(), max_iter=0, iter_cap=17, flags=lib.PATH_STREAMING)
+    a = {k: (v.clone() if v is not None else None) for k, v in a.items()}
+    b = eng.decode_device(lib.MSA, pri, y_hard=torch.from_numpy(Yb).cuda(), max_iter=0, iter_cap=17, flags=lib.PATH_RESIDENT)
+    assert bool((a["iters"] == b["iters"]).all()) and bool((a["reason"] == b["reason"]).all()) and bool((a["x_hat"] == b["x_hat"]).all())
+
+
+def test_resident_path_is_refused_where_it_cannot_run(mods):
+    torch, lib = mods["torch"], mods["lib"]
+    from ldpc_decoders_b200 import LdpcError
+    eng = mods["engine"].engine_for(tables(mods, "1200_3_6_rand_ldpc_1"))
+    pri = torch.zeros((4, 1200), dtype=torch.float64, device="cuda")
+    with pytest.raises(LdpcError):
+        eng.decode_device(lib.MSA, pri, max_iter=3, flags=lib.PATH_RESIDENT)      # float64 has no resident kernel
+
+
 def test_register_and_bulk_async_check_node_sweeps_agree(mods):
     """Both stagings of the check-node sweep (cn_sweep_tma, default; cn_sweep, LDPC_CN_REGISTER) run the same
     arithmetic: identical words, iteration counts and marginals, all decoders and dtypes."""
@@ -322,9 +363,9 @@ def test_register_and_bulk_async_check_node_sweeps_agree(mods):
         for algo in (lib.MSA, lib.SPA):
             for dt in (np.float32, np.float64):
                 pri = torch.from_numpy(O.llr_biawgn(2.0, Y).astype(dt)).cuda()
-                a = eng.decode_device(algo, pri, max_iter=10, want_marg=True)
+                a = eng.decode_device(algo, pri, max_iter=10, want_marg=True, flags=lib.PATH_STREAMING)
                 a = {k: v.clone() for k, v in a.items()}
-                b = eng.decode_device(algo, pri, max_iter=10, want_marg=True, flags=lib.CN_REGISTER)
+                b = eng.decode_device(algo, pri, max_iter=10, want_marg=True, flags=lib.PATH_STREAMING | lib.CN_REGISTER)
                 assert bool((a["iters"] == b["iters"]).all()) and bool((a["x_hat"] == b["x_hat"]).all())
                 assert bool(((a["marg"] == b["marg"]) | (a["marg"].isnan() & b["marg"].isnan())).all())
 

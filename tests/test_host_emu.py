@@ -73,6 +73,27 @@ def test_bp_math_matches_oracle(emu, rec):
         assert same.all()
 
 
+@pytest.mark.parametrize("rec", [r for r in BP_RUNS if r["decoder"] == "MSA" and r["dtype"] == "f32"], ids=lambda r: r["key"])
+def test_msa_bit_pattern_variant_is_identical(emu, rec):
+    """cn_msa_bits (integer min/max on float32 bit patterns, used by the resident kernel) == cn_msa<float>."""
+    g = graph(rec["code"])
+    x, Y = G.run_inputs(rec)
+    Y = Y[:96]
+    if rec["channel"] == "bsc":
+        pri, yh = O.llr_bsc(rec["param"], Y.astype(np.uint8)).astype(np.float32), np.ascontiguousarray(Y, np.uint8)
+    else:
+        pri, yh = O.llr_biawgn(rec["param"], Y).astype(np.float32), None
+    ref = O.bp_decode(g, O.MSA, pri, y_hard=yh, max_iter=rec["max_iter"], want_marg=True)
+    x_hat, iters, marg = emu_bp(emu, g, 2, np.ascontiguousarray(pri), yh, rec["max_iter"])
+    assert (iters == ref["iters"]).all() and (x_hat == ref["x_hat"]).all() and (marg == ref["marg"]).all()
+    rng = np.random.RandomState(0)                        # zeros, negative zeros, ties, infinities
+    v = rng.choice(np.array([0.0, -0.0, 1.5, -1.5, 2.0, np.inf, -np.inf, 1e-38, -3.25], np.float32), size=g.E)
+    a = O.cn_sweep(g, O.MSA, v)
+    b = np.zeros_like(v)
+    emu.emu_cn_msa_bits(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(v), ptr(b))
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
+
+
 def test_spa_phi_f32_teacher_forced(emu):
     """float32 phi-domain check node vs the float64 reference formula on the same (f32-rounded) inputs:
     |d| <= 1e-4 * max(1,|ref|) for |ref| < 20 (north_star tolerance); sign + large magnitude beyond."""
