@@ -17,7 +17,7 @@ REASONS = {0: "decoded", 1: "maximum", 2: "stopping", 4: "cap"}
 # every symbol include/ldpc_b200.h declares
 SYMBOLS = ("ldpc_abi_version", "ldpc_create", "ldpc_destroy", "ldpc_last_error", "ldpc_workspace_bytes",
            "ldpc_decode", "ldpc_decode_channel", "ldpc_llr_bsc", "ldpc_llr_biawgn", "ldpc_debug_step", "ldpc_decode_host",
-           "ldpc_launch_count", "ldpc_profile_enable", "ldpc_profile_read")
+           "ldpc_launch_count", "ldpc_profile_enable", "ldpc_profile_read", "ldpc_resident_frames")
 
 
 class LdpcError(RuntimeError):
@@ -64,6 +64,8 @@ def load():
     L.ldpc_profile_read.restype = i32
     L.ldpc_profile_read.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_ulonglong),
                                     ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_ulonglong)]
+    L.ldpc_resident_frames.restype = i32
+    L.ldpc_resident_frames.argtypes = [vp]
     L.ldpc_launch_count.restype = ctypes.c_ulonglong
     L.ldpc_launch_count.argtypes = [vp]
     if L.ldpc_abi_version() != 1:

@@ -501,11 +501,11 @@ template <int ALGO, int F, int DCP, int DVP>
 int launch_resident_t(ldpc_t *h, const ResParams &rp, int grid, cudaStream_t s)
 {
     auto kern = resident_bp<ALGO, F, DCP, DVP>;
-    static bool ready = false;
-    if (!ready) {
+    static size_t opted = 0;               // the attribute is per kernel instance: raise it when a larger code comes along
+    if (h->res.smem > opted) {
         int rc = opt_in_smem(h, kern, h->res.smem);
         if (rc) return rc;
-        ready = true;
+        opted = h->res.smem;
     }
     kern<<<grid, h->res.threads, h->res.smem, s>>>(rp);
     h->launches++;
@@ -713,6 +713,8 @@ int ldpc_abi_version(void) { return LDPC_ABI_VERSION; }
 const char *ldpc_last_error(const ldpc_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 unsigned long long ldpc_launch_count(const ldpc_t *h) { return h ? h->launches : 0ull; }
+
+int ldpc_resident_frames(const ldpc_t *h) { return (h && h->res.ok) ? h->res.F : 0; }
 
 int ldpc_create(ldpc_t **out, int device, int n, int m, int E,
                 const int32_t *chk_ptr, const int32_t *edge_var,

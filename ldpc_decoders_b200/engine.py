@@ -58,6 +58,11 @@ class Engine:
     def launch_count(self):
         return int(self.lib.ldpc_launch_count(self.handle))
 
+    @property
+    def resident_frames(self):
+        """Frames per CTA of the on-chip path for this code; 0 = the code does not fit in shared memory."""
+        return int(self.lib.ldpc_resident_frames(self.handle))
+
     def profile(self, on):
         """Record CUDA events around every CN / VN sweep launch (see ldpc_profile_enable)."""
         _lib.check(self.handle, self.lib.ldpc_profile_enable(self.handle, 1 if on else 0))
