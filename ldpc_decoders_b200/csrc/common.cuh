@@ -31,10 +31,10 @@ struct HostStage;                            // ldpc_decode_host staging (api fi
 
 struct ResidentInfo {                        // compact tables of the on-chip path (resident_bp.cuh)
     bool ok = false;
-    uint16_t *cvar = nullptr, *vpos = nullptr;
+    bool regular36 = false;                  // every check has 6 edges and every variable 3: the register-resident variant
+    uint16_t *cvar = nullptr, *vrow = nullptr;
     uint8_t *cdeg = nullptr, *vdeg = nullptr;
-    int S = 0, DCP = 0, DVP = 0, F = 0, threads = 0;
-    size_t smem = 0;
+    int planes = 0, threads = 0;
 };
 
 struct ProfEvent {                           // one timed launch (ldpc_profile_*)

@@ -497,30 +497,27 @@ int decode_bec_stream(ldpc_t *h, const uint8_t *y, int B, int max_iter, int iter
 // ------------------------------------------------------------------------------------------------
 // resident (on-chip) BP decode for short codes
 // ------------------------------------------------------------------------------------------------
-template <int ALGO, int F, int DCP, int DVP>
-int launch_resident_t(ldpc_t *h, const ResParams &rp, int grid, cudaStream_t s)
+struct ResLaunch {
+    int grid, threads;
+    size_t smem;
+};
+
+template <int ALGO, int DCP, bool UDC, int DVP, bool UDV, bool REGC>
+int launch_resident_t(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
-    auto kern = resident_bp<ALGO, F, DCP, DVP>;
+    auto kern = resident_bp<ALGO, DCP, UDC, DVP, UDV, REGC>;
     static size_t opted = 0;               // the attribute is per kernel instance: raise it when a larger code comes along
-    if (h->res.smem > opted) {
-        int rc = opt_in_smem(h, kern, h->res.smem);
+    if (lc.smem > opted) {
+        int rc = opt_in_smem(h, kern, lc.smem);
         if (rc) return rc;
-        opted = h->res.smem;
+        opted = lc.smem;
     }
-    kern<<<grid, h->res.threads, h->res.smem, s>>>(rp);
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lc.threads, lc.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int grid = std::max(1, std::min(max_grid, h->sm_count * per_sm));
+    kern<<<grid, lc.threads, lc.smem, s>>>(rp);
     h->launches++;
     return LDPC_OK;
-}
-
-template <int ALGO>
-int launch_resident(ldpc_t *h, const ResParams &rp, int grid, cudaStream_t s)
-{
-    const ResidentInfo &r = h->res;
-#define RES_CASE(FF, DC, DV) if (r.F == FF && r.DCP == DC && r.DVP == DV) return launch_resident_t<ALGO, FF, DC, DV>(h, rp, grid, s)
-    RES_CASE(8, 8, 4); RES_CASE(8, 8, 8); RES_CASE(8, 4, 4); RES_CASE(8, 4, 8);
-    RES_CASE(4, 8, 4); RES_CASE(4, 8, 8); RES_CASE(4, 4, 4); RES_CASE(4, 4, 8);
-#undef RES_CASE
-    return fail(h, LDPC_EUNSUPPORTED, "no resident kernel for this degree profile");
 }
 
 bool resident_eligible(const ldpc_t *h, int algo, int dtype, const void *marg_out)
@@ -538,16 +535,16 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     const int limit = max_iter > 0 ? max_iter : iter_cap;
     if (limit <= 0) return fail(h, LDPC_EINVAL, "max_iter <= 0 (unlimited in the reference) needs iter_cap > 0");
     ResParams rp;
-    rp.n = t.n; rp.m = t.m; rp.S = r.S;
-    rp.cvar = r.cvar; rp.vpos = r.vpos; rp.cdeg = r.cdeg; rp.vdeg = r.vdeg;
+    rp.n = t.n; rp.m = t.m; rp.planes = r.planes;
+    rp.cvar = r.cvar; rp.vrow = r.vrow; rp.cdeg = r.cdeg; rp.vdeg = r.vdeg;
+    rp.cn_items = t.m * kResQ; rp.vn_items = t.n * kResQ;
     rp.src = in.src;
     rp.y_hard = in.y_hard;
     rp.param = in.param;
-    rp.in_f64 = (in.in_dtype == LDPC_F64) ? 1 : 0;
     switch (in.channel) {
-    case LDPC_CH_PRIORS: rp.in_mode = IN_COPY; break;
-    case LDPC_CH_BSC: rp.in_mode = IN_BSC; break;
-    case LDPC_CH_BIAWGN: rp.in_mode = IN_BIAWGN; break;
+    case LDPC_CH_PRIORS: rp.in_mode = IN_COPY; rp.in_es = (in.in_dtype == LDPC_F64) ? 8 : 4; break;
+    case LDPC_CH_BSC: rp.in_mode = IN_BSC; rp.in_es = 1; break;
+    case LDPC_CH_BIAWGN: rp.in_mode = IN_BIAWGN; rp.in_es = (in.in_dtype == LDPC_F64) ? 8 : 4; break;
     default: return fail(h, LDPC_EINVAL, "bad channel for MSA/SPA");
     }
     rp.B = B; rp.limit = limit;
@@ -555,11 +552,32 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     rp.sat_llr = (flags & LDPC_SPA_ROBUST) ? INFINITY : kSpaSatLlr;
     rp.x_hat = x_hat; rp.iters = iters; rp.reason = reason;
     rp.counter = static_cast<int *>(ws);
+
+    // Ring of received rows landed by the bulk-copy engine: needs 16-byte aligned rows; as deep as shared memory allows.
+    const size_t row_bytes = (size_t)t.n * rp.in_es;
+    size_t stride = align_up(row_bytes, 16);
+    while ((stride / 4) % 32 != 4) stride += 16;            // slot s, variable v -> bank (4 s + v) mod 32 in the refill loop
+    const size_t budget = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
+    const size_t state = resident_smem_layout(t.n, t.m, r.planes, 0, 0).total;
+    int ring = 0;
+    if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(in.src) & 15u) == 0 && budget > state)
+        ring = (int)std::min<size_t>(kResRingMax, (budget - state) / stride);
+    rp.ring = ring;
+    rp.stage_stride = (int)stride;
+    ResLaunch lc;
+    lc.threads = r.threads;
+    lc.smem = resident_smem_layout(t.n, t.m, r.planes, ring, (int)stride).total;
+    const int max_grid = (B + kResF - 1) / kResF;
+
     CUDA_TRY(h, cudaMemsetAsync(rp.counter, 0, sizeof(int), s));
-    const int batches = (B + r.F - 1) / r.F;
-    const int grid = std::min(h->sm_count, batches);
     ProfEvent *pe = prof_begin(h, 0, s);
-    int rc = (algo == LDPC_MSA) ? launch_resident<ALGO_MSA>(h, rp, grid, s) : launch_resident<ALGO_SPA_PHI>(h, rp, grid, s);
+    int rc;
+    if (r.regular36)
+        rc = (algo == LDPC_MSA) ? launch_resident_t<ALGO_MSA, 6, true, 3, true, true>(h, rp, lc, max_grid, s)
+                                : launch_resident_t<ALGO_SPA_PHI, 6, true, 3, true, true>(h, rp, lc, max_grid, s);
+    else
+        rc = (algo == LDPC_MSA) ? launch_resident_t<ALGO_MSA, 8, false, 8, false, false>(h, rp, lc, max_grid, s)
+                                : launch_resident_t<ALGO_SPA_PHI, 8, false, 8, false, false>(h, rp, lc, max_grid, s);
     prof_end(pe, s);
     if (rc) return rc;
     return check_launch(h, "decode_bp_resident");
@@ -570,39 +588,35 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
 {
     const Tables &t = h->t;
     ResidentInfo &r = h->res;
-    if (t.max_dc > 8 || t.max_dv > 8 || t.max_dc < 1 || t.n > 65535) return LDPC_OK;
-    r.S = t.max_dc | 1;
-    if ((long long)t.m * r.S > 65535) return LDPC_OK;
-    r.DCP = t.max_dc <= 4 ? 4 : 8;
-    r.DVP = t.max_dv <= 4 ? 4 : 8;
+    if (t.max_dc > 8 || t.max_dv > 8 || t.max_dc < 1) return LDPC_OK;
+    r.planes = t.max_dc;
+    if ((long long)r.planes * t.m * kResQ + 1 > 65535) return LDPC_OK;               // c2v float4 index must fit 16 bits
+    if (((long long)t.n * kResQ + 1) * 16 > 65535) return LDPC_OK;                   // marg byte offset must fit 16 bits
     const size_t budget = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
-    r.F = 0;
-    for (int F : {8, 4}) {
-        const size_t need = resident_smem_bytes(t.n, t.m, r.S, F, r.DCP, r.DVP);
-        if (need <= budget) { r.F = F; r.smem = need; break; }
-    }
-    if (r.F == 0) return LDPC_OK;
-    const int Q = r.F / 4;
-    const int items = t.m * Q;
-    const int passes = (items + kResMaxThreads - 1) / kResMaxThreads;
-    int T = (items + passes - 1) / passes;
-    T = std::max(64, (T + 31) / 32 * 32);
-    r.threads = std::min(T, kResMaxThreads);
+    if (resident_smem_layout(t.n, t.m, r.planes, 0, 0).total > budget) return LDPC_OK;
+    // threads: check items (m * Q) in at most 2 passes, variable items (n * Q) in at most 4
+    const int citems = t.m * kResQ, vitems = t.n * kResQ;
+    const int need = std::max((citems + kResCnPasses - 1) / kResCnPasses, (vitems + kResVnPasses - 1) / kResVnPasses);
+    int T = std::max(64, (need + 31) / 32 * 32);
+    if (citems <= kResMaxThreads && vitems <= 2 * kResMaxThreads) T = std::max(64, (std::max(citems, (vitems + 1) / 2) + 31) / 32 * 32);
+    if (T > kResMaxThreads) return LDPC_OK;
+    r.threads = T;
+    r.regular36 = (t.uni_dc == 6 && t.uni_dv == 3);
 
-    std::vector<uint16_t> cvar((size_t)t.m * r.DCP, 0), vpos((size_t)t.n * r.DVP, 0);
+    std::vector<uint16_t> cvar((size_t)t.m * 8, (uint16_t)t.n), vrow((size_t)t.n * 8, 0);
     std::vector<uint8_t> cdeg((size_t)t.m), vdeg((size_t)t.n);
     std::vector<int> row_of_edge((size_t)t.E);
     for (int c = 0; c < t.m; ++c) {
         cdeg[c] = (uint8_t)(chk_ptr[c + 1] - chk_ptr[c]);
         for (int e = chk_ptr[c], k = 0; e < chk_ptr[c + 1]; ++e, ++k) {
-            cvar[(size_t)c * r.DCP + k] = (uint16_t)edge_var[e];
-            row_of_edge[e] = c * r.S + k;
+            cvar[(size_t)c * 8 + k] = (uint16_t)edge_var[e];
+            row_of_edge[e] = k * t.m + c;
         }
     }
     for (int v = 0; v < t.n; ++v) {
         vdeg[v] = (uint8_t)(var_ptr[v + 1] - var_ptr[v]);
         for (int p0 = var_ptr[v], k = 0; p0 < var_ptr[v + 1]; ++p0, ++k)
-            vpos[(size_t)v * r.DVP + k] = (uint16_t)row_of_edge[var_edges[p0]];
+            vrow[(size_t)v * 8 + k] = (uint16_t)row_of_edge[var_edges[p0]];
     }
     auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, bytes);
@@ -610,7 +624,7 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
         return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
     };
     cudaError_t e;
-    if ((e = up((void **)&r.cvar, cvar.data(), cvar.size() * 2)) != cudaSuccess || (e = up((void **)&r.vpos, vpos.data(), vpos.size() * 2)) != cudaSuccess ||
+    if ((e = up((void **)&r.cvar, cvar.data(), cvar.size() * 2)) != cudaSuccess || (e = up((void **)&r.vrow, vrow.data(), vrow.size() * 2)) != cudaSuccess ||
         (e = up((void **)&r.cdeg, cdeg.data(), cdeg.size())) != cudaSuccess || (e = up((void **)&r.vdeg, vdeg.data(), vdeg.size())) != cudaSuccess)
         return fail(nullptr, LDPC_ECUDA, std::string("resident table upload: ") + cudaGetErrorString(e));
     r.ok = true;
@@ -714,7 +728,7 @@ const char *ldpc_last_error(const ldpc_t *h) { return h ? h->err.c_str() : g_cre
 
 unsigned long long ldpc_launch_count(const ldpc_t *h) { return h ? h->launches : 0ull; }
 
-int ldpc_resident_frames(const ldpc_t *h) { return (h && h->res.ok) ? h->res.F : 0; }
+int ldpc_resident_frames(const ldpc_t *h) { return (h && h->res.ok) ? kResF : 0; }
 
 int ldpc_create(ldpc_t **out, int device, int n, int m, int E,
                 const int32_t *chk_ptr, const int32_t *edge_var,
@@ -842,7 +856,7 @@ void ldpc_destroy(ldpc_t *h)
         delete h->stage;
     }
     if (h->res.cvar) cudaFree(h->res.cvar);
-    if (h->res.vpos) cudaFree(h->res.vpos);
+    if (h->res.vrow) cudaFree(h->res.vrow);
     if (h->res.cdeg) cudaFree(h->res.cdeg);
     if (h->res.vdeg) cudaFree(h->res.vdeg);
     if (h->t.chk_ptr) cudaFree(h->t.chk_ptr);

@@ -136,6 +136,47 @@ LDPC_HD void cn_msa_bits(const float (&v)[DCMAX], int dc, float (&out)[DCMAX])
 }
 
 // ---------------------------------------------------------------------------------------------
+// Lean float32 min-sum for a check of EXACTLY DC edges (on-chip kernel, where the ALU pipe is the limiter):
+//   |out_k| = min_{j != k} |v_j|  built from 3-input minima (FMNMX3 with free |.| operand modifiers),
+//   sign    = xor of all sign bits ^ own sign bit, applied as a multiplication by +-1.0f on the FMA pipe
+//             (the reference's literal `sign * mag`, bpa.py:102, so 0 * -1 = -0.0 comes out the same).
+// Precondition: no input is NaN or -0.0 — then "v < 0" is the sign bit, and the result is bit-identical to
+// cn_msa<float>.  The resident kernel guarantees it: v2c = marg - c2v can only be -0.0 if marg is, and
+// marg = prior + (0.0 + c ...) never is once -0.0 priors are folded to +0.0 at load (same values everywhere:
+// -0.0 and +0.0 priors are indistinguishable to every formula of bpa.py).
+// ---------------------------------------------------------------------------------------------
+LDPC_HD float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+template <int DC>
+LDPC_HD void cn_msa_lean(const float (&v)[DC], float (&out)[DC])
+{
+    float a[DC], mag[DC];
+#pragma unroll
+    for (int k = 0; k < DC; ++k) a[k] = fabsf(v[k]);
+    if (DC == 6) {
+        const float mL = fmin3(a[0], a[1], a[2]), mR = fmin3(a[3], a[4], a[5]);
+        mag[0] = fmin3(a[1], a[2], mR); mag[1] = fmin3(a[0], a[2], mR); mag[2] = fmin3(a[0], a[1], mR);
+        mag[3] = fmin3(a[4], a[5], mL); mag[4] = fmin3(a[3], a[5], mL); mag[5] = fmin3(a[3], a[4], mL);
+    } else {
+        float pre[DC], suf[DC];
+        pre[0] = INFINITY;
+#pragma unroll
+        for (int k = 1; k < DC; ++k) pre[k] = fminf(pre[k - 1], a[k - 1]);
+        suf[DC - 1] = INFINITY;
+#pragma unroll
+        for (int k = DC - 2; k >= 0; --k) suf[k] = fminf(suf[k + 1], a[k + 1]);
+#pragma unroll
+        for (int k = 0; k < DC; ++k) mag[k] = fminf(pre[k], suf[k]);
+    }
+    uint32_t x = 0u;
+#pragma unroll
+    for (int k = 0; k < DC; ++k) x ^= f32_bits(v[k]);
+    const uint32_t xs = (x & 0x80000000u) | 0x3f800000u;                    // +-1.0f carrying the check's parity
+#pragma unroll
+    for (int k = 0; k < DC; ++k) out[k] = mag[k] * bits_f32(xs ^ (f32_bits(v[k]) & 0x80000000u));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Sum-product check node, formula mirror (float64 verification mode).
 //   t = tanh(v / 2); S = sum_k log|t_k| (ordered, from 0); P = (-1)^{#(t<0)} exp(S)
 //   q = P / t_k;  out = 2 * (|q| == 1 ? inf * q : atanh(q))

@@ -1,39 +1,57 @@
-// resident_bp.cuh — on-chip flooding BP for short codes.
+// resident_bp.cuh — on-chip flooding BP for short codes, with continuous frame refill.
 //
-// For n = 1200 one frame's whole decoder state is 19 KB, so a CTA keeps F frames (8 for float32) in shared
-// memory for ALL iterations: HBM sees the received block once on the way in and the hard decisions once on
-// the way out (~6 KB per frame instead of 63 KB per frame-iteration).  The arithmetic, its order and the
-// exit rules are exactly those of the streaming sweeps (same ldpc_math.cuh functions), so results are
-// bit-identical to them and to the reference.
+// For n = 1200 one frame's decoder state is 19 KB, so a CTA keeps F = 8 frames ("slots") in shared memory
+// and registers for ALL their iterations: HBM sees the received row once on the way in and the hard
+// decisions once on the way out (~6 KB per frame instead of 63 KB per frame-iteration).
 //
-// Shared-memory layout (Q = F/4 quads of 4 frames; one float4 = one quad of one row):
-//   msg  [m*S][Q] float4   check-major rows, S = max_dc | 1 (odd): row of edge k of check c is c*S + k.
-//                          A quarter-warp (8 lanes = 8/Q checks x Q quads) then touches 8 different
-//                          16-byte bank groups in the check-node phase -> conflict-free LDS.128 / STS.128.
-//   prior[n][Q]    float4
-//   xb   [Q][n]    uint8   hard decisions of a quad (low 4 bits)
-//   cvar [m][DCP]  uint16  variable index of every edge of a check (padded)
-//   vpos [n][DVP]  uint16  msg row of every edge of a variable, ascending edge order (padded)
-//   cdeg [m], vdeg [n] uint8
-// Thread = (check or variable, quad); a CTA walks its items in passes, phases separated by __syncthreads:
-//   load (LLR map fused) -> { CN + syndrome -> sync -> run = act & unsat -> VN -> sync } x iterations -> store.
-// The F frames of a CTA run in lock-step; a frame that converged keeps its word and counter (masked), the CTA
-// leaves the loop as soon as none of its frames runs.  CTAs fetch batches of F frames from an atomic counter.
+// State of one slot (frames are the innermost dimension: a float4 = the 4 frames of one "quad", Q = 2 quads):
+//   marg [n][Q]        float4  shared   last marginal of every variable (bpa.py:35); before the first
+//                                       iteration it holds the prior, so v2c = marg - 0 = priors[yy] (bpa.py:19)
+//   prior[n][Q]        float4  shared
+//   c2v  [dc][m][Q]    float4  shared   check-to-variable messages, plane k = k-th edge of every check
+//   c2v of the thread's OWN checks      additionally stays in registers across iterations (REGC variant)
+// One iteration (src/bpa.py:27-63), two phases separated by __syncthreads:
+//   CN  thread = (check, quad): gathers marg of its dc variables (their sign bits are the hard decisions,
+//       so the syndrome of bpa.py:29 costs three LOP3), forms v2c = marg - c2v_old ("total minus own",
+//       bpa.py:37, the same subtraction the reference does), runs the check-node rule, stores c2v.
+//   VN  thread = (variable, quad): marg = prior + ((0 + c0) + c1 + ...) in ascending edge order (bpa.py:35).
+// Shared-memory traffic per frame-iteration is 3E + 2n floats instead of the 4E + n of a message-array
+// design, the per-thread graph indices live in registers (loaded once per CTA), and no hard-decision array
+// is kept at all.
+//
+// Slots are independent: a frame that leaves (syndrome zero after the CN phase, or iteration bound after
+// the VN phase) is written out at once and its slot is refilled from a ring of received rows that the
+// bulk-copy engine (cp.async.bulk + mbarrier, TMA 1-D) keeps landing in shared memory while the CTA
+// iterates — converged frames never occupy a lane, and no thread ever waits for HBM in steady state.
+// Frames are handed out by a global atomic counter; results do not depend on which slot decodes a frame.
+//
+// Arithmetic and exit rules are those of the streaming sweeps (same ldpc_math.cuh functions; the (3,6)
+// min-sum uses cn_msa_lean, value-identical for the finite inputs it is given), so words, iteration
+// counts and exit reasons are bit-identical to them and to the reference.
 #pragma once
 #include "common.cuh"
 #include "io_kernels.cuh"
+#include "stream_bp_tma.cuh"
 
 namespace ldpc {
 
-constexpr int kResMaxThreads = 640;
+constexpr int kResF = 8;                     // frames (slots) per CTA
+constexpr int kResQ = 2;                     // quads per CTA
+constexpr int kResMaxThreads = 608;          // 65536 registers / 104
+constexpr int kResCnPasses = 2;              // check items per thread  (m * Q <= 2 * threads)
+constexpr int kResVnPasses = 4;              // variable items per thread (n * Q <= 4 * threads)
+constexpr int kResRingMax = 8;               // staged received rows
 
 struct ResParams {
-    int n, m, S;
-    const uint16_t *cvar, *vpos;
+    int n, m;
+    int planes;                        // c2v planes = max check degree
+    const uint16_t *cvar;              // [m][8]  variable of the k-th edge of a check (padding: n)
+    const uint16_t *vrow;              // [n][8]  c2v row (k * m + c) of the variable's edges, ascending edge order
     const uint8_t *cdeg, *vdeg;
+    int cn_items, vn_items;            // m * Q, n * Q
     const void *src;                   // [B][n] received block (or priors)
     int in_mode;                       // IN_COPY / IN_BSC / IN_BIAWGN
-    int in_f64;                        // element type of src for COPY / BIAWGN
+    int in_es;                         // element size of src: 1 (BSC), 4, 8
     const uint8_t *y_hard;             // optional hard input for IN_COPY
     double param;
     int B, limit, bound_reason;
@@ -41,188 +59,410 @@ struct ResParams {
     uint8_t *x_hat;
     int *iters;
     uint8_t *reason;
-    int *counter;                      // batch dispenser (zeroed before launch)
+    int *counter;                      // frame dispenser (zeroed before launch)
+    int ring;                          // staged rows (0: rows are read straight from global memory at refill)
+    int stage_stride;                  // bytes between staged rows
 };
 
-template <int DCP> struct IdxVec;
-template <> struct IdxVec<8> { uint4 raw; __device__ __forceinline__ int get(int k) const { const uint32_t w = (&raw.x)[k >> 1]; return (k & 1) ? (int)(w >> 16) : (int)(w & 0xffffu); } };
-template <> struct IdxVec<4> { uint2 raw; __device__ __forceinline__ int get(int k) const { const uint32_t w = (&raw.x)[k >> 1]; return (k & 1) ? (int)(w >> 16) : (int)(w & 0xffffu); } };
-
-__device__ __forceinline__ float res_llr(const ResParams &p, size_t idx, uint8_t *hard)
+// Shared-memory carve-up, shared by the kernel and the host-side size computation.
+struct ResSmem {
+    size_t c2v, marg, prior, stage, hb, bars, total;
+};
+__host__ __device__ inline ResSmem resident_smem_layout(int n, int m, int planes, int ring, int stage_stride)
 {
-    *hard = 0;
-    if (p.in_mode == IN_BSC) {
-        const uint8_t y = ((const uint8_t *)p.src)[idx];
-        *hard = (uint8_t)(y != 0);
-        return (float)(p.param * (double)(1 - 2 * (int)y));
-    }
-    const double y = p.in_f64 ? ((const double *)p.src)[idx] : (double)((const float *)p.src)[idx];
-    if (p.in_mode == IN_BIAWGN) return (float)((-2.0 * y) / p.param);
-    if (p.y_hard != nullptr) *hard = (uint8_t)(p.y_hard[idx] != 0);
-    return (float)y;
+    ResSmem L;
+    size_t o = 0;
+    L.c2v = o;   o += ((size_t)planes * m * kResQ + 1) * 16;          // + one all-zero cell (padding edges of a variable)
+    L.marg = o;  o += ((size_t)n * kResQ + 1) * 16;                   // + one +inf cell (padding edges of a check)
+    L.prior = o; o += (size_t)n * kResQ * 16;
+    L.stage = o; o += (size_t)ring * stage_stride;
+    L.bars = o;  o += (size_t)kResRingMax * 8;
+    L.hb = o;    o += ((size_t)n + 15) / 16 * 16;
+    L.total = o + 16;
+    return L;
 }
 
-template <int ALGO, int F, int DCP, int DVP>
-__global__ void __launch_bounds__(kResMaxThreads) resident_bp(const ResParams p)
+__device__ __forceinline__ float res_llr(const void *row, int v, int in_mode, int in_es, double param, uint32_t *hard)
 {
-    constexpr int Q = F / 4;
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int n = p.n, m = p.m, S = p.S;
-    float4 *msg = reinterpret_cast<float4 *>(smem);                                   // [m*S][Q]
-    float4 *prior = msg + (size_t)m * S * Q;                                          // [n][Q]
-    uint16_t *cvar = reinterpret_cast<uint16_t *>(prior + (size_t)n * Q);             // [m][DCP]
-    uint16_t *vpos = cvar + (size_t)m * DCP;                                          // [n][DVP]
-    uint8_t *xb = reinterpret_cast<uint8_t *>(vpos + (size_t)n * DVP);                // [Q][n]
-    uint8_t *cdeg = xb + (size_t)Q * n;                                               // [m]
-    uint8_t *vdeg = cdeg + m;                                                         // [n]
-    __shared__ uint32_t s_unsat[2];
-    __shared__ int s_batch;
+    *hard = 0u;
+    float val;
+    if (in_mode == IN_BSC) {
+        const uint8_t y = ((const uint8_t *)row)[v];
+        *hard = (uint32_t)(y != 0);
+        val = (float)(param * (double)(1 - 2 * (int)y));
+    } else {
+        const double y = (in_es == 8) ? ((const double *)row)[v] : (double)((const float *)row)[v];
+        val = (in_mode == IN_BIAWGN) ? (float)((-2.0 * y) / param) : (float)y;
+    }
+    return __fadd_rn(val, 0.0f);          // -0.0 -> +0.0 (value-neutral, see cn_msa_lean), NaN -> canonical
+}
 
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+// Half of a packed index word.  Opaque to the optimiser on purpose: otherwise the unpacked offsets are hoisted out of
+// the iteration loop as 24 loop-invariant registers, which do not exist (the kernel is capped at 96) and get spilled.
+__device__ __forceinline__ uint32_t lds_u16x2(const uint32_t w, int hi)
+{
+    uint32_t r;
+    if (hi) asm volatile("shr.u32 %0, %1, 16;" : "=r"(r) : "r"(w));
+    else asm volatile("and.b32 %0, %1, 0xffff;" : "=r"(r) : "r"(w));
+    return r;
+}
 
-    // ---- tables -> shared memory (once per CTA)
-    for (int i = tid; i < m * DCP / 2; i += T) reinterpret_cast<uint32_t *>(cvar)[i] = reinterpret_cast<const uint32_t *>(p.cvar)[i];
-    for (int i = tid; i < n * DVP / 2; i += T) reinterpret_cast<uint32_t *>(vpos)[i] = reinterpret_cast<const uint32_t *>(p.vpos)[i];
-    for (int i = tid; i < m; i += T) cdeg[i] = p.cdeg[i];
-    for (int i = tid; i < n; i += T) vdeg[i] = p.vdeg[i];
+template <int ALGO, int DCP, bool UDC, int DVP, bool UDV, bool REGC>
+__global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams p)
+{
+    constexpr int Q = kResQ, F = kResF;
+    constexpr int CH = (DCP + 1) / 2, VH = (DVP + 1) / 2;
+    constexpr uint32_t ALL = (1u << F) - 1u;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int n = p.n, m = p.m;
+    const ResSmem L = resident_smem_layout(n, m, p.planes, p.ring, p.stage_stride);
+    float4 *c2v = reinterpret_cast<float4 *>(smem + L.c2v);
+    float4 *marg = reinterpret_cast<float4 *>(smem + L.marg);
+    float4 *prior = reinterpret_cast<float4 *>(smem + L.prior);
+    unsigned char *stage = smem + L.stage;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+    uint8_t *hb = smem + L.hb;                                       // hard input bits of the slots being loaded
+    const uint32_t zero_cell = (uint32_t)p.planes * m * Q;           // float4 index into c2v
+    const uint32_t inf_off = (uint32_t)n * Q * 16;                   // byte offset into marg
 
+    __shared__ int s_frame[F], s_it[F], s_assign[F];
+    __shared__ int r_frame[kResRingMax], r_uses[kResRingMax];
+    __shared__ uint32_t s_unsat[2], s_maxed[2], s_unsat0, s_newmask, s_exhausted;
+
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int q = tid & 1;                                           // T is even: every item of a thread is in quad q
+    const bool async = p.ring > 0;
     const bool have_hard = (p.in_mode == IN_BSC) || (p.in_mode == IN_COPY && p.y_hard != nullptr);
-    float *prior_f = reinterpret_cast<float *>(prior);                                // [n][F] scalar view
+    const size_t row_bytes = (size_t)n * p.in_es;
 
-    for (;;) {
-        __syncthreads();                                   // previous batch fully stored / tables visible
-        if (tid == 0) s_batch = atomicAdd(p.counter, 1);
-        if (tid < 2) s_unsat[tid] = 0u;
-        __syncthreads();
-        const int g0 = s_batch * F;
-        if (g0 >= p.B) break;
-        const uint32_t valid = (p.B - g0 >= F) ? ((1u << F) - 1u) : ((1u << (p.B - g0)) - 1u);
-
-        // ---- load F frames: lane = frame + F * (variable mod 32/F); shared stores are conflict-free
-        for (int i = tid; i < ((n * F + 31) & ~31); i += T) {      // whole warps stay in the loop (ballot below)
-            const int f = i % F, v = i / F;
-            const bool in = i < n * F;
-            uint8_t hb = 0;
-            float pr = 0.0f;
-            if (in && ((valid >> f) & 1u)) pr = res_llr(p, (size_t)(g0 + f) * n + v, &hb);
-            if (in) prior_f[i] = pr;
-            // hard bits of the F frames of one variable sit in F adjacent lanes
-            const uint32_t bal = __ballot_sync(kFull, hb != 0);
-            if (in && f == 0) {
-                const uint32_t byte = (bal >> (lane & ~(F - 1))) & ((1u << F) - 1u);
+    // ---- per-thread graph indices -> registers (once per CTA)
+    uint32_t cidx[kResCnPasses][CH];          // byte offsets into marg of the check's variables, two per word
+    int cdeg[kResCnPasses];
+    uint32_t vidx[kResVnPasses][VH];          // float4 indices into c2v of the variable's edges, two per word
 #pragma unroll
-                for (int q = 0; q < Q; ++q) xb[q * n + v] = (uint8_t)((byte >> (4 * q)) & 0xFu);
+    for (int ps = 0; ps < kResCnPasses; ++ps) {
+        const int item = tid + ps * T;
+        cdeg[ps] = 0;
+#pragma unroll
+        for (int h = 0; h < CH; ++h) cidx[ps][h] = inf_off | (inf_off << 16);
+        if (item < p.cn_items) {
+            const int c = item >> 1;
+            cdeg[ps] = UDC ? DCP : (int)p.cdeg[c];
+#pragma unroll
+            for (int k = 0; k < DCP; ++k) {
+                const uint32_t var = p.cvar[(size_t)c * 8 + k];
+                const uint32_t off = (k < cdeg[ps]) ? (var * Q + q) * 16u : inf_off;
+                if (k & 1) cidx[ps][k >> 1] = (cidx[ps][k >> 1] & 0xffffu) | (off << 16);
+                else cidx[ps][k >> 1] = (cidx[ps][k >> 1] & 0xffff0000u) | off;
             }
         }
-        __syncthreads();
-
-        uint32_t act = valid;
-        int my_iters = 0;                                  // threads 0..F-1 count their frame's iterations
-        int it = 0;
-        for (; it < p.limit; ++it) {
-            const bool first = (it == 0);
-            const bool skip_syn = first && !have_hard;
-            // ================= check-node phase (+ syndrome of the current hard decisions) =================
-            uint32_t unsat = 0u;
-            for (int item = tid; item < m * Q; item += T) {
-                const int c = item / Q, q = item % Q;
-                const int dc = cdeg[c];
-                IdxVec<DCP> vars;
-                vars.raw = *reinterpret_cast<const decltype(vars.raw) *>(cvar + (size_t)c * DCP);
-                const int row0 = c * S;
-                float4 v[DCP];
-                uint32_t syn = 0u;
+    }
 #pragma unroll
-                for (int k = 0; k < DCP; ++k) {
-                    if (k < dc) {
-                        const int var = vars.get(k);
-                        v[k] = first ? prior[var * Q + q] : msg[(row0 + k) * Q + q];
-                        if (!skip_syn) syn ^= xb[q * n + var];
+    for (int ps = 0; ps < kResVnPasses; ++ps) {
+        const int item = tid + ps * T;
+#pragma unroll
+        for (int h = 0; h < VH; ++h) vidx[ps][h] = zero_cell | (zero_cell << 16);
+        if (item < p.vn_items) {
+            const int v = item >> 1;
+            const int dv = UDV ? DVP : (int)p.vdeg[v];
+#pragma unroll
+            for (int k = 0; k < DVP; ++k) {
+                const uint32_t row = p.vrow[(size_t)v * 8 + k];
+                const uint32_t idx = (k < dv) ? row * Q + q : zero_cell;
+                if (k & 1) vidx[ps][k >> 1] = (vidx[ps][k >> 1] & 0xffffu) | (idx << 16);
+                else vidx[ps][k >> 1] = (vidx[ps][k >> 1] & 0xffff0000u) | idx;
+            }
+        }
+    }
+    float4 old[REGC ? kResCnPasses : 1][REGC ? DCP : 1];            // c2v of the thread's own checks
+    if (REGC) {
+#pragma unroll
+        for (int ps = 0; ps < kResCnPasses; ++ps)
+#pragma unroll
+            for (int k = 0; k < DCP; ++k) old[ps][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // ---- constants cells, slot state, ring
+    if (tid == 0) {
+        c2v[zero_cell] = make_float4(0.f, 0.f, 0.f, 0.f);
+        marg[n * Q] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+        s_unsat[0] = s_unsat[1] = s_maxed[0] = s_maxed[1] = 0u;
+        s_unsat0 = 0u;
+        s_exhausted = 0u;
+        for (int e = 0; e < kResRingMax; ++e) { r_frame[e] = -1; r_uses[e] = 0; }
+        if (async) {
+            for (int e = 0; e < p.ring; ++e) mbar_init(&bars[e], 1u);
+            fence_mbar_init();
+        }
+    }
+    __syncthreads();
+    int head = 0;                                                    // thread 0: next ring entry to hand out
+    auto issue = [&](int e) {                                        // thread 0: fetch the next frame into ring entry e
+        const int g = atomicAdd(p.counter, 1);
+        if (g < p.B) {
+            r_frame[e] = g;
+            mbar_expect_tx(&bars[e], (uint32_t)row_bytes);
+            bulk_g2s(stage + (size_t)e * p.stage_stride, (const char *)p.src + (size_t)g * row_bytes, (uint32_t)row_bytes, &bars[e]);
+        } else {
+            r_frame[e] = -1;
+        }
+    };
+    if (tid == 0 && async)
+        for (int e = 0; e < p.ring; ++e) issue(e);
+
+    // hard decisions of the slots in `mask` -> global, from the sign of marg (bpa.py:62; NaN and 0 -> bit 0)
+    auto output_marg = [&](uint32_t mask, int why) {
+        for (int s = 0; s < F; ++s) {
+            if (!((mask >> s) & 1u)) continue;
+            const int g = s_frame[s];
+            const float *col = reinterpret_cast<const float *>(marg) + (s >> 2) * 4 + (s & 3);
+            uint8_t *dst = p.x_hat + (size_t)g * n;
+            for (int v = tid; v < n; v += T) dst[v] = (uint8_t)(col[(size_t)v * (Q * 4)] < 0.0f);
+            if (tid == 0) {
+                p.iters[g] = s_it[s];
+                if (p.reason != nullptr) p.reason[g] = (uint8_t)why;
+            }
+        }
+    };
+
+    uint32_t active = 0u, fresh = 0u, freem = ALL;                   // CTA-uniform slot masks
+    bool exhausted = false;
+    int par = 0;
+
+    for (;;) {
+        // ======================================= refill free slots =======================================
+        while (freem != 0u && !exhausted) {
+            __syncthreads();                               // outputs of leaving frames have read marg / hb
+            if (tid == 0) {
+                uint32_t nm = 0u;
+                int used = 0;
+                uint32_t exh = 0u;
+                for (int s = 0; s < F; ++s) {
+                    s_assign[s] = -1;
+                    if (!((freem >> s) & 1u) || exh) continue;
+                    int g, e = 0;
+                    if (async) {
+                        if (used == p.ring) continue;      // the rest is refilled at the next refill point
+                        e = head % p.ring;
+                        g = r_frame[e];
+                    } else {
+                        g = atomicAdd(p.counter, 1);
+                        if (g >= p.B) g = -1;
+                    }
+                    if (g < 0) { exh = 1u; continue; }
+                    s_assign[s] = e; s_frame[s] = g; s_it[s] = 0;
+                    nm |= 1u << s;
+                    ++head; ++used;
+                }
+                s_newmask = nm;
+                s_exhausted = exh;
+                s_unsat0 = 0u;
+            }
+            __syncthreads();
+            const uint32_t nm = s_newmask;
+            exhausted = s_exhausted != 0u;
+            if (nm == 0u) break;
+
+            // ---- received rows -> prior / marg columns.  lane = (variable mod 4, slot): the 8 slots x 4 variables
+            //      of a warp store to 32 different banks.
+            {
+                const int s = lane & 7, vl = lane >> 3;
+                const bool mine = (nm >> s) & 1u;
+                const void *row = nullptr;
+                const uint8_t *hrow = nullptr;
+                if (mine) {
+                    const int g = s_frame[s];
+                    if (async) {
+                        const int e = s_assign[s];
+                        mbar_wait(&bars[e], (uint32_t)(r_uses[e] & 1));
+                        row = stage + (size_t)e * p.stage_stride;
+                    } else {
+                        row = (const char *)p.src + (size_t)g * row_bytes;
+                    }
+                    if (p.in_mode == IN_COPY && p.y_hard != nullptr) hrow = p.y_hard + (size_t)g * n;
+                }
+                float *mcol = reinterpret_cast<float *>(marg) + (s >> 2) * 4 + (s & 3);
+                float *pcol = reinterpret_cast<float *>(prior) + (s >> 2) * 4 + (s & 3);
+                for (int vb = warp * 4; vb < n; vb += nwarps * 4) {
+                    const int v = vb + vl;
+                    uint32_t hbit = 0u;
+                    if (mine && v < n) {
+                        const float val = res_llr(row, v, p.in_mode, p.in_es, p.param, &hbit);
+                        if (hrow != nullptr) hbit = (uint32_t)(hrow[v] != 0);
+                        mcol[(size_t)v * (Q * 4)] = val;
+                        pcol[(size_t)v * (Q * 4)] = val;
+                    }
+                    if (have_hard) {
+                        const uint32_t bal = __ballot_sync(kFull, hbit != 0u);
+                        if (s == 0 && v < n) hb[v] = (uint8_t)((bal >> (lane & ~7)) & 0xffu);
                     }
                 }
-                unsat |= (syn & 0xFu) << (4 * q);
+            }
+            // ---- the new frames start from c2v = 0
+            const uint32_t nq = (nm >> (4 * q)) & 0xFu;
+            if (nq != 0u) {
+                if (REGC) {
+#pragma unroll
+                    for (int ps = 0; ps < kResCnPasses; ++ps)
+#pragma unroll
+                        for (int k = 0; k < DCP; ++k) {
+                            if (nq & 1u) old[ps][k].x = 0.f;
+                            if (nq & 2u) old[ps][k].y = 0.f;
+                            if (nq & 4u) old[ps][k].z = 0.f;
+                            if (nq & 8u) old[ps][k].w = 0.f;
+                        }
+                } else {
+#pragma unroll
+                    for (int ps = 0; ps < kResCnPasses; ++ps) {
+                        const int item = tid + ps * T;
+                        if (item < p.cn_items)
+                            for (int k = 0; k < cdeg[ps]; ++k) {
+                                float *cell = reinterpret_cast<float *>(c2v + (size_t)k * m * Q + item);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if ((nq >> j) & 1u) cell[j] = 0.f;
+                            }
+                    }
+                }
+            }
+            __syncthreads();                               // columns / hb visible; staged rows consumed
+            if (tid == 0 && async) {
+                for (int s = 0; s < F; ++s)
+                    if ((nm >> s) & 1u) { const int e = s_assign[s]; r_uses[e] += 1; issue(e); }
+            }
+            uint32_t z = 0u;
+            if (have_hard) {
+                // ---- iteration-0 exit (bpa.py:29 on x_hat = y): syndrome of the hard input of the new frames
+                uint32_t u0 = 0u;
+#pragma unroll
+                for (int ps = 0; ps < kResCnPasses; ++ps) {
+                    const int item = tid + ps * T;
+                    if (item < p.cn_items) {
+                        uint32_t syn = 0u;
+#pragma unroll
+                        for (int k = 0; k < DCP; ++k)
+                            if (UDC || k < cdeg[ps]) syn ^= hb[lds_u16x2(cidx[ps][k >> 1], k & 1) >> 5];
+                        u0 |= ((syn >> (4 * q)) & 0xFu) << (4 * q);
+                    }
+                }
+                u0 = __reduce_or_sync(kFull, u0);
+                if (lane == 0 && u0 != 0u) atomicOr(&s_unsat0, u0);
+                __syncthreads();
+                z = nm & ~s_unsat0;
+                for (int s = 0; s < F; ++s) {
+                    if (!((z >> s) & 1u)) continue;
+                    const int g = s_frame[s];
+                    uint8_t *dst = p.x_hat + (size_t)g * n;
+                    for (int v = tid; v < n; v += T) dst[v] = (uint8_t)((hb[v] >> s) & 1u);
+                    if (tid == 0) {
+                        p.iters[g] = 0;
+                        if (p.reason != nullptr) p.reason[g] = (uint8_t)LDPC_REASON_DECODED;
+                    }
+                }
+            }
+            const uint32_t started = nm & ~z;
+            active |= started; fresh |= started; freem &= ~started;
+            if (z == 0u) break;
+        }
+        if (active == 0u) break;
+
+        // ======================================= check-node phase =======================================
+        uint32_t unsat = 0u;
+#pragma unroll
+        for (int ps = 0; ps < kResCnPasses; ++ps) {
+            const int item = tid + ps * T;
+            if (item < p.cn_items) {
+                const int dc = cdeg[ps];
+                float4 mg[DCP];
+#pragma unroll
+                for (int k = 0; k < DCP; ++k)
+                    mg[k] = *reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(marg) + lds_u16x2(cidx[ps][k >> 1], k & 1));
+                float4 *own = c2v + item;
+                // v2c = marg - c2v_old (bpa.py:37); the sign bits of marg are the current hard decisions (bpa.py:62)
+                uint32_t sx[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int k = 0; k < DCP; ++k) {
+                    float4 ov = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (REGC) ov = old[ps][k];
+                    else if (UDC || k < dc) ov = own[(size_t)k * m * Q];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float mv = (&mg[k].x)[j];
+                        if (ALGO == ALGO_MSA) sx[j] ^= f32_bits(mv);                   // sign bit == (marg < 0): no NaN, no -0.0
+                        else sx[j] ^= (mv < 0.0f) ? 0x80000000u : 0u;
+                        (&mg[k].x)[j] = (UDC || k < dc) ? __fsub_rn(mv, (&ov.x)[j]) : INFINITY;
+                    }
+                }
+                const uint32_t syn = (sx[0] >> 31) | ((sx[1] >> 31) << 1) | ((sx[2] >> 31) << 2) | ((sx[3] >> 31) << 3);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float a[DCP], o[DCP];
 #pragma unroll
-                    for (int k = 0; k < DCP; ++k) a[k] = (k < dc) ? (&v[k].x)[j] : 0.0f;
-                    if (ALGO == ALGO_MSA) cn_msa_bits<DCP>(a, dc, o);
-                    else cn_spa_phi<DCP>(a, dc, o, p.sat_llr);
+                    for (int k = 0; k < DCP; ++k) a[k] = (&mg[k].x)[j];
+                    if (ALGO == ALGO_MSA) {
+                        if (UDC) cn_msa_lean<DCP>(a, o);
+                        else cn_msa_bits<DCP>(a, dc, o);
+                    } else {
+                        cn_spa_phi<DCP>(a, dc, o, p.sat_llr);
+                    }
 #pragma unroll
-                    for (int k = 0; k < DCP; ++k)
-                        if (k < dc) (&v[k].x)[j] = o[k];
+                    for (int k = 0; k < DCP; ++k) (&mg[k].x)[j] = o[k];
                 }
 #pragma unroll
                 for (int k = 0; k < DCP; ++k)
-                    if (k < dc) msg[(row0 + k) * Q + q] = v[k];
+                    if (UDC || k < dc) {
+                        own[(size_t)k * m * Q] = mg[k];
+                        if (REGC) old[ps][k] = mg[k];
+                    }
+                unsat |= syn << (4 * q);
             }
-            if (skip_syn) unsat = act;
-            unsat = __reduce_or_sync(kFull, unsat);
-            if (lane == 0 && unsat != 0u) atomicOr(&s_unsat[it & 1], unsat);
-            __syncthreads();
-            // ================= book-keeping (every thread computes the same masks) =================
-            const uint32_t run = act & s_unsat[it & 1];      // frames whose syndrome was zero stop here (bpa.py:29)
-            act = run;
-            if (tid < F && ((run >> tid) & 1u)) my_iters += 1;                        // bpa.py:63
-            if (tid == 0) s_unsat[(it + 1) & 1] = 0u;        // nobody touches the other buffer until the next CN phase
-            if (run == 0u) break;
-            // ================= variable-node phase =================
-            for (int item = tid; item < n * Q; item += T) {
-                const int vv = item / Q, q = item % Q;
-                const int dv = vdeg[vv];
-                IdxVec<DVP> pos;
-                pos.raw = *reinterpret_cast<const decltype(pos.raw) *>(vpos + (size_t)vv * DVP);
-                float4 cmsg[DVP];
+        }
+        unsat = __reduce_or_sync(kFull, unsat);
+        if (lane == 0 && unsat != 0u) atomicOr(&s_unsat[par], unsat);
+        __syncthreads();
+
+        // ---- book-keeping: frames whose syndrome was zero leave here (bpa.py:29), iteration count unchanged
+        const uint32_t us = s_unsat[par] | fresh;            // a new frame's marg is its prior: no syndrome yet
+        const uint32_t decoded = active & ~us;
+        const uint32_t run = active & us;
+        fresh = 0u;
+        if (tid < F && ((run >> tid) & 1u)) {
+            const int it = ++s_it[tid];                      // bpa.py:63
+            if (it >= p.limit) atomicOr(&s_maxed[par], 1u << tid);       // bpa.py:28 at the top of the next round
+        }
+        if (tid == 0) { s_unsat[par ^ 1] = 0u; s_maxed[par ^ 1] = 0u; }
+        if (decoded != 0u) {
+            output_marg(decoded, LDPC_REASON_DECODED);
+            __syncthreads();                                 // marg is rewritten below
+        }
+
+        // ======================================= variable-node phase =======================================
 #pragma unroll
-                for (int k = 0; k < DVP; ++k)
-                    if (k < dv) cmsg[k] = msg[pos.get(k) * Q + q];
-                const float4 pr = prior[vv * Q + q];
-                uint32_t bits = 0u;
+        for (int ps = 0; ps < kResVnPasses; ++ps) {
+            const int item = tid + ps * T;
+            if (item < p.vn_items) {
+                float4 c[DVP];
+#pragma unroll
+                for (int k = 0; k < DVP; ++k) c[k] = c2v[lds_u16x2(vidx[ps][k >> 1], k & 1)];
+                const float4 pr = prior[item];
+                float4 mgv;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float a[DVP], o[DVP];
+                    float s = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < DVP; ++k) a[k] = (k < dv) ? (&cmsg[k].x)[j] : 0.0f;
-                    const float marg = vn_update<float, DVP>((&pr.x)[j], a, dv, o);
-#pragma unroll
-                    for (int k = 0; k < DVP; ++k)
-                        if (k < dv) (&cmsg[k].x)[j] = o[k];
-                    bits |= (marg < 0.0f ? 1u : 0u) << j;
+                    for (int k = 0; k < DVP; ++k) s = __fadd_rn(s, (&c[k].x)[j]);      // padding edges add +0.0: exact
+                    (&mgv.x)[j] = __fadd_rn((&pr.x)[j], s);                            // bpa.py:35
                 }
-#pragma unroll
-                for (int k = 0; k < DVP; ++k)
-                    if (k < dv) msg[pos.get(k) * Q + q] = cmsg[k];
-                const uint32_t runq = (run >> (4 * q)) & 0xFu;
-                uint8_t *xw = xb + q * n + vv;
-                *xw = (uint8_t)((*xw & ~runq) | (bits & runq));                       // stopped frames keep their bits
+                marg[item] = mgv;
             }
-            __syncthreads();
         }
-
-        // ---- store: words, iteration counts, exit reasons (frames still running hit the loop bound)
-        for (int i = tid; i < n * F; i += T) {
-            const int f = i / n, v = i % n;
-            if ((valid >> f) & 1u) p.x_hat[(size_t)(g0 + f) * n + v] = (uint8_t)((xb[(f >> 2) * n + v] >> (f & 3)) & 1u);
-        }
-        if (tid < F && ((valid >> tid) & 1u)) {
-            p.iters[g0 + tid] = my_iters;
-            if (p.reason != nullptr)
-                p.reason[g0 + tid] = ((act >> tid) & 1u) ? (uint8_t)p.bound_reason : (uint8_t)LDPC_REASON_DECODED;
-        }
+        __syncthreads();
+        const uint32_t maxed = s_maxed[par];
+        if (maxed != 0u) output_marg(maxed, p.bound_reason);
+        active = run & ~maxed;
+        freem |= decoded | maxed;
+        par ^= 1;
     }
-}
-
-inline size_t resident_smem_bytes(int n, int m, int S, int F, int DCP, int DVP)
-{
-    const int Q = F / 4;
-    size_t b = 0;
-    b += (size_t)m * S * Q * 16;        // msg
-    b += (size_t)n * Q * 16;            // prior
-    b += (size_t)m * DCP * 2;           // cvar
-    b += (size_t)n * DVP * 2;           // vpos
-    b += (size_t)Q * n;                 // xb
-    b += (size_t)m + n;                 // degrees
-    return align_up(b, 16) + 16;
 }
 
 }  // namespace ldpc
