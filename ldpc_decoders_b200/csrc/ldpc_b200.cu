@@ -541,6 +541,7 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     rp.src = in.src;
     rp.y_hard = in.y_hard;
     rp.param = in.param;
+    rp.inv_param = (in.param != 0.0) ? 1.0 / in.param : 0.0;
     switch (in.channel) {
     case LDPC_CH_PRIORS: rp.in_mode = IN_COPY; rp.in_es = (in.in_dtype == LDPC_F64) ? 8 : 4; break;
     case LDPC_CH_BSC: rp.in_mode = IN_BSC; rp.in_es = 1; break;
@@ -555,8 +556,7 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
 
     // Ring of received rows landed by the bulk-copy engine: needs 16-byte aligned rows; as deep as shared memory allows.
     const size_t row_bytes = (size_t)t.n * rp.in_es;
-    size_t stride = align_up(row_bytes, 16);
-    while ((stride / 4) % 32 != 4) stride += 16;            // slot s, variable v -> bank (4 s + v) mod 32 in the refill loop
+    const size_t stride = align_up(row_bytes, 16);
     const size_t budget = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
     const size_t state = resident_smem_layout(t.n, t.m, r.planes, 0, 0).total;
     int ring = 0;

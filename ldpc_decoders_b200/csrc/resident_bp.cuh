@@ -53,7 +53,7 @@ struct ResParams {
     int in_mode;                       // IN_COPY / IN_BSC / IN_BIAWGN
     int in_es;                         // element size of src: 1 (BSC), 4, 8
     const uint8_t *y_hard;             // optional hard input for IN_COPY
-    double param;
+    double param, inv_param;           // inv_param = 1 / param (BIAWGN fast path)
     int B, limit, bound_reason;
     float sat_llr;                     // SPA: reference saturation point (ldpc_math.cuh)
     uint8_t *x_hat;
@@ -82,17 +82,29 @@ __host__ __device__ inline ResSmem resident_smem_layout(int n, int m, int planes
     return L;
 }
 
-__device__ __forceinline__ float res_llr(const void *row, int v, int in_mode, int in_es, double param, uint32_t *hard)
+// Channel LLR of one received value, rounded exactly like the reference's float64 expression cast to float32
+// (io_kernels.cuh llr_map).  BIAWGN: (-2 y) / noise_var needs a float64 division per value; the product with the
+// reciprocal is within 2 ulp (double) of the quotient, so it rounds to the same float unless it lies within 4 ulp
+// of a float32 rounding boundary (probability 2^-26) or outside the normal float32 range — only then divide.
+__device__ __forceinline__ float res_llr(const void *row, int v, int in_mode, int in_es, double param, double inv_param, uint32_t *hard)
 {
     *hard = 0u;
     float val;
     if (in_mode == IN_BSC) {
         const uint8_t y = ((const uint8_t *)row)[v];
         *hard = (uint32_t)(y != 0);
-        val = (float)(param * (double)(1 - 2 * (int)y));
-    } else {
+        const float lf = (float)param;                                   // (float)(L * (+-1)) == +-(float)L
+        val = y ? -lf : lf;
+    } else if (in_mode == IN_BIAWGN) {
         const double y = (in_es == 8) ? ((const double *)row)[v] : (double)((const float *)row)[v];
-        val = (in_mode == IN_BIAWGN) ? (float)((-2.0 * y) / param) : (float)y;
+        const double t = -2.0 * y;                                       // exact
+        const double pr = t * inv_param;
+        const uint32_t lo = (uint32_t)__double2loint(pr) & 0x1fffffffu;  // mantissa bits below float32 precision
+        const double ap = fabs(pr);
+        const bool safe = (lo - 0x0ffffffcu) > 8u && ap >= 2e-38 && ap < 3e38;
+        val = safe ? (float)pr : (float)(t / param);
+    } else {
+        val = (in_es == 8) ? (float)((const double *)row)[v] : ((const float *)row)[v];
     }
     return __fadd_rn(val, 0.0f);          // -0.0 -> +0.0 (value-neutral, see cn_msa_lean), NaN -> canonical
 }
@@ -263,38 +275,29 @@ __global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams
             exhausted = s_exhausted != 0u;
             if (nm == 0u) break;
 
-            // ---- received rows -> prior / marg columns.  lane = (variable mod 4, slot): the 8 slots x 4 variables
-            //      of a warp store to 32 different banks.
-            {
-                const int s = lane & 7, vl = lane >> 3;
-                const bool mine = (nm >> s) & 1u;
-                const void *row = nullptr;
-                const uint8_t *hrow = nullptr;
-                if (mine) {
-                    const int g = s_frame[s];
-                    if (async) {
-                        const int e = s_assign[s];
-                        mbar_wait(&bars[e], (uint32_t)(r_uses[e] & 1));
-                        row = stage + (size_t)e * p.stage_stride;
-                    } else {
-                        row = (const char *)p.src + (size_t)g * row_bytes;
-                    }
-                    if (p.in_mode == IN_COPY && p.y_hard != nullptr) hrow = p.y_hard + (size_t)g * n;
+            // ---- received rows -> prior / marg columns, one new slot at a time (cost proportional to the frames loaded)
+            for (int s = 0; s < F; ++s) {
+                if (!((nm >> s) & 1u)) continue;
+                const int g = s_frame[s];
+                const void *row;
+                if (async) {
+                    const int e = s_assign[s];
+                    mbar_wait(&bars[e], (uint32_t)(r_uses[e] & 1));
+                    row = stage + (size_t)e * p.stage_stride;
+                } else {
+                    row = (const char *)p.src + (size_t)g * row_bytes;
                 }
+                const uint8_t *hrow = (p.in_mode == IN_COPY && p.y_hard != nullptr) ? p.y_hard + (size_t)g * n : nullptr;
                 float *mcol = reinterpret_cast<float *>(marg) + (s >> 2) * 4 + (s & 3);
                 float *pcol = reinterpret_cast<float *>(prior) + (s >> 2) * 4 + (s & 3);
-                for (int vb = warp * 4; vb < n; vb += nwarps * 4) {
-                    const int v = vb + vl;
-                    uint32_t hbit = 0u;
-                    if (mine && v < n) {
-                        const float val = res_llr(row, v, p.in_mode, p.in_es, p.param, &hbit);
-                        if (hrow != nullptr) hbit = (uint32_t)(hrow[v] != 0);
-                        mcol[(size_t)v * (Q * 4)] = val;
-                        pcol[(size_t)v * (Q * 4)] = val;
-                    }
+                for (int v = tid; v < n; v += T) {
+                    uint32_t hbit;
+                    const float val = res_llr(row, v, p.in_mode, p.in_es, p.param, p.inv_param, &hbit);
+                    mcol[(size_t)v * (Q * 4)] = val;
+                    pcol[(size_t)v * (Q * 4)] = val;
                     if (have_hard) {
-                        const uint32_t bal = __ballot_sync(kFull, hbit != 0u);
-                        if (s == 0 && v < n) hb[v] = (uint8_t)((bal >> (lane & ~7)) & 0xffu);
+                        if (hrow != nullptr) hbit = (uint32_t)(hrow[v] != 0);
+                        hb[v] = (uint8_t)((hb[v] & ~(1u << s)) | (hbit << s));       // the same thread owns hb[v] for every slot
                     }
                 }
             }
