@@ -76,6 +76,7 @@ extern "C" {
 #define LDPC_SPA_ROBUST     4u   /* float32 SPA: do not emulate the reference's float64 tanh saturation (|v| > 38.123
                                     contributes exactly 0, which is what floods a frame with inf/NaN in the reference);
                                     honoured by the resident path */
+#define LDPC_RES_ONE_CTA   16u   /* resident path: one CTA of 8 frame slots per SM instead of two CTAs of 4 (A/B measurements) */
 #define LDPC_CN_REGISTER    8u   /* streaming path: use the register-staged check-node sweep instead of the
                                     bulk-async (TMA) staged one (A/B measurements; it is also the fallback for
                                     check degrees > 8) */

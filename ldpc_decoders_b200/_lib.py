@@ -12,6 +12,7 @@ CH_PRIORS, CH_BSC, CH_BIAWGN, CH_BEC = 0, 1, 2, 3
 PATH_AUTO, PATH_STREAMING, PATH_RESIDENT = 0, 1, 2
 SPA_ROBUST = 4
 CN_REGISTER = 8
+RES_ONE_CTA = 16
 REASONS = {0: "decoded", 1: "maximum", 2: "stopping", 4: "cap"}
 
 # every symbol include/ldpc_b200.h declares

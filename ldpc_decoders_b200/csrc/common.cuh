@@ -34,7 +34,9 @@ struct ResidentInfo {                        // compact tables of the on-chip pa
     bool regular36 = false;                  // every check has 6 edges and every variable 3: the register-resident variant
     uint16_t *cvar = nullptr, *vrow = nullptr;
     uint8_t *cdeg = nullptr, *vdeg = nullptr;
-    int planes = 0, threads = 0;
+    int planes = 0, threads = 0, threads2 = 0;
+    bool ok2 = false;                        // the 8-slot geometry fits too (LDPC_RES_ONE_CTA)
+    int Q = 0;                               // quads per CTA: 2 (8 slots, one CTA per SM) or 1 (4 slots, two CTAs per SM)
 };
 
 struct ProfEvent {                           // one timed launch (ldpc_profile_*)
@@ -45,7 +47,7 @@ struct ProfEvent {                           // one timed launch (ldpc_profile_*
 struct ldpc_handle {
     int device = 0;
     int sm_count = 148;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0, smem_per_sm = 0;
     ldpc::Tables t;
     std::string err;
     unsigned long long launches = 0;

@@ -502,15 +502,16 @@ struct ResLaunch {
     size_t smem;
 };
 
-template <int ALGO, int DCP, bool UDC, int DVP, bool UDV, bool REGC>
+template <int Q, int ALGO, int DCP, bool UDC, int DVP, bool UDV, bool REGC, bool VSM>
 int launch_resident_t(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
-    auto kern = resident_bp<ALGO, DCP, UDC, DVP, UDV, REGC>;
+    auto kern = resident_bp<Q, ALGO, DCP, UDC, DVP, UDV, REGC, VSM>;
     static size_t opted = 0;               // the attribute is per kernel instance: raise it when a larger code comes along
     if (lc.smem > opted) {
         int rc = opt_in_smem(h, kern, lc.smem);
         if (rc) return rc;
         opted = lc.smem;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lc.threads, lc.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -537,7 +538,9 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     ResParams rp;
     rp.n = t.n; rp.m = t.m; rp.planes = r.planes;
     rp.cvar = r.cvar; rp.vrow = r.vrow; rp.cdeg = r.cdeg; rp.vdeg = r.vdeg;
-    rp.cn_items = t.m * kResQ; rp.vn_items = t.n * kResQ;
+    const int Q = (flags & LDPC_RES_ONE_CTA) ? 2 : r.Q;
+    if (Q == 2 && !r.ok2) return fail(h, LDPC_EUNSUPPORTED, "this code does not fit the 8-slot geometry of the resident kernel");
+    rp.cn_items = t.m * Q; rp.vn_items = t.n * Q;
     rp.src = in.src;
     rp.y_hard = in.y_hard;
     rp.param = in.param;
@@ -557,27 +560,34 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     // Ring of received rows landed by the bulk-copy engine: needs 16-byte aligned rows; as deep as shared memory allows.
     const size_t row_bytes = (size_t)t.n * rp.in_es;
     const size_t stride = align_up(row_bytes, 16);
-    const size_t budget = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
-    const size_t state = resident_smem_layout(t.n, t.m, r.planes, 0, 0).total;
+    const size_t sm_bytes = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
+    const size_t budget = (Q == 2) ? sm_bytes : (h->smem_per_sm / 2 > 2048 ? h->smem_per_sm / 2 - 1536 : 0);    // Q = 1: two CTAs share an SM
+    const int vtw = r.regular36 ? 2 : 0;                     // (3,6) variant keeps the variable-edge table in shared memory
+    const size_t state = resident_smem_layout(Q, t.n, t.m, r.planes, vtw, 0, 0).total;
     int ring = 0;
     if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(in.src) & 15u) == 0 && budget > state)
         ring = (int)std::min<size_t>(kResRingMax, (budget - state) / stride);
     rp.ring = ring;
     rp.stage_stride = (int)stride;
     ResLaunch lc;
-    lc.threads = r.threads;
-    lc.smem = resident_smem_layout(t.n, t.m, r.planes, ring, (int)stride).total;
-    const int max_grid = (B + kResF - 1) / kResF;
+    lc.threads = (Q == 2) ? r.threads2 : r.threads;
+    lc.smem = resident_smem_layout(Q, t.n, t.m, r.planes, vtw, ring, (int)stride).total;
+    const int max_grid = (B + 4 * Q - 1) / (4 * Q);
 
     CUDA_TRY(h, cudaMemsetAsync(rp.counter, 0, sizeof(int), s));
     ProfEvent *pe = prof_begin(h, 0, s);
     int rc;
-    if (r.regular36)
-        rc = (algo == LDPC_MSA) ? launch_resident_t<ALGO_MSA, 6, true, 3, true, true>(h, rp, lc, max_grid, s)
-                                : launch_resident_t<ALGO_SPA_PHI, 6, true, 3, true, true>(h, rp, lc, max_grid, s);
-    else
-        rc = (algo == LDPC_MSA) ? launch_resident_t<ALGO_MSA, 8, false, 8, false, false>(h, rp, lc, max_grid, s)
-                                : launch_resident_t<ALGO_SPA_PHI, 8, false, 8, false, false>(h, rp, lc, max_grid, s);
+#define RES_LAUNCH(QQ)                                                                                                   \
+    do {                                                                                                                \
+        if (r.regular36)                                                                                                \
+            rc = (algo == LDPC_MSA) ? launch_resident_t<QQ, ALGO_MSA, 6, true, 3, true, true, true>(h, rp, lc, max_grid, s)     \
+                                    : launch_resident_t<QQ, ALGO_SPA_PHI, 6, true, 3, true, true, true>(h, rp, lc, max_grid, s); \
+        else                                                                                                            \
+            rc = (algo == LDPC_MSA) ? launch_resident_t<QQ, ALGO_MSA, 8, false, 8, false, false, false>(h, rp, lc, max_grid, s) \
+                                    : launch_resident_t<QQ, ALGO_SPA_PHI, 8, false, 8, false, false, false>(h, rp, lc, max_grid, s); \
+    } while (0)
+    if (Q == 2) RES_LAUNCH(2); else RES_LAUNCH(1);
+#undef RES_LAUNCH
     prof_end(pe, s);
     if (rc) return rc;
     return check_launch(h, "decode_bp_resident");
@@ -590,19 +600,28 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
     ResidentInfo &r = h->res;
     if (t.max_dc > 8 || t.max_dv > 8 || t.max_dc < 1) return LDPC_OK;
     r.planes = t.max_dc;
-    if ((long long)r.planes * t.m * kResQ + 1 > 65535) return LDPC_OK;               // c2v float4 index must fit 16 bits
-    if (((long long)t.n * kResQ + 1) * 16 > 65535) return LDPC_OK;                   // marg byte offset must fit 16 bits
-    const size_t budget = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
-    if (resident_smem_layout(t.n, t.m, r.planes, 0, 0).total > budget) return LDPC_OK;
-    // threads: check items (m * Q) in at most 2 passes, variable items (n * Q) in at most 4
-    const int citems = t.m * kResQ, vitems = t.n * kResQ;
-    const int need = std::max((citems + kResCnPasses - 1) / kResCnPasses, (vitems + kResVnPasses - 1) / kResVnPasses);
-    int T = std::max(64, (need + 31) / 32 * 32);
-    if (citems <= kResMaxThreads && vitems <= 2 * kResMaxThreads) T = std::max(64, (std::max(citems, (vitems + 1) / 2) + 31) / 32 * 32);
-    if (T > kResMaxThreads) return LDPC_OK;
-    r.threads = T;
     r.regular36 = (t.uni_dc == 6 && t.uni_dv == 3);
-
+    const int vtw = r.regular36 ? 2 : 0;
+    // Geometry: threads so that the check items (m * Q) take at most 2 passes and the variable items (n * Q) at most 4.
+    auto geometry = [&](int Q, size_t budget, int *threads) -> bool {
+        if ((long long)r.planes * t.m * Q + 1 > 65535) return false;                 // c2v float4 index must fit 16 bits
+        if (((long long)t.n * Q + 1) * 16 > 65535) return false;                     // marg byte offset must fit 16 bits
+        if (resident_smem_layout(Q, t.n, t.m, r.planes, vtw, 0, 0).total > budget) return false;
+        const int citems = t.m * Q, vitems = t.n * Q, maxT = res_max_threads(Q);
+        int T = std::max((citems + kResCnPasses - 1) / kResCnPasses, (vitems + kResVnPasses - 1) / kResVnPasses);
+        if (citems <= maxT && vitems <= 2 * maxT) T = std::max(citems, (vitems + 1) / 2);
+        T = std::max(64, (T + 31) / 32 * 32);
+        if (T > maxT) return false;
+        *threads = T;
+        return true;
+    };
+    const size_t sm_bytes = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
+    const size_t half_bytes = h->smem_per_sm / 2 > 2048 ? h->smem_per_sm / 2 - 1536 : 0;
+    r.ok2 = geometry(2, sm_bytes, &r.threads2);
+    const bool ok1 = geometry(1, half_bytes, &r.threads);
+    if (!ok1 && !r.ok2) return LDPC_OK;
+    r.Q = ok1 ? 1 : 2;
+    if (!ok1) r.threads = r.threads2;
     std::vector<uint16_t> cvar((size_t)t.m * 8, (uint16_t)t.n), vrow((size_t)t.n * 8, 0);
     std::vector<uint8_t> cdeg((size_t)t.m), vdeg((size_t)t.n);
     std::vector<int> row_of_edge((size_t)t.E);
@@ -728,7 +747,7 @@ const char *ldpc_last_error(const ldpc_t *h) { return h ? h->err.c_str() : g_cre
 
 unsigned long long ldpc_launch_count(const ldpc_t *h) { return h ? h->launches : 0ull; }
 
-int ldpc_resident_frames(const ldpc_t *h) { return (h && h->res.ok) ? kResF : 0; }
+int ldpc_resident_frames(const ldpc_t *h) { return (h && h->res.ok) ? 4 * h->res.Q : 0; }
 
 int ldpc_create(ldpc_t **out, int device, int n, int m, int E,
                 const int32_t *chk_ptr, const int32_t *edge_var,
@@ -779,6 +798,7 @@ int ldpc_create(ldpc_t **out, int device, int n, int m, int E,
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
         h->sm_count = prop.multiProcessorCount;
         h->smem_optin = prop.sharedMemPerBlockOptin;
+        h->smem_per_sm = prop.sharedMemPerMultiprocessor;
     }
     Tables &t = h->t;
     t.n = n; t.m = m; t.E = E;

@@ -35,9 +35,11 @@
 
 namespace ldpc {
 
-constexpr int kResF = 8;                     // frames (slots) per CTA
-constexpr int kResQ = 2;                     // quads per CTA
-constexpr int kResMaxThreads = 608;          // 65536 registers / 104
+// Two geometries: Q = 2 quads (8 slots) in one CTA per SM of up to 608 threads, or Q = 1 quad (4 slots) in CTAs of up
+// to 320 threads, two of which share an SM and hide each other's barriers and refills.
+constexpr int kResMaxQ = 2;
+constexpr int kResMaxF = 4 * kResMaxQ;       // slots per CTA
+__host__ __device__ constexpr int res_max_threads(int Q) { return Q == 2 ? 608 : 320; }    // 96 registers per thread either way
 constexpr int kResCnPasses = 2;              // check items per thread  (m * Q <= 2 * threads)
 constexpr int kResVnPasses = 4;              // variable items per thread (n * Q <= 4 * threads)
 constexpr int kResRingMax = 8;               // staged received rows
@@ -66,15 +68,17 @@ struct ResParams {
 
 // Shared-memory carve-up, shared by the kernel and the host-side size computation.
 struct ResSmem {
-    size_t c2v, marg, prior, stage, hb, bars, total;
+    size_t c2v, marg, prior, vtab, stage, hb, bars, total;
 };
-__host__ __device__ inline ResSmem resident_smem_layout(int n, int m, int planes, int ring, int stage_stride)
+// vtab_words: 32-bit words per variable item of the shared-memory edge table (0: the table lives in registers).
+__host__ __device__ inline ResSmem resident_smem_layout(int Q, int n, int m, int planes, int vtab_words, int ring, int stage_stride)
 {
     ResSmem L;
     size_t o = 0;
-    L.c2v = o;   o += ((size_t)planes * m * kResQ + 1) * 16;          // + one all-zero cell (padding edges of a variable)
-    L.marg = o;  o += ((size_t)n * kResQ + 1) * 16;                   // + one +inf cell (padding edges of a check)
-    L.prior = o; o += (size_t)n * kResQ * 16;
+    L.c2v = o;   o += ((size_t)planes * m * Q + 1) * 16;          // + one all-zero cell (padding edges of a variable)
+    L.marg = o;  o += ((size_t)n * Q + 1) * 16;                   // + one +inf cell (padding edges of a check)
+    L.prior = o; o += (size_t)n * Q * 16;
+    L.vtab = o;  o += ((size_t)n * Q * vtab_words * 4 + 15) / 16 * 16;
     L.stage = o; o += (size_t)ring * stage_stride;
     L.bars = o;  o += (size_t)kResRingMax * 8;
     L.hb = o;    o += ((size_t)n + 15) / 16 * 16;
@@ -86,6 +90,8 @@ __host__ __device__ inline ResSmem resident_smem_layout(int n, int m, int planes
 // (io_kernels.cuh llr_map).  BIAWGN: (-2 y) / noise_var needs a float64 division per value; the product with the
 // reciprocal is within 2 ulp (double) of the quotient, so it rounds to the same float unless it lies within 4 ulp
 // of a float32 rounding boundary (probability 2^-26) or outside the normal float32 range — only then divide.
+__device__ __noinline__ float res_llr_biawgn_exact(double t, double param) { return (float)(t / param); }
+
 __device__ __forceinline__ float res_llr(const void *row, int v, int in_mode, int in_es, double param, double inv_param, uint32_t *hard)
 {
     *hard = 0u;
@@ -102,7 +108,8 @@ __device__ __forceinline__ float res_llr(const void *row, int v, int in_mode, in
         const uint32_t lo = (uint32_t)__double2loint(pr) & 0x1fffffffu;  // mantissa bits below float32 precision
         const double ap = fabs(pr);
         const bool safe = (lo - 0x0ffffffcu) > 8u && ap >= 2e-38 && ap < 3e38;
-        val = safe ? (float)pr : (float)(t / param);
+        val = (float)pr;
+        if (!safe) val = res_llr_biawgn_exact(t, param);             // rare: keep the division out of line
     } else {
         val = (in_es == 8) ? (float)((const double *)row)[v] : ((const float *)row)[v];
     }
@@ -119,15 +126,17 @@ __device__ __forceinline__ uint32_t lds_u16x2(const uint32_t w, int hi)
     return r;
 }
 
-template <int ALGO, int DCP, bool UDC, int DVP, bool UDV, bool REGC>
-__global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams p)
+template <int Q, int ALGO, int DCP, bool UDC, int DVP, bool UDV, bool REGC, bool VSM>
+__global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const ResParams p)
 {
-    constexpr int Q = kResQ, F = kResF;
+    constexpr int F = 4 * Q, QSH = (Q == 2) ? 1 : 0;
     constexpr int CH = (DCP + 1) / 2, VH = (DVP + 1) / 2;
+    constexpr int VR = VSM ? 1 : kResVnPasses;
     constexpr uint32_t ALL = (1u << F) - 1u;
     extern __shared__ __align__(128) unsigned char smem[];
     const int n = p.n, m = p.m;
-    const ResSmem L = resident_smem_layout(n, m, p.planes, p.ring, p.stage_stride);
+    const ResSmem L = resident_smem_layout(Q, n, m, p.planes, VSM ? VH : 0, p.ring, p.stage_stride);
+    uint32_t *vtab = reinterpret_cast<uint32_t *>(smem + L.vtab);      // VSM: [n * Q][VH] packed c2v indices of a variable item
     float4 *c2v = reinterpret_cast<float4 *>(smem + L.c2v);
     float4 *marg = reinterpret_cast<float4 *>(smem + L.marg);
     float4 *prior = reinterpret_cast<float4 *>(smem + L.prior);
@@ -137,12 +146,12 @@ __global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams
     const uint32_t zero_cell = (uint32_t)p.planes * m * Q;           // float4 index into c2v
     const uint32_t inf_off = (uint32_t)n * Q * 16;                   // byte offset into marg
 
-    __shared__ int s_frame[F], s_it[F], s_assign[F];
+    __shared__ int s_frame[kResMaxF], s_it[kResMaxF], s_assign[kResMaxF];
     __shared__ int r_frame[kResRingMax], r_uses[kResRingMax];
     __shared__ uint32_t s_unsat[2], s_maxed[2], s_unsat0, s_newmask, s_exhausted;
 
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-    const int q = tid & 1;                                           // T is even: every item of a thread is in quad q
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+    const int q = tid & (Q - 1);                                     // T is even: every item of a thread is in quad q
     const bool async = p.ring > 0;
     const bool have_hard = (p.in_mode == IN_BSC) || (p.in_mode == IN_COPY && p.y_hard != nullptr);
     const size_t row_bytes = (size_t)n * p.in_es;
@@ -150,7 +159,7 @@ __global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams
     // ---- per-thread graph indices -> registers (once per CTA)
     uint32_t cidx[kResCnPasses][CH];          // byte offsets into marg of the check's variables, two per word
     int cdeg[kResCnPasses];
-    uint32_t vidx[kResVnPasses][VH];          // float4 indices into c2v of the variable's edges, two per word
+    uint32_t vidx[VR][VH];                    // float4 indices into c2v of the variable's edges, two per word (VSM: staged in vtab)
 #pragma unroll
     for (int ps = 0; ps < kResCnPasses; ++ps) {
         const int item = tid + ps * T;
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams
 #pragma unroll
         for (int h = 0; h < CH; ++h) cidx[ps][h] = inf_off | (inf_off << 16);
         if (item < p.cn_items) {
-            const int c = item >> 1;
+            const int c = item >> QSH;
             cdeg[ps] = UDC ? DCP : (int)p.cdeg[c];
 #pragma unroll
             for (int k = 0; k < DCP; ++k) {
@@ -172,18 +181,24 @@ __global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams
 #pragma unroll
     for (int ps = 0; ps < kResVnPasses; ++ps) {
         const int item = tid + ps * T;
+        uint32_t w[VH];
 #pragma unroll
-        for (int h = 0; h < VH; ++h) vidx[ps][h] = zero_cell | (zero_cell << 16);
+        for (int h = 0; h < VH; ++h) w[h] = zero_cell | (zero_cell << 16);
         if (item < p.vn_items) {
-            const int v = item >> 1;
+            const int v = item >> QSH;
             const int dv = UDV ? DVP : (int)p.vdeg[v];
 #pragma unroll
             for (int k = 0; k < DVP; ++k) {
                 const uint32_t row = p.vrow[(size_t)v * 8 + k];
                 const uint32_t idx = (k < dv) ? row * Q + q : zero_cell;
-                if (k & 1) vidx[ps][k >> 1] = (vidx[ps][k >> 1] & 0xffffu) | (idx << 16);
-                else vidx[ps][k >> 1] = (vidx[ps][k >> 1] & 0xffff0000u) | idx;
+                if (k & 1) w[k >> 1] = (w[k >> 1] & 0xffffu) | (idx << 16);
+                else w[k >> 1] = (w[k >> 1] & 0xffff0000u) | idx;
             }
+        }
+#pragma unroll
+        for (int h = 0; h < VH; ++h) {
+            if (VSM) { if (item < p.vn_items) vtab[(size_t)item * VH + h] = w[h]; }
+            else vidx[ps][h] = w[h];
         }
     }
     float4 old[REGC ? kResCnPasses : 1][REGC ? DCP : 1];            // c2v of the thread's own checks
@@ -222,18 +237,25 @@ __global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams
     if (tid == 0 && async)
         for (int e = 0; e < p.ring; ++e) issue(e);
 
-    // hard decisions of the slots in `mask` -> global, from the sign of marg (bpa.py:62; NaN and 0 -> bit 0)
-    auto output_marg = [&](uint32_t mask, int why) {
-        for (int s = 0; s < F; ++s) {
-            if (!((mask >> s) & 1u)) continue;
-            const int g = s_frame[s];
-            const float *col = reinterpret_cast<const float *>(marg) + (s >> 2) * 4 + (s & 3);
-            uint8_t *dst = p.x_hat + (size_t)g * n;
-            for (int v = tid; v < n; v += T) dst[v] = (uint8_t)(col[(size_t)v * (Q * 4)] < 0.0f);
-            if (tid == 0) {
-                p.iters[g] = s_it[s];
-                if (p.reason != nullptr) p.reason[g] = (uint8_t)why;
+    // Hard decisions (bpa.py:62; NaN and 0 -> bit 0) of the thread's own variable items after the last VN phase:
+    // bit 4 * pass + j = frame j of the quad.  A leaving frame is written out from these registers.
+    uint32_t hbits = 0u;
+    auto output_bits = [&](uint32_t mask, int why) {
+        uint32_t mq = (mask >> (4 * q)) & 0xFu;
+        while (mq != 0u) {
+            const int j = __ffs(mq) - 1;
+            mq &= mq - 1u;
+            uint8_t *dst = p.x_hat + (size_t)s_frame[4 * q + j] * n;
+#pragma unroll
+            for (int ps = 0; ps < kResVnPasses; ++ps) {
+                const int item = tid + ps * T;
+                if (item < p.vn_items) dst[item >> QSH] = (uint8_t)((hbits >> (4 * ps + j)) & 1u);
             }
+        }
+        if (tid < F && ((mask >> tid) & 1u)) {
+            const int g = s_frame[tid];
+            p.iters[g] = s_it[tid];
+            if (p.reason != nullptr) p.reason[g] = (uint8_t)why;
         }
     };
 
@@ -271,8 +293,8 @@ __global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams
                 s_unsat0 = 0u;
             }
             __syncthreads();
-            const uint32_t nm = s_newmask;
-            exhausted = s_exhausted != 0u;
+            const uint32_t nm = __reduce_or_sync(kFull, s_newmask);          // warp-uniform by construction: keep the
+            exhausted = __reduce_or_sync(kFull, s_exhausted) != 0u;          // slot masks in uniform registers
             if (nm == 0u) break;
 
             // ---- received rows -> prior / marg columns, one new slot at a time (cost proportional to the frames loaded)
@@ -344,14 +366,14 @@ __global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams
                         uint32_t syn = 0u;
 #pragma unroll
                         for (int k = 0; k < DCP; ++k)
-                            if (UDC || k < cdeg[ps]) syn ^= hb[lds_u16x2(cidx[ps][k >> 1], k & 1) >> 5];
+                            if (UDC || k < cdeg[ps]) syn ^= hb[lds_u16x2(cidx[ps][k >> 1], k & 1) >> (4 + QSH)];
                         u0 |= ((syn >> (4 * q)) & 0xFu) << (4 * q);
                     }
                 }
                 u0 = __reduce_or_sync(kFull, u0);
                 if (lane == 0 && u0 != 0u) atomicOr(&s_unsat0, u0);
                 __syncthreads();
-                z = nm & ~s_unsat0;
+                z = nm & ~__reduce_or_sync(kFull, s_unsat0);
                 for (int s = 0; s < F; ++s) {
                     if (!((z >> s) & 1u)) continue;
                     const int g = s_frame[s];
@@ -425,7 +447,7 @@ __global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams
         __syncthreads();
 
         // ---- book-keeping: frames whose syndrome was zero leave here (bpa.py:29), iteration count unchanged
-        const uint32_t us = s_unsat[par] | fresh;            // a new frame's marg is its prior: no syndrome yet
+        const uint32_t us = __reduce_or_sync(kFull, s_unsat[par]) | fresh;            // a new frame's marg is its prior: no syndrome yet
         const uint32_t decoded = active & ~us;
         const uint32_t run = active & us;
         fresh = 0u;
@@ -434,34 +456,38 @@ __global__ void __launch_bounds__(kResMaxThreads, 1) resident_bp(const ResParams
             if (it >= p.limit) atomicOr(&s_maxed[par], 1u << tid);       // bpa.py:28 at the top of the next round
         }
         if (tid == 0) { s_unsat[par ^ 1] = 0u; s_maxed[par ^ 1] = 0u; }
-        if (decoded != 0u) {
-            output_marg(decoded, LDPC_REASON_DECODED);
-            __syncthreads();                                 // marg is rewritten below
-        }
+        if (decoded != 0u) output_bits(decoded, LDPC_REASON_DECODED);     // hbits still are those of the last VN phase
 
         // ======================================= variable-node phase =======================================
 #pragma unroll
         for (int ps = 0; ps < kResVnPasses; ++ps) {
             const int item = tid + ps * T;
             if (item < p.vn_items) {
+                uint32_t w[VH];
+#pragma unroll
+                for (int h = 0; h < VH; ++h) w[h] = VSM ? vtab[(size_t)item * VH + h] : vidx[VSM ? 0 : ps][h];
                 float4 c[DVP];
 #pragma unroll
-                for (int k = 0; k < DVP; ++k) c[k] = c2v[lds_u16x2(vidx[ps][k >> 1], k & 1)];
+                for (int k = 0; k < DVP; ++k) c[k] = c2v[VSM ? ((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu)) : lds_u16x2(w[k >> 1], k & 1)];
                 const float4 pr = prior[item];
                 float4 mgv;
+                uint32_t hb4 = 0u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float s = 0.0f;
 #pragma unroll
                     for (int k = 0; k < DVP; ++k) s = __fadd_rn(s, (&c[k].x)[j]);      // padding edges add +0.0: exact
-                    (&mgv.x)[j] = __fadd_rn((&pr.x)[j], s);                            // bpa.py:35
+                    const float mj = __fadd_rn((&pr.x)[j], s);                         // bpa.py:35
+                    (&mgv.x)[j] = mj;
+                    hb4 |= (mj < 0.0f ? 1u : 0u) << j;
                 }
+                hbits = (hbits & ~(0xFu << (4 * ps))) | (hb4 << (4 * ps));
                 marg[item] = mgv;
             }
         }
         __syncthreads();
-        const uint32_t maxed = s_maxed[par];
-        if (maxed != 0u) output_marg(maxed, p.bound_reason);
+        const uint32_t maxed = __reduce_or_sync(kFull, s_maxed[par]);
+        if (maxed != 0u) output_bits(maxed, p.bound_reason);
         active = run & ~maxed;
         freem |= decoded | maxed;
         par ^= 1;
