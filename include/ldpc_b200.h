@@ -76,7 +76,6 @@ extern "C" {
 #define LDPC_SPA_ROBUST     4u   /* float32 SPA: do not emulate the reference's float64 tanh saturation (|v| > 38.123
                                     contributes exactly 0, which is what floods a frame with inf/NaN in the reference);
                                     honoured by the resident path */
-#define LDPC_RES_ONE_CTA   16u   /* resident path: one CTA of 8 frame slots per SM instead of two CTAs of 4 (A/B measurements) */
 #define LDPC_CN_REGISTER    8u   /* streaming path: use the register-staged check-node sweep instead of the
                                     bulk-async (TMA) staged one (A/B measurements; it is also the fallback for
                                     check degrees > 8) */
@@ -184,6 +183,13 @@ int ldpc_profile_read(ldpc_t *h, double *cn_ms, unsigned long long *cn_launches,
 /* Frames a CTA of the on-chip path (LDPC_PATH_RESIDENT) keeps in shared memory for this code, or 0 when the code does
  * not fit on chip (then LDPC_PATH_AUTO streams and LDPC_PATH_RESIDENT is refused with LDPC_EUNSUPPORTED). */
 int ldpc_resident_frames(const ldpc_t *h);
+
+/* Shared-memory placement of the on-chip path (csrc/res_layout.h): predicted 128-bit shared-memory wavefronts per
+ * iteration of the two gather phases, out[7] = { check-node ideal, file order, planned positions with natural edge
+ * order (sum-product), planned (min-sum), variable-node ideal, file order, planned }.  Returns LDPC_EUNSUPPORTED when
+ * the code has no on-chip path.  The annealing effort can be set with the environment variable LDPC_PLAN_EFFORT
+ * (default 0.4; 0 keeps file order) before ldpc_create. */
+int ldpc_resident_plan(const ldpc_t *h, long *out);
 
 /* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
 unsigned long long ldpc_launch_count(const ldpc_t *h);

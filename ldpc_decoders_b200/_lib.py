@@ -12,13 +12,12 @@ CH_PRIORS, CH_BSC, CH_BIAWGN, CH_BEC = 0, 1, 2, 3
 PATH_AUTO, PATH_STREAMING, PATH_RESIDENT = 0, 1, 2
 SPA_ROBUST = 4
 CN_REGISTER = 8
-RES_ONE_CTA = 16
 REASONS = {0: "decoded", 1: "maximum", 2: "stopping", 4: "cap"}
 
 # every symbol include/ldpc_b200.h declares
 SYMBOLS = ("ldpc_abi_version", "ldpc_create", "ldpc_destroy", "ldpc_last_error", "ldpc_workspace_bytes",
            "ldpc_decode", "ldpc_decode_channel", "ldpc_llr_bsc", "ldpc_llr_biawgn", "ldpc_debug_step", "ldpc_decode_host",
-           "ldpc_launch_count", "ldpc_profile_enable", "ldpc_profile_read", "ldpc_resident_frames")
+           "ldpc_launch_count", "ldpc_profile_enable", "ldpc_profile_read", "ldpc_resident_frames", "ldpc_resident_plan")
 
 
 class LdpcError(RuntimeError):
@@ -67,6 +66,8 @@ def load():
                                     ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_ulonglong)]
     L.ldpc_resident_frames.restype = i32
     L.ldpc_resident_frames.argtypes = [vp]
+    L.ldpc_resident_plan.restype = i32
+    L.ldpc_resident_plan.argtypes = [vp, ctypes.POINTER(ctypes.c_long)]
     L.ldpc_launch_count.restype = ctypes.c_ulonglong
     L.ldpc_launch_count.argtypes = [vp]
     if L.ldpc_abi_version() != 1:

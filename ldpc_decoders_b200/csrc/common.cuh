@@ -29,14 +29,17 @@ struct Tables {
 
 struct HostStage;                            // ldpc_decode_host staging (api file)
 
-struct ResidentInfo {                        // compact tables of the on-chip path (resident_bp.cuh)
+struct ResidentInfo {                        // position-indexed tables of the on-chip path (resident_bp.cuh, res_layout.h)
     bool ok = false;
-    bool regular36 = false;                  // every check has 6 edges and every variable 3: the register-resident variant
-    uint16_t *cvar = nullptr, *vrow = nullptr;
+    bool regular36 = false;                  // every check has 6 edges, every variable 3, no holes: the register-resident variant
+    int Q = 1;                               // quads per CTA (4 slots, two CTAs per SM)
+    int np = 0, mp = 0;                      // variable / check positions
+    int planes = 0, threads = 0;
+    // [0]: edge planes ordered for conflict-free gathers (min-sum, symmetric check rule); [1]: natural order (sum-product)
+    uint16_t *cvar[2] = {nullptr, nullptr}, *vrow[2] = {nullptr, nullptr};
     uint8_t *cdeg = nullptr, *vdeg = nullptr;
-    int planes = 0, threads = 0, threads2 = 0;
-    bool ok2 = false;                        // the 8-slot geometry fits too (LDPC_RES_ONE_CTA)
-    int Q = 0;                               // quads per CTA: 2 (8 slots, one CTA per SM) or 1 (4 slots, two CTAs per SM)
+    uint16_t *vposmap = nullptr, *vinvmap = nullptr;
+    long plan[7] = {0, 0, 0, 0, 0, 0, 0};    // predicted wavefronts: cn ideal/file/plan-natural/plan, vn ideal/file/plan
 };
 
 struct ProfEvent {                           // one timed launch (ldpc_profile_*)
@@ -53,6 +56,7 @@ struct ldpc_handle {
     unsigned long long launches = 0;
     HostStage *stage = nullptr;
     ResidentInfo res;
+    double plan_effort = 0.4;                // annealing effort of the shared-memory placement (LDPC_PLAN_EFFORT)
     bool prof = false;
     std::vector<ProfEvent> prof_ev;
     size_t prof_used = 0;

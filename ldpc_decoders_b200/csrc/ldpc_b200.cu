@@ -4,12 +4,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
 
 #include "common.cuh"
 #include "io_kernels.cuh"
+#include "res_layout.h"
 #include "resident_bp.cuh"
 #include "stream_bec.cuh"
 #include "stream_bp.cuh"
@@ -521,6 +523,12 @@ int launch_resident_t(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid
     return LDPC_OK;
 }
 
+// Shared memory one resident CTA may use: two CTAs share an SM (1 KB each is reserved by the system).
+size_t resident_budget(const ldpc_t *h)
+{
+    return h->smem_per_sm / 2 > 4096 ? std::min(h->smem_optin, h->smem_per_sm / 2 - 1536) : 0;
+}
+
 bool resident_eligible(const ldpc_t *h, int algo, int dtype, const void *marg_out)
 {
     return h->res.ok && dtype == LDPC_F32 && (algo == LDPC_MSA || algo == LDPC_SPA) && marg_out == nullptr;
@@ -532,15 +540,16 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
 {
     const Tables &t = h->t;
     const ResidentInfo &r = h->res;
+    constexpr int Q = 1;
     if (ws_bytes < 256) return fail(h, LDPC_EWORKSPACE, "workspace too small");
     const int limit = max_iter > 0 ? max_iter : iter_cap;
     if (limit <= 0) return fail(h, LDPC_EINVAL, "max_iter <= 0 (unlimited in the reference) needs iter_cap > 0");
+    const int tb = (algo == LDPC_MSA) ? 0 : 1;              // sum-product keeps the natural edge order inside a check
     ResParams rp;
-    rp.n = t.n; rp.m = t.m; rp.planes = r.planes;
-    rp.cvar = r.cvar; rp.vrow = r.vrow; rp.cdeg = r.cdeg; rp.vdeg = r.vdeg;
-    const int Q = (flags & LDPC_RES_ONE_CTA) ? 2 : r.Q;
-    if (Q == 2 && !r.ok2) return fail(h, LDPC_EUNSUPPORTED, "this code does not fit the 8-slot geometry of the resident kernel");
-    rp.cn_items = t.m * Q; rp.vn_items = t.n * Q;
+    rp.n = r.np; rp.m = r.mp; rp.nref = t.n; rp.planes = r.planes;
+    rp.cvar = r.cvar[tb]; rp.vrow = r.vrow[tb]; rp.cdeg = r.cdeg; rp.vdeg = r.vdeg;
+    rp.vposmap = r.vposmap; rp.vinvmap = r.vinvmap;
+    rp.cn_items = r.mp * Q; rp.vn_items = r.np * Q;
     rp.src = in.src;
     rp.y_hard = in.y_hard;
     rp.param = in.param;
@@ -560,91 +569,96 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     // Ring of received rows landed by the bulk-copy engine: needs 16-byte aligned rows; as deep as shared memory allows.
     const size_t row_bytes = (size_t)t.n * rp.in_es;
     const size_t stride = align_up(row_bytes, 16);
-    const size_t sm_bytes = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
-    const size_t budget = (Q == 2) ? sm_bytes : (h->smem_per_sm / 2 > 2048 ? h->smem_per_sm / 2 - 1536 : 0);    // Q = 1: two CTAs share an SM
+    const size_t budget = resident_budget(h);
     const int vtw = r.regular36 ? 2 : 0;                     // (3,6) variant keeps the variable-edge table in shared memory
-    const size_t state = resident_smem_layout(Q, t.n, t.m, r.planes, vtw, 0, 0).total;
+    const size_t state = resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, 0, 0).total;
     int ring = 0;
     if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(in.src) & 15u) == 0 && budget > state)
         ring = (int)std::min<size_t>(kResRingMax, (budget - state) / stride);
     rp.ring = ring;
     rp.stage_stride = (int)stride;
     ResLaunch lc;
-    lc.threads = (Q == 2) ? r.threads2 : r.threads;
-    lc.smem = resident_smem_layout(Q, t.n, t.m, r.planes, vtw, ring, (int)stride).total;
+    lc.threads = r.threads;
+    lc.smem = resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, ring, (int)stride).total;
     const int max_grid = (B + 4 * Q - 1) / (4 * Q);
 
     CUDA_TRY(h, cudaMemsetAsync(rp.counter, 0, sizeof(int), s));
     ProfEvent *pe = prof_begin(h, 0, s);
     int rc;
-#define RES_LAUNCH(QQ)                                                                                                   \
-    do {                                                                                                                \
-        if (r.regular36)                                                                                                \
-            rc = (algo == LDPC_MSA) ? launch_resident_t<QQ, ALGO_MSA, 6, true, 3, true, true, true>(h, rp, lc, max_grid, s)     \
-                                    : launch_resident_t<QQ, ALGO_SPA_PHI, 6, true, 3, true, true, true>(h, rp, lc, max_grid, s); \
-        else                                                                                                            \
-            rc = (algo == LDPC_MSA) ? launch_resident_t<QQ, ALGO_MSA, 8, false, 8, false, false, false>(h, rp, lc, max_grid, s) \
-                                    : launch_resident_t<QQ, ALGO_SPA_PHI, 8, false, 8, false, false, false>(h, rp, lc, max_grid, s); \
-    } while (0)
-    if (Q == 2) RES_LAUNCH(2); else RES_LAUNCH(1);
-#undef RES_LAUNCH
+    if (r.regular36)
+        rc = (algo == LDPC_MSA) ? launch_resident_t<Q, ALGO_MSA, 6, true, 3, true, true, true>(h, rp, lc, max_grid, s)
+                                : launch_resident_t<Q, ALGO_SPA_PHI, 6, true, 3, true, true, true>(h, rp, lc, max_grid, s);
+    else
+        rc = (algo == LDPC_MSA) ? launch_resident_t<Q, ALGO_MSA, 8, false, 8, false, false, false>(h, rp, lc, max_grid, s)
+                                : launch_resident_t<Q, ALGO_SPA_PHI, 8, false, 8, false, false, false>(h, rp, lc, max_grid, s);
     prof_end(pe, s);
     if (rc) return rc;
     return check_launch(h, "decode_bp_resident");
 }
 
-// Compact uint16 tables + the geometry of the resident kernel; leaves res.ok = false when the code does not fit.
+// Places the graph in shared memory (res_layout.h), builds the position-indexed uint16 tables and the geometry of
+// the resident kernel; leaves res.ok = false when the code does not fit.
 int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, const int32_t *var_ptr, const int32_t *var_edges)
 {
     const Tables &t = h->t;
     ResidentInfo &r = h->res;
+    constexpr int Q = 1;
     if (t.max_dc > 8 || t.max_dv > 8 || t.max_dc < 1) return LDPC_OK;
+    const int G = 8 / Q;
+    const int mp = (t.m + G - 1) / G * G, np = (t.n + G - 1) / G * G;
     r.planes = t.max_dc;
-    r.regular36 = (t.uni_dc == 6 && t.uni_dv == 3);
+    r.regular36 = (t.uni_dc == 6 && t.uni_dv == 3 && mp == t.m && np == t.n);
     const int vtw = r.regular36 ? 2 : 0;
-    // Geometry: threads so that the check items (m * Q) take at most 2 passes and the variable items (n * Q) at most 4.
-    auto geometry = [&](int Q, size_t budget, int *threads) -> bool {
-        if ((long long)r.planes * t.m * Q + 1 > 65535) return false;                 // c2v float4 index must fit 16 bits
-        if (((long long)t.n * Q + 1) * 16 > 65535) return false;                     // marg byte offset must fit 16 bits
-        if (resident_smem_layout(Q, t.n, t.m, r.planes, vtw, 0, 0).total > budget) return false;
-        const int citems = t.m * Q, vitems = t.n * Q, maxT = res_max_threads(Q);
-        int T = std::max((citems + kResCnPasses - 1) / kResCnPasses, (vitems + kResVnPasses - 1) / kResVnPasses);
-        if (citems <= maxT && vitems <= 2 * maxT) T = std::max(citems, (vitems + 1) / 2);
-        T = std::max(64, (T + 31) / 32 * 32);
-        if (T > maxT) return false;
-        *threads = T;
-        return true;
-    };
-    const size_t sm_bytes = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
-    const size_t half_bytes = h->smem_per_sm / 2 > 2048 ? h->smem_per_sm / 2 - 1536 : 0;
-    r.ok2 = geometry(2, sm_bytes, &r.threads2);
-    const bool ok1 = geometry(1, half_bytes, &r.threads);
-    if (!ok1 && !r.ok2) return LDPC_OK;
-    r.Q = ok1 ? 1 : 2;
-    if (!ok1) r.threads = r.threads2;
-    std::vector<uint16_t> cvar((size_t)t.m * 8, (uint16_t)t.n), vrow((size_t)t.n * 8, 0);
-    std::vector<uint8_t> cdeg((size_t)t.m), vdeg((size_t)t.n);
-    std::vector<int> row_of_edge((size_t)t.E);
-    for (int c = 0; c < t.m; ++c) {
-        cdeg[c] = (uint8_t)(chk_ptr[c + 1] - chk_ptr[c]);
-        for (int e = chk_ptr[c], k = 0; e < chk_ptr[c + 1]; ++e, ++k) {
-            cvar[(size_t)c * 8 + k] = (uint16_t)edge_var[e];
-            row_of_edge[e] = k * t.m + c;
-        }
-    }
+    if ((long long)r.planes * mp * Q + 1 > 65535) return LDPC_OK;                    // c2v float4 index must fit 16 bits
+    if (((long long)np * Q + 1) * 16 > 65535) return LDPC_OK;                        // marg byte offset must fit 16 bits
+    if (resident_smem_layout(Q, np, mp, r.planes, vtw, 0, 0).total > resident_budget(h)) return LDPC_OK;
+    // threads: check items (mp * Q) in at most 2 passes, variable items (np * Q) in at most 4
+    const int citems = mp * Q, vitems = np * Q, maxT = res_max_threads(Q);
+    int T = std::max((citems + kResCnPasses - 1) / kResCnPasses, (vitems + kResVnPasses - 1) / kResVnPasses);
+    if (citems <= maxT && vitems <= 2 * maxT) T = std::max(citems, (vitems + 1) / 2);
+    T = std::max(64, (T + 31) / 32 * 32);
+    if (T > maxT) return LDPC_OK;
+    r.threads = T; r.Q = Q; r.np = np; r.mp = mp;
+
+    ResPlanner planner(t.n, t.m, t.E, chk_ptr, edge_var, var_ptr, var_edges, G);
+    const ResLayout L = planner.plan(12345u, h->plan_effort);
+    const long pl[7] = {L.cn_ideal, L.cn_file, L.cn_plan_natural, L.cn_plan, L.vn_ideal, L.vn_file, L.vn_plan};
+    std::copy(pl, pl + 7, r.plan);
+
+    std::vector<int> edge_chk((size_t)t.E);
+    for (int c = 0; c < t.m; ++c)
+        for (int e = chk_ptr[c]; e < chk_ptr[c + 1]; ++e) edge_chk[e] = c;
+    std::vector<uint8_t> cdeg((size_t)mp, 0), vdeg((size_t)np, 0);
+    std::vector<uint16_t> vposmap((size_t)t.n), vinvmap((size_t)np, 0xffffu);
+    for (int c = 0; c < t.m; ++c) cdeg[L.cpos[c]] = (uint8_t)(chk_ptr[c + 1] - chk_ptr[c]);
     for (int v = 0; v < t.n; ++v) {
-        vdeg[v] = (uint8_t)(var_ptr[v + 1] - var_ptr[v]);
-        for (int p0 = var_ptr[v], k = 0; p0 < var_ptr[v + 1]; ++p0, ++k)
-            vrow[(size_t)v * 8 + k] = (uint16_t)row_of_edge[var_edges[p0]];
+        vdeg[L.vpos[v]] = (uint8_t)(var_ptr[v + 1] - var_ptr[v]);
+        vposmap[v] = (uint16_t)L.vpos[v];
+        vinvmap[L.vpos[v]] = (uint16_t)v;
     }
     auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, bytes);
         if (e != cudaSuccess) return e;
         return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
     };
-    cudaError_t e;
-    if ((e = up((void **)&r.cvar, cvar.data(), cvar.size() * 2)) != cudaSuccess || (e = up((void **)&r.vrow, vrow.data(), vrow.size() * 2)) != cudaSuccess ||
-        (e = up((void **)&r.cdeg, cdeg.data(), cdeg.size())) != cudaSuccess || (e = up((void **)&r.vdeg, vdeg.data(), vdeg.size())) != cudaSuccess)
+    cudaError_t e = cudaSuccess;
+    for (int tb = 0; tb < 2 && e == cudaSuccess; ++tb) {
+        const std::vector<uint8_t> &plane = tb == 0 ? L.eord : L.enat;
+        std::vector<uint16_t> cvar((size_t)mp * 8, (uint16_t)np), vrow((size_t)np * 8, 0);
+        for (int ed = 0; ed < t.E; ++ed)
+            cvar[(size_t)L.cpos[edge_chk[ed]] * 8 + plane[ed]] = (uint16_t)L.vpos[edge_var[ed]];
+        for (int v = 0; v < t.n; ++v)
+            for (int p0 = var_ptr[v], k = 0; p0 < var_ptr[v + 1]; ++p0, ++k) {
+                const int ed = var_edges[p0];
+                vrow[(size_t)L.vpos[v] * 8 + k] = (uint16_t)(plane[ed] * mp + L.cpos[edge_chk[ed]]);
+            }
+        if ((e = up((void **)&r.cvar[tb], cvar.data(), cvar.size() * 2)) != cudaSuccess) break;
+        e = up((void **)&r.vrow[tb], vrow.data(), vrow.size() * 2);
+    }
+    if (e != cudaSuccess || (e = up((void **)&r.cdeg, cdeg.data(), cdeg.size())) != cudaSuccess ||
+        (e = up((void **)&r.vdeg, vdeg.data(), vdeg.size())) != cudaSuccess ||
+        (e = up((void **)&r.vposmap, vposmap.data(), vposmap.size() * 2)) != cudaSuccess ||
+        (e = up((void **)&r.vinvmap, vinvmap.data(), vinvmap.size() * 2)) != cudaSuccess)
         return fail(nullptr, LDPC_ECUDA, std::string("resident table upload: ") + cudaGetErrorString(e));
     r.ok = true;
     return LDPC_OK;
@@ -749,6 +763,14 @@ unsigned long long ldpc_launch_count(const ldpc_t *h) { return h ? h->launches :
 
 int ldpc_resident_frames(const ldpc_t *h) { return (h && h->res.ok) ? 4 * h->res.Q : 0; }
 
+int ldpc_resident_plan(const ldpc_t *h, long *out)
+{
+    if (!h || !out) return LDPC_EINVAL;
+    if (!h->res.ok) return LDPC_EUNSUPPORTED;
+    std::copy(h->res.plan, h->res.plan + 7, out);
+    return LDPC_OK;
+}
+
 int ldpc_create(ldpc_t **out, int device, int n, int m, int E,
                 const int32_t *chk_ptr, const int32_t *edge_var,
                 const int32_t *var_ptr, const int32_t *var_edges)
@@ -800,6 +822,7 @@ int ldpc_create(ldpc_t **out, int device, int n, int m, int E,
         h->smem_optin = prop.sharedMemPerBlockOptin;
         h->smem_per_sm = prop.sharedMemPerMultiprocessor;
     }
+    if (const char *pe = getenv("LDPC_PLAN_EFFORT")) h->plan_effort = std::max(0.0, atof(pe));
     Tables &t = h->t;
     t.n = n; t.m = m; t.E = E;
     t.max_dc = max_dc; t.max_dv = max_dv;
@@ -875,8 +898,12 @@ void ldpc_destroy(ldpc_t *h)
         if (h->stage->h_flag) cudaFreeHost(h->stage->h_flag);
         delete h->stage;
     }
-    if (h->res.cvar) cudaFree(h->res.cvar);
-    if (h->res.vrow) cudaFree(h->res.vrow);
+    for (int tb = 0; tb < 2; ++tb) {
+        if (h->res.cvar[tb]) cudaFree(h->res.cvar[tb]);
+        if (h->res.vrow[tb]) cudaFree(h->res.vrow[tb]);
+    }
+    if (h->res.vposmap) cudaFree(h->res.vposmap);
+    if (h->res.vinvmap) cudaFree(h->res.vinvmap);
     if (h->res.cdeg) cudaFree(h->res.cdeg);
     if (h->res.vdeg) cudaFree(h->res.vdeg);
     if (h->t.chk_ptr) cudaFree(h->t.chk_ptr);

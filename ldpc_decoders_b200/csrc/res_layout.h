@@ -1,0 +1,260 @@
+// res_layout.h — bank-conflict-aware placement of a Tanner graph in shared memory (host code, no CUDA).
+//
+// The on-chip decoder (resident_bp.cuh) gathers 16-byte cells at graph-determined addresses: a check thread reads
+// the marginals of its variables, a variable thread reads the messages of its checks.  A 128-bit shared-memory
+// access is served one quarter-warp (8 lanes) per wavefront, conflict-free iff the 8 cells lie in 8 different
+// 16-byte bank groups, i.e. iff their cell indices differ mod G = 8 (with Q quads per cell row G = 8 / Q row
+// colours).  With the graph in file order those indices are random and a gather costs ~2.4 wavefronts.
+//
+// Everything the kernel touches is position-indexed, so the placement is free:
+//   cpos[c]   position of check c    -> colour of all its message rows = cpos mod G; thread item order of the CN phase
+//   vpos[v]   position of variable v -> colour of its marginal cell    = vpos mod G; thread item order of the VN phase
+//   eord[e]   plane (step) of edge e inside its check (min-sum only: the check rule is symmetric in its edges;
+//             the variable-node sum keeps the reference's ascending-edge order, bpa.py:35)
+// A group = G consecutive positions = the items of one quarter-warp.  Wanted:
+//   VN: for every variable group and every k, the k-th checks of its variables have G different colours;
+//   CN: for every check group and every step, the variables read in that step have G different colours.
+// Simulated annealing over position swaps minimises the predicted extra wavefronts of both phases, then each
+// check group orders its edges by local search.  Any placement is CORRECT (results do not depend on it: the
+// arithmetic per check / variable is unchanged); a better one is only faster.
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace ldpc {
+
+struct ResLayout {
+    int G = 8;                          // colours = cells per conflict-free quarter-warp access
+    int mp = 0, np = 0;                 // positions (multiples of G; holes are degree-0 items)
+    std::vector<int> cpos, vpos;        // [m], [n]
+    std::vector<int> cinv, vinv;        // [mp], [np]: item at a position, -1 = hole
+    std::vector<uint8_t> eord;          // [E] plane of every edge within its check (optimised, min-sum)
+    std::vector<uint8_t> enat;          // [E] natural plane (position in np.where order) for order-sensitive rules
+    // predicted shared-memory wavefronts per iteration of the two gather phases (ideal = one per quarter-warp access)
+    long cn_ideal = 0, cn_file = 0, cn_plan = 0, cn_plan_natural = 0;
+    long vn_ideal = 0, vn_file = 0, vn_plan = 0;
+};
+
+class ResPlanner {
+  public:
+    ResPlanner(int n, int m, int E, const int32_t *chk_ptr, const int32_t *edge_var, const int32_t *var_ptr,
+               const int32_t *var_edges, int G)
+        : n_(n), m_(m), E_(E), G_(G), chk_ptr_(chk_ptr), edge_var_(edge_var), var_ptr_(var_ptr), var_edges_(var_edges)
+    {
+        edge_chk_.resize(E);
+        for (int c = 0; c < m; ++c)
+            for (int e = chk_ptr[c]; e < chk_ptr[c + 1]; ++e) edge_chk_[e] = c;
+        mp_ = (m + G - 1) / G * G;
+        np_ = (n + G - 1) / G * G;
+    }
+
+    ResLayout plan(unsigned seed = 12345u, double effort = 1.0)
+    {
+        ResLayout L;
+        L.G = G_; L.mp = mp_; L.np = np_;
+        cpos_.resize(m_); vpos_.resize(n_);
+        cinv_.assign(mp_, -1); vinv_.assign(np_, -1);
+        for (int c = 0; c < m_; ++c) { cpos_[c] = c; cinv_[c] = c; }
+        for (int v = 0; v < n_; ++v) { vpos_[v] = v; vinv_[v] = v; }
+        L.enat.resize(E_);
+        for (int c = 0; c < m_; ++c)
+            for (int e = chk_ptr_[c]; e < chk_ptr_[c + 1]; ++e) L.enat[e] = (uint8_t)(e - chk_ptr_[c]);
+        eord_ = L.enat;
+        L.cn_ideal = cn_ideal();
+        L.vn_ideal = vn_ideal();
+        L.cn_file = L.cn_ideal + cn_extra_exact_all();
+        L.vn_file = L.vn_ideal + vn_cost_all();
+
+        anneal(seed, effort);
+        L.cn_plan_natural = L.cn_ideal + cn_extra_exact_all();
+        order_edges(seed ^ 0x9e3779b9u, effort);
+        L.cn_plan = L.cn_ideal + cn_extra_exact_all();
+        L.vn_plan = L.vn_ideal + vn_cost_all();
+        L.cpos = cpos_; L.vpos = vpos_; L.cinv = cinv_; L.vinv = vinv_; L.eord = eord_;
+        return L;
+    }
+
+  private:
+    int n_, m_, E_, G_, mp_, np_;
+    const int32_t *chk_ptr_, *edge_var_, *var_ptr_, *var_edges_;
+    std::vector<int> edge_chk_, cpos_, vpos_, cinv_, vinv_;
+    std::vector<uint8_t> eord_;
+    std::vector<int> vgc_, cgc_;        // cached group costs
+    uint64_t rng_ = 88172645463325252ull;
+
+    uint32_t rnd()
+    {
+        rng_ ^= rng_ << 13; rng_ ^= rng_ >> 7; rng_ ^= rng_ << 17;
+        return (uint32_t)(rng_ >> 32);
+    }
+    double rnd01() { return (rnd() >> 8) * (1.0 / 16777216.0); }
+
+    long cn_ideal() const
+    {
+        long w = 0;
+        for (int g = 0; g < mp_ / G_; ++g) {
+            int d = 0;
+            for (int i = 0; i < G_; ++i) { const int c = cinv_[g * G_ + i]; if (c >= 0) d = std::max(d, chk_ptr_[c + 1] - chk_ptr_[c]); }
+            w += d;
+        }
+        return w;
+    }
+    long vn_ideal() const
+    {
+        long w = 0;
+        for (int g = 0; g < np_ / G_; ++g) {
+            int d = 0;
+            for (int i = 0; i < G_; ++i) { const int v = vinv_[g * G_ + i]; if (v >= 0) d = std::max(d, var_ptr_[v + 1] - var_ptr_[v]); }
+            w += d;
+        }
+        return w;
+    }
+
+    // Extra wavefronts of one variable group: for every k, (largest colour multiplicity among the k-th checks) - 1.
+    int vn_group_cost(int g) const
+    {
+        int cost = 0;
+        for (int k = 0;; ++k) {
+            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+            bool any = false;
+            for (int i = 0; i < G_; ++i) {
+                const int v = vinv_[g * G_ + i];
+                if (v < 0 || var_ptr_[v + 1] - var_ptr_[v] <= k) continue;
+                any = true;
+                const int col = cpos_[edge_chk_[var_edges_[var_ptr_[v] + k]]] % G_;
+                mx = std::max(mx, ++cnt[col]);
+            }
+            if (!any) break;
+            cost += mx - 1;
+        }
+        return cost;
+    }
+    // Proxy for one check group while positions move: colour counts beyond the number of steps cannot be hidden by any
+    // edge order (each wavefront serves one cell per colour).
+    int cn_group_cost(int g) const
+    {
+        int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, steps = 0;
+        for (int i = 0; i < G_; ++i) {
+            const int c = cinv_[g * G_ + i];
+            if (c < 0) continue;
+            steps = std::max(steps, chk_ptr_[c + 1] - chk_ptr_[c]);
+            for (int e = chk_ptr_[c]; e < chk_ptr_[c + 1]; ++e) ++cnt[vpos_[edge_var_[e]] % G_];
+        }
+        int cost = 0;
+        for (int a = 0; a < G_; ++a) cost += std::max(0, cnt[a] - steps);
+        return cost;
+    }
+    // Exact extra wavefronts of one check group for the current edge planes.
+    int cn_group_exact(int g) const
+    {
+        int cost = 0;
+        for (int k = 0; k < 8; ++k) {
+            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+            bool any = false;
+            for (int i = 0; i < G_; ++i) {
+                const int c = cinv_[g * G_ + i];
+                if (c < 0) continue;
+                for (int e = chk_ptr_[c]; e < chk_ptr_[c + 1]; ++e)
+                    if (eord_[e] == k) { any = true; mx = std::max(mx, ++cnt[vpos_[edge_var_[e]] % G_]); }
+            }
+            if (any) cost += mx - 1;
+        }
+        return cost;
+    }
+    long vn_cost_all() const { long s = 0; for (int g = 0; g < np_ / G_; ++g) s += vn_group_cost(g); return s; }
+    long cn_extra_exact_all() const { long s = 0; for (int g = 0; g < mp_ / G_; ++g) s += cn_group_exact(g); return s; }
+
+    void touched_by_check(int c, std::vector<int> &vg) const
+    {
+        if (c < 0) return;
+        for (int e = chk_ptr_[c]; e < chk_ptr_[c + 1]; ++e) vg.push_back(vpos_[edge_var_[e]] / G_);
+    }
+    void touched_by_var(int v, std::vector<int> &cg) const
+    {
+        if (v < 0) return;
+        for (int p = var_ptr_[v]; p < var_ptr_[v + 1]; ++p) cg.push_back(cpos_[edge_chk_[var_edges_[p]]] / G_);
+    }
+    static void uniq(std::vector<int> &a) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+
+    void anneal(unsigned seed, double effort)
+    {
+        rng_ ^= (uint64_t)seed * 0x9e3779b97f4a7c15ull;
+        vgc_.resize(np_ / G_); cgc_.resize(mp_ / G_);
+        for (int g = 0; g < np_ / G_; ++g) vgc_[g] = vn_group_cost(g);
+        for (int g = 0; g < mp_ / G_; ++g) cgc_[g] = cn_group_cost(g);
+        const long moves = (long)(effort * 60.0 * (mp_ + np_)) * 10;
+        const double t0 = 0.8, t1 = 0.05;
+        std::vector<int> vg, cg, oldv, oldc;
+        for (long it = 0; it < moves; ++it) {
+            const double T = t0 * std::pow(t1 / t0, (double)it / (double)moves);
+            const bool move_check = (rnd() % (unsigned)(mp_ + np_)) < (unsigned)mp_;
+            vg.clear(); cg.clear();
+            int a, b;
+            if (move_check) {
+                a = (int)(rnd() % (unsigned)mp_); b = (int)(rnd() % (unsigned)mp_);
+                if (a == b || (cinv_[a] < 0 && cinv_[b] < 0)) continue;
+                cg.push_back(a / G_); cg.push_back(b / G_);
+                touched_by_check(cinv_[a], vg); touched_by_check(cinv_[b], vg);
+            } else {
+                a = (int)(rnd() % (unsigned)np_); b = (int)(rnd() % (unsigned)np_);
+                if (a == b || (vinv_[a] < 0 && vinv_[b] < 0)) continue;
+                vg.push_back(a / G_); vg.push_back(b / G_);
+                touched_by_var(vinv_[a], cg); touched_by_var(vinv_[b], cg);
+            }
+            uniq(vg); uniq(cg);
+            int before = 0;
+            for (int g : vg) before += vgc_[g];
+            for (int g : cg) before += cgc_[g];
+            swap_pos(move_check, a, b);
+            oldv.clear(); oldc.clear();
+            int after = 0;
+            for (int g : vg) { oldv.push_back(vgc_[g]); vgc_[g] = vn_group_cost(g); after += vgc_[g]; }
+            for (int g : cg) { oldc.push_back(cgc_[g]); cgc_[g] = cn_group_cost(g); after += cgc_[g]; }
+            const int d = after - before;
+            if (d > 0 && rnd01() >= std::exp(-(double)d / T)) {                         // reject: undo
+                swap_pos(move_check, a, b);
+                for (size_t i = 0; i < vg.size(); ++i) vgc_[vg[i]] = oldv[i];
+                for (size_t i = 0; i < cg.size(); ++i) cgc_[cg[i]] = oldc[i];
+            }
+        }
+    }
+    void swap_pos(bool check, int a, int b)
+    {
+        if (check) {
+            std::swap(cinv_[a], cinv_[b]);
+            if (cinv_[a] >= 0) cpos_[cinv_[a]] = a;
+            if (cinv_[b] >= 0) cpos_[cinv_[b]] = b;
+        } else {
+            std::swap(vinv_[a], vinv_[b]);
+            if (vinv_[a] >= 0) vpos_[vinv_[a]] = a;
+            if (vinv_[b] >= 0) vpos_[vinv_[b]] = b;
+        }
+    }
+
+    // Per check group: permute the planes of each check's edges to make every step's colours distinct.
+    void order_edges(unsigned seed, double effort)
+    {
+        rng_ ^= (uint64_t)seed << 17;
+        for (int g = 0; g < mp_ / G_; ++g) {
+            int cost = cn_group_exact(g);
+            const int tries = (int)(effort * 4000);
+            for (int t = 0; t < tries && cost > 0; ++t) {
+                const int c = cinv_[g * G_ + (int)(rnd() % (unsigned)G_)];
+                if (c < 0) continue;
+                const int dc = chk_ptr_[c + 1] - chk_ptr_[c];
+                if (dc < 2) continue;
+                const int e1 = chk_ptr_[c] + (int)(rnd() % (unsigned)dc), e2 = chk_ptr_[c] + (int)(rnd() % (unsigned)dc);
+                if (e1 == e2) continue;
+                std::swap(eord_[e1], eord_[e2]);
+                const int nc = cn_group_exact(g);
+                if (nc <= cost) cost = nc;
+                else std::swap(eord_[e1], eord_[e2]);
+            }
+        }
+    }
+};
+
+}  // namespace ldpc

@@ -45,11 +45,14 @@ constexpr int kResVnPasses = 4;              // variable items per thread (n * Q
 constexpr int kResRingMax = 8;               // staged received rows
 
 struct ResParams {
-    int n, m;
+    int n, m;                          // POSITIONS of variables / checks (res_layout.h; >= the code's n, m, multiples of 8)
+    int nref;                          // the code's n: row length of src / x_hat
     int planes;                        // c2v planes = max check degree
-    const uint16_t *cvar;              // [m][8]  variable of the k-th edge of a check (padding: n)
-    const uint16_t *vrow;              // [n][8]  c2v row (k * m + c) of the variable's edges, ascending edge order
-    const uint8_t *cdeg, *vdeg;
+    const uint16_t *cvar;              // [m][8]  position of the variable read in step k of the check at a position (padding: n)
+    const uint16_t *vrow;              // [n][8]  c2v row (plane * m + check position) of the variable's edges, ascending edge order
+    const uint8_t *cdeg, *vdeg;        // [m], [n] degrees by position (0 = hole)
+    const uint16_t *vposmap;           // [nref] position of variable v
+    const uint16_t *vinvmap;           // [n]    variable at a position (0xffff = hole)
     int cn_items, vn_items;            // m * Q, n * Q
     const void *src;                   // [B][n] received block (or priors)
     int in_mode;                       // IN_COPY / IN_BSC / IN_BIAWGN
@@ -154,7 +157,8 @@ __global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const R
     const int q = tid & (Q - 1);                                     // T is even: every item of a thread is in quad q
     const bool async = p.ring > 0;
     const bool have_hard = (p.in_mode == IN_BSC) || (p.in_mode == IN_COPY && p.y_hard != nullptr);
-    const size_t row_bytes = (size_t)n * p.in_es;
+    const int nref = p.nref;
+    const size_t row_bytes = (size_t)nref * p.in_es;
 
     // ---- per-thread graph indices -> registers (once per CTA)
     uint32_t cidx[kResCnPasses][CH];          // byte offsets into marg of the check's variables, two per word
@@ -245,11 +249,14 @@ __global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const R
         while (mq != 0u) {
             const int j = __ffs(mq) - 1;
             mq &= mq - 1u;
-            uint8_t *dst = p.x_hat + (size_t)s_frame[4 * q + j] * n;
+            uint8_t *dst = p.x_hat + (size_t)s_frame[4 * q + j] * nref;
 #pragma unroll
             for (int ps = 0; ps < kResVnPasses; ++ps) {
                 const int item = tid + ps * T;
-                if (item < p.vn_items) dst[item >> QSH] = (uint8_t)((hbits >> (4 * ps + j)) & 1u);
+                if (item < p.vn_items) {
+                    const uint32_t v = __ldg(p.vinvmap + (item >> QSH));
+                    if (v != 0xffffu) dst[v] = (uint8_t)((hbits >> (4 * ps + j)) & 1u);
+                }
             }
         }
         if (tid < F && ((mask >> tid) & 1u)) {
@@ -309,17 +316,18 @@ __global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const R
                 } else {
                     row = (const char *)p.src + (size_t)g * row_bytes;
                 }
-                const uint8_t *hrow = (p.in_mode == IN_COPY && p.y_hard != nullptr) ? p.y_hard + (size_t)g * n : nullptr;
+                const uint8_t *hrow = (p.in_mode == IN_COPY && p.y_hard != nullptr) ? p.y_hard + (size_t)g * nref : nullptr;
                 float *mcol = reinterpret_cast<float *>(marg) + (s >> 2) * 4 + (s & 3);
                 float *pcol = reinterpret_cast<float *>(prior) + (s >> 2) * 4 + (s & 3);
-                for (int v = tid; v < n; v += T) {
+                for (int v = tid; v < nref; v += T) {
                     uint32_t hbit;
                     const float val = res_llr(row, v, p.in_mode, p.in_es, p.param, p.inv_param, &hbit);
-                    mcol[(size_t)v * (Q * 4)] = val;
-                    pcol[(size_t)v * (Q * 4)] = val;
+                    const uint32_t pos = __ldg(p.vposmap + v);
+                    mcol[(size_t)pos * (Q * 4)] = val;
+                    pcol[(size_t)pos * (Q * 4)] = val;
                     if (have_hard) {
                         if (hrow != nullptr) hbit = (uint32_t)(hrow[v] != 0);
-                        hb[v] = (uint8_t)((hb[v] & ~(1u << s)) | (hbit << s));       // the same thread owns hb[v] for every slot
+                        hb[pos] = (uint8_t)((hb[pos] & ~(1u << s)) | (hbit << s));   // the same thread owns hb[pos] for every slot
                     }
                 }
             }
@@ -377,8 +385,8 @@ __global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const R
                 for (int s = 0; s < F; ++s) {
                     if (!((z >> s) & 1u)) continue;
                     const int g = s_frame[s];
-                    uint8_t *dst = p.x_hat + (size_t)g * n;
-                    for (int v = tid; v < n; v += T) dst[v] = (uint8_t)((hb[v] >> s) & 1u);
+                    uint8_t *dst = p.x_hat + (size_t)g * nref;
+                    for (int v = tid; v < nref; v += T) dst[v] = (uint8_t)((hb[__ldg(p.vposmap + v)] >> s) & 1u);
                     if (tid == 0) {
                         p.iters[g] = 0;
                         if (p.reason != nullptr) p.reason[g] = (uint8_t)LDPC_REASON_DECODED;

@@ -63,6 +63,14 @@ class Engine:
         """Frames per CTA of the on-chip path for this code; 0 = the code does not fit in shared memory."""
         return int(self.lib.ldpc_resident_frames(self.handle))
 
+    def resident_plan(self):
+        """Predicted shared-memory wavefronts per iteration of the on-chip path (ldpc_resident_plan), or None."""
+        out = (ctypes.c_long * 7)()
+        if self.lib.ldpc_resident_plan(self.handle, out) != 0:
+            return None
+        keys = ("cn_ideal", "cn_file", "cn_plan_natural", "cn_plan", "vn_ideal", "vn_file", "vn_plan")
+        return dict(zip(keys, [int(x) for x in out]))
+
     def profile(self, on):
         """Record CUDA events around every CN / VN sweep launch (see ldpc_profile_enable)."""
         _lib.check(self.handle, self.lib.ldpc_profile_enable(self.handle, 1 if on else 0))
