@@ -71,7 +71,7 @@ struct ResParams {
 
 // Shared-memory carve-up, shared by the kernel and the host-side size computation.
 struct ResSmem {
-    size_t c2v, marg, prior, vtab, stage, hb, bars, total;
+    size_t c2v, marg, prior, vtab, stage, hb, imap, bars, total;
 };
 // vtab_words: 32-bit words per variable item of the shared-memory edge table (0: the table lives in registers).
 __host__ __device__ inline ResSmem resident_smem_layout(int Q, int n, int m, int planes, int vtab_words, int ring, int stage_stride)
@@ -85,6 +85,7 @@ __host__ __device__ inline ResSmem resident_smem_layout(int Q, int n, int m, int
     L.stage = o; o += (size_t)ring * stage_stride;
     L.bars = o;  o += (size_t)kResRingMax * 8;
     L.hb = o;    o += ((size_t)n + 15) / 16 * 16;
+    L.imap = o;  o += ((size_t)n * 2 + 15) / 16 * 16;                 // variable at a position (output)
     L.total = o + 16;
     return L;
 }
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const R
     float4 *prior = reinterpret_cast<float4 *>(smem + L.prior);
     unsigned char *stage = smem + L.stage;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+    uint16_t *imap = reinterpret_cast<uint16_t *>(smem + L.imap);
     uint8_t *hb = smem + L.hb;                                       // hard input bits of the slots being loaded
     const uint32_t zero_cell = (uint32_t)p.planes * m * Q;           // float4 index into c2v
     const uint32_t inf_off = (uint32_t)n * Q * 16;                   // byte offset into marg
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const R
             for (int k = 0; k < DCP; ++k) old[ps][k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
+    for (int i = tid; i < n; i += T) imap[i] = p.vinvmap[i];
     // ---- constants cells, slot state, ring
     if (tid == 0) {
         c2v[zero_cell] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const R
             for (int ps = 0; ps < kResVnPasses; ++ps) {
                 const int item = tid + ps * T;
                 if (item < p.vn_items) {
-                    const uint32_t v = __ldg(p.vinvmap + (item >> QSH));
+                    const uint32_t v = imap[item >> QSH];
                     if (v != 0xffffu) dst[v] = (uint8_t)((hbits >> (4 * ps + j)) & 1u);
                 }
             }
