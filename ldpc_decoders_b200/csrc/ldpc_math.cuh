@@ -300,6 +300,35 @@ LDPC_HD T vn_update(T prior, const T (&c)[DVMAX], int dv, T (&out)[DVMAX])
 }
 
 // ---------------------------------------------------------------------------------------------
+// BIAWGN prior in float32, rounded exactly like the reference's float64 expression cast to float32:
+//   priors = (-2 y) / noise_var  (biawgn.py:28), then .astype(float32).
+// The float64 product with the reciprocal is within 2 ulp of the quotient, so it rounds to the same float32 unless it
+// lies within 4 ulp of a float32 rounding boundary (29 mantissa bits below float32 precision == 0x10000000 +- 4,
+// probability 2^-26) or outside the normal float32 range — only then is the division evaluated.
+// ---------------------------------------------------------------------------------------------
+LDPC_HD uint32_t f64_lo_bits(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(d);
+#else
+    union { double d; uint64_t u; } c; c.d = d; return (uint32_t)c.u;
+#endif
+}
+LDPC_HD bool llr_biawgn_fast_ok(double pr)
+{
+    const uint32_t lo = f64_lo_bits(pr) & 0x1fffffffu;
+    const double ap = fabs(pr);
+    return (lo - 0x0ffffffcu) > 8u && ap >= 2e-38 && ap < 3e38;
+}
+LDPC_HD float llr_biawgn_f32(double y, double noise_var, double inv_noise_var)
+{
+    const double t = -2.0 * y;                                           // exact
+    const double pr = t * inv_noise_var;
+    if (llr_biawgn_fast_ok(pr)) return (float)pr;
+    return (float)(t / noise_var);
+}
+
+// ---------------------------------------------------------------------------------------------
 // BEC, 32 frames per word.  A message in {-1,0,+1} is two bit planes: nz (|msg|) and pos (msg > 0),
 // pos is a subset of nz.  Literal restatement of bec.py:100-119 in bit-sliced integer arithmetic.
 // ---------------------------------------------------------------------------------------------

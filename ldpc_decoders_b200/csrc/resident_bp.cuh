@@ -91,9 +91,7 @@ __host__ __device__ inline ResSmem resident_smem_layout(int Q, int n, int m, int
 }
 
 // Channel LLR of one received value, rounded exactly like the reference's float64 expression cast to float32
-// (io_kernels.cuh llr_map).  BIAWGN: (-2 y) / noise_var needs a float64 division per value; the product with the
-// reciprocal is within 2 ulp (double) of the quotient, so it rounds to the same float unless it lies within 4 ulp
-// of a float32 rounding boundary (probability 2^-26) or outside the normal float32 range — only then divide.
+// (io_kernels.cuh llr_map; BIAWGN without a float64 division in the common case, ldpc_math.cuh llr_biawgn_f32).
 __device__ __noinline__ float res_llr_biawgn_exact(double t, double param) { return (float)(t / param); }
 
 __device__ __forceinline__ float res_llr(const void *row, int v, int in_mode, int in_es, double param, double inv_param, uint32_t *hard)
@@ -109,11 +107,8 @@ __device__ __forceinline__ float res_llr(const void *row, int v, int in_mode, in
         const double y = (in_es == 8) ? ((const double *)row)[v] : (double)((const float *)row)[v];
         const double t = -2.0 * y;                                       // exact
         const double pr = t * inv_param;
-        const uint32_t lo = (uint32_t)__double2loint(pr) & 0x1fffffffu;  // mantissa bits below float32 precision
-        const double ap = fabs(pr);
-        const bool safe = (lo - 0x0ffffffcu) > 8u && ap >= 2e-38 && ap < 3e38;
         val = (float)pr;
-        if (!safe) val = res_llr_biawgn_exact(t, param);             // rare: keep the division out of line
+        if (!llr_biawgn_fast_ok(pr)) val = res_llr_biawgn_exact(t, param);   // rare: keep the division out of line
     } else {
         val = (in_es == 8) ? (float)((const double *)row)[v] : ((const float *)row)[v];
     }

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../ldpc_decoders_b200/csrc/ldpc_math.cuh"
+#include "../../ldpc_decoders_b200/csrc/res_layout.h"
 
 using namespace ldpc;
 
@@ -225,4 +226,124 @@ int emu_bec(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The on-chip kernel's FORMULATION of a decode (csrc/resident_bp.cuh), one frame, plain loops:
+//   state = marg[position], prior[position], c2v[plane][check position]; v2c is never stored:
+//   CN: v2c = marg - c2v_old, syndrome from the sign bits of marg, lean min-sum for degree 6 (else the bit-pattern rule),
+//       edges of a check visited in the PLANNED order; VN: marg = prior + ordered sum of c2v (reference edge order);
+//   -0.0 priors folded to +0.0; exit rules per frame as in the kernel's book-keeping.
+// Driven with the placement of res_layout.h, so the permutation tables are exercised on the CPU too.
+// ---------------------------------------------------------------------------------------------------------------
+int emu_resident_msa(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+                     double effort, int B, const float *priors, const uint8_t *y_hard, int limit,
+                     uint8_t *x_hat, int32_t *iters, uint8_t *decoded)
+{
+    ResPlanner planner(n, m, E, cp, ev, vp, ve, 8);
+    const ResLayout L = planner.plan(12345u, effort);
+    std::vector<int> edge_chk((size_t)E);
+    for (int c = 0; c < m; ++c)
+        for (int e = cp[c]; e < cp[c + 1]; ++e) edge_chk[e] = c;
+    // position-indexed tables, exactly what build_resident uploads
+    std::vector<int> cvar((size_t)L.mp * 8, -1), vrow((size_t)L.np * 8, -1), cdeg((size_t)L.mp, 0), vdeg((size_t)L.np, 0);
+    for (int c = 0; c < m; ++c) cdeg[L.cpos[c]] = cp[c + 1] - cp[c];
+    for (int e = 0; e < E; ++e) cvar[(size_t)L.cpos[edge_chk[e]] * 8 + L.eord[e]] = L.vpos[ev[e]];
+    for (int v = 0; v < n; ++v) {
+        vdeg[L.vpos[v]] = vp[v + 1] - vp[v];
+        for (int p0 = vp[v], k = 0; p0 < vp[v + 1]; ++p0, ++k)
+            vrow[(size_t)L.vpos[v] * 8 + k] = L.eord[ve[p0]] * L.mp + L.cpos[edge_chk[ve[p0]]];
+    }
+    std::vector<float> marg((size_t)L.np), prior((size_t)L.np), c2v((size_t)8 * L.mp);
+    std::vector<uint8_t> hb((size_t)L.np);
+    for (int b = 0; b < B; ++b) {
+        std::fill(marg.begin(), marg.end(), 0.f);
+        std::fill(c2v.begin(), c2v.end(), 0.f);
+        for (int v = 0; v < n; ++v) {
+            volatile float val = priors[(size_t)b * n + v] + 0.0f;                 // -0.0 -> +0.0
+            marg[L.vpos[v]] = prior[L.vpos[v]] = val;
+            hb[L.vpos[v]] = y_hard ? y_hard[(size_t)b * n + v] : 0;
+        }
+        bool fresh = true, done = false;
+        int it = 0;
+        if (y_hard) {                                                              // iteration-0 exit on the received bits
+            bool unsat = false;
+            for (int c = 0; c < L.mp && !unsat; ++c) {
+                unsigned s = 0;
+                for (int k = 0; k < cdeg[c]; ++k) s ^= hb[cvar[(size_t)c * 8 + k]];
+                unsat = s & 1u;
+            }
+            if (!unsat) {
+                for (int v = 0; v < n; ++v) x_hat[(size_t)b * n + v] = hb[L.vpos[v]];
+                iters[b] = 0; decoded[b] = 1;
+                continue;
+            }
+        }
+        for (;;) {
+            bool unsat = false;
+            for (int c = 0; c < L.mp; ++c) {
+                const int dc = cdeg[c];
+                if (dc == 0) continue;
+                float a[8], o[8];
+                uint32_t sx = 0u;
+                for (int k = 0; k < 8; ++k) a[k] = INFINITY;
+                for (int k = 0; k < dc; ++k) {
+                    const float mv = marg[cvar[(size_t)c * 8 + k]];
+                    sx ^= f32_bits(mv);
+                    a[k] = num<float>::sub(mv, c2v[(size_t)k * L.mp + c]);
+                }
+                unsat |= (sx >> 31) != 0u;
+                if (dc == 6) {
+                    float a6[6], o6[6];
+                    for (int k = 0; k < 6; ++k) a6[k] = a[k];
+                    cn_msa_lean<6>(a6, o6);
+                    for (int k = 0; k < 6; ++k) o[k] = o6[k];
+                } else {
+                    cn_msa_bits<8>(a, dc, o);
+                }
+                for (int k = 0; k < dc; ++k) c2v[(size_t)k * L.mp + c] = o[k];
+            }
+            if (!fresh && !unsat) { done = true; break; }                          // syndrome of the last hard decisions
+            fresh = false;
+            ++it;
+            for (int p0 = 0; p0 < L.np; ++p0) {
+                float s = 0.0f;
+                for (int k = 0; k < vdeg[p0]; ++k) s = num<float>::add(s, c2v[vrow[(size_t)p0 * 8 + k]]);
+                marg[p0] = num<float>::add(prior[p0], s);
+            }
+            if (it >= limit) break;
+        }
+        for (int v = 0; v < n; ++v) x_hat[(size_t)b * n + v] = (uint8_t)(marg[L.vpos[v]] < 0.0f);
+        iters[b] = it; decoded[b] = done ? 1 : 0;
+    }
+    return 0;
+}
+
+// Placement statistics and tables of res_layout.h (stats[7] as ldpc_resident_plan).
+int emu_plan(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+             int G, double effort, long *stats, int32_t *cpos, int32_t *vpos, uint8_t *eord)
+{
+    ResPlanner planner(n, m, E, cp, ev, vp, ve, G);
+    const ResLayout L = planner.plan(12345u, effort);
+    const long st[9] = {L.cn_ideal, L.cn_file, L.cn_plan_natural, L.cn_plan, L.vn_ideal, L.vn_file, L.vn_plan, L.mp, L.np};
+    for (int i = 0; i < 9; ++i) stats[i] = st[i];
+    for (int c = 0; c < m; ++c) cpos[c] = L.cpos[c];
+    for (int v = 0; v < n; ++v) vpos[v] = L.vpos[v];
+    for (int e = 0; e < E; ++e) eord[e] = L.eord[e];
+    return 0;
+}
+
+// llr_biawgn_f32 (fast exact path) next to the plain division, elementwise.
+int emu_llr_biawgn(size_t count, const double *y, double noise_var, float *fast, float *exact, int64_t *slow_path)
+{
+    const double inv = 1.0 / noise_var;
+    int64_t slow = 0;
+    for (size_t i = 0; i < count; ++i) {
+        fast[i] = llr_biawgn_f32(y[i], noise_var, inv);
+        exact[i] = (float)((-2.0 * y[i]) / noise_var);
+        slow += llr_biawgn_fast_ok((-2.0 * y[i]) * inv) ? 0 : 1;
+    }
+    *slow_path = slow;
+    return 0;
+}
+
 }

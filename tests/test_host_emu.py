@@ -23,8 +23,8 @@ EMU_DIR = os.path.join(HERE, "host_emu")
 def emu():
     so = os.path.join(EMU_DIR, "libhost_emu.so")
     src = os.path.join(EMU_DIR, "emu.cpp")
-    hdr = os.path.join(HERE, "..", "ldpc_decoders_b200", "csrc", "ldpc_math.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(HERE, "..", "ldpc_decoders_b200", "csrc", h) for h in ("ldpc_math.cuh", "res_layout.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src],
                        check=True, cwd=EMU_DIR)
     return ctypes.CDLL(so)
@@ -163,3 +163,82 @@ def test_bec_bitplanes_arbitrary_symbols(emu, nb):
             emu.emu_bec(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(g.var_ptr), ptr(g.var_edges), B, ptr(Y),
                         mi, nb, ptr(x_hat), ptr(iters), ptr(reason))
             assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all()
+
+
+# --------------------------------------------------------------------------------------------- on-chip formulation
+@pytest.mark.parametrize("channel,code,param,cw", [("biawgn", "1200_3_6_rand_ldpc_1", 2.0, 1),
+                                                   ("biawgn", "1200_3_6_rand_ldpc_1", 2.6, 0),
+                                                   ("bsc", "1200_rho_x5_rand_ldpc_10", .045, 0),
+                                                   ("bsc", "1200_3_6_rand_ldpc_1", .05, 1),
+                                                   ("biawgn", "7_4_hamming", 1.0, 1),
+                                                   ("biawgn", "512_3_6_rand_ldpc_1", 2.0, 0)])
+def test_resident_formulation_matches_oracle(emu, channel, code, param, cw):
+    """The on-chip kernel's restructured decode (marginal gathers, v2c = marg - c2v_old never stored, syndrome from the
+    sign bits of marg, lean 3-input-min min-sum, -0.0 priors folded, graph positions and per-check edge order from
+    res_layout.h) gives the oracle's words, iteration counts and exit reasons bit for bit."""
+    g = graph(code)
+    frames = 300
+    x = np.zeros(g.n, np.int64) + cw
+    Y = G.channel_send(channel, param, np.tile(x, (frames, 1)), 2024)
+    if channel == "bsc":
+        yh = np.ascontiguousarray(Y, np.uint8)
+        pri = O.llr_bsc(param, yh).astype(np.float32)
+        yh[0] = cw                                   # a clean word: iteration-0 exit
+        pri[0] = O.llr_bsc(param, yh[:1]).astype(np.float32)[0]
+    else:
+        yh = None
+        pri = O.llr_biawgn(param, Y).astype(np.float32)
+        pri[1, :5] = [0.0, -0.0, 0.0, -0.0, 1.0]     # zero and negative-zero priors
+    ref = O.bp_decode(g, O.MSA, pri, y_hard=yh, max_iter=10, nthreads=4)
+    x_hat = np.zeros((frames, g.n), np.uint8)
+    iters = np.zeros(frames, np.int32)
+    dec = np.zeros(frames, np.uint8)
+    emu.emu_resident_msa(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(g.var_ptr), ptr(g.var_edges),
+                         ctypes.c_double(0.05), frames, ptr(pri), ptr(yh), 10, ptr(x_hat), ptr(iters), ptr(dec))
+    assert (iters == ref["iters"]).all()
+    assert (x_hat == ref["x_hat"]).all()
+    assert ((dec == 1) == (ref["reason"] == 0)).all()
+    if channel == "bsc":
+        assert iters[0] == 0
+
+
+@pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_10", "7_4_hamming", "12_3_4_ldpc"])
+def test_shared_memory_placement(emu, code):
+    """res_layout.h: positions are permutations into a padded range, every check's edge planes are a permutation of
+    0..dc-1, and the predicted gather wavefronts only go down (to near the ideal for the (3,6) code's check phase)."""
+    g = graph(code)
+    stats = (ctypes.c_long * 9)()
+    cpos, vpos, eord = np.zeros(g.m, np.int32), np.zeros(g.n, np.int32), np.zeros(g.E, np.uint8)
+    emu.emu_plan(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(g.var_ptr), ptr(g.var_edges), 8,
+                 ctypes.c_double(0.4), stats, ptr(cpos), ptr(vpos), ptr(eord))
+    cn_ideal, cn_file, cn_nat, cn_plan, vn_ideal, vn_file, vn_plan, mp, npos = list(stats)
+    assert mp % 8 == 0 and npos % 8 == 0 and mp >= g.m and npos >= g.n and mp < g.m + 8 and npos < g.n + 8
+    assert len(set(cpos.tolist())) == g.m and cpos.min() >= 0 and cpos.max() < mp
+    assert len(set(vpos.tolist())) == g.n and vpos.min() >= 0 and vpos.max() < npos
+    for c in range(g.m):
+        e0, e1 = g.chk_ptr[c], g.chk_ptr[c + 1]
+        assert sorted(eord[e0:e1].tolist()) == list(range(e1 - e0))
+    assert cn_ideal <= cn_plan <= cn_file and vn_ideal <= vn_plan <= vn_file and cn_plan <= cn_nat
+    if code == "1200_3_6_rand_ldpc_1":
+        assert cn_file > 2.3 * cn_ideal and vn_file > 2.3 * vn_ideal        # file order: random gathers
+        assert cn_plan < 1.35 * cn_ideal and vn_plan < 2.0 * vn_ideal
+
+
+def test_biawgn_llr_without_division_is_exact(emu):
+    """llr_biawgn_f32 == float32((-2 y) / noise_var) for every input, the division being evaluated for ~2^-26 of them."""
+    rng = np.random.RandomState(5)
+    total_slow = 0
+    for snr in (0.01, 1.0, 2.0, 2.3, 3.0, 6.0):
+        nv = 10 ** (-snr / 10)
+        y = (1 + np.sqrt(nv) * rng.standard_normal(2_000_000)).astype(np.float32).astype(np.float64)
+        y[:8] = [0.0, -0.0, 1e-42, -1e-40, 1e30, -3e38, np.inf, 1.0]
+        y[8:200008] = rng.standard_normal(200000) * 10.0 ** rng.randint(-40, 38, 200000)
+        fast, exact = np.zeros(y.size, np.float32), np.zeros(y.size, np.float32)
+        slow = ctypes.c_int64()
+        emu.emu_llr_biawgn(ctypes.c_size_t(y.size), ptr(y), ctypes.c_double(nv), ptr(fast), ptr(exact), ctypes.byref(slow))
+        with np.errstate(over="ignore"):
+            ref = (-2 * y / nv).astype(np.float32)
+        assert (fast.view(np.uint32) == ref.view(np.uint32)).all()
+        assert (exact.view(np.uint32) == ref.view(np.uint32)).all()
+        total_slow += slow.value
+    assert total_slow < 120000          # the out-of-range test values, plus a handful of boundary cases
