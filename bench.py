@@ -231,6 +231,21 @@ def extra_workloads(torch, lib, eng_mod, Tables, peak):
     big = codes.random_regular(64800, 3, 6, seed=0).tables
     bp_case("synthetic (3,6) n=64800 BIAWGN 1.0 dB MSA f32, max_iter 10 (no convergence)", big, lib.MSA, lib.F32, 1.0, 2048)
     bp_case("synthetic (3,6) n=64800 BIAWGN 2.5 dB MSA f32, max_iter 10", big, lib.MSA, lib.F32, 2.5, 2048)
+    # Monte-Carlo round entirely on the GPU (on-device Philox channel + decode + error count): what sim.py --noise device runs
+    eng = eng_mod.engine_for(tab)
+    frames = 32768
+    xone = torch.ones(tab.n, dtype=torch.uint8, device="cuda")
+    bufs, rs, cnt = {}, {}, [0]
+    def fs():
+        rs["o"] = eng.simulate(lib.CH_BIAWGN, lib.MSA, lib.F32, 10 ** (-SNR_DB / 10), frames, seed=1, frame0=cnt[0] * frames,
+                               x=xone, max_iter=MAX_ITER, bufs=bufs)
+        cnt[0] += 1
+    ms = timed_steps(torch, fs, 5, 2, None)
+    iters = rs["o"]["iters"].cpu().numpy()
+    out.append({"workload": "Monte-Carlo round on the GPU: Philox BIAWGN 2.0 dB noise + MSA f32 decode + bit-error count, LDPC(1200,3,6), cw=1",
+                "value": frames * 5 / (ms / 1e3), "unit": UNIT, "mean_iters": float(iters.mean()),
+                "wer": float((rs["o"]["bit_errs"] > 0).float().mean().item()),
+                "edge_updates_per_s": 2 * tab.E * float(iters.sum()) * 5 / (ms / 1e3)})
     # BEC, config 2
     eng = eng_mod.engine_for(tab)
     frames = 131072

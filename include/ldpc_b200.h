@@ -148,6 +148,18 @@ int ldpc_llr_bsc(ldpc_t *h, int dtype, double llr, const uint8_t *y, void *prior
 int ldpc_llr_biawgn(ldpc_t *h, int y_dtype, int dtype, double noise_var, const void *y, void *priors,
                     size_t count, void *stream);
 
+/* On-device channel simulators (the reference's Channel.send, src/bec.py:15-18, src/bsc.py:15-16,
+ * src/biawgn.py:17-18) with counter-based Philox4x32-10 noise: statistically, not bit-, equivalent to numpy's global
+ * RNG.  The noise of a received value depends only on (seed, frame0 + frame, variable), so a Monte-Carlo run gives
+ * the same frames however it is cut into batches or spread over GPUs.
+ *   channel  LDPC_CH_BSC / LDPC_CH_BEC: param = p, y uint8 [B,n];  LDPC_CH_BIAWGN: param = noise_var, y float32 [B,n]
+ *   x        device [n] uint8 transmitted word, or NULL = the all-zero word */
+int ldpc_channel_generate(ldpc_t *h, int channel, double param, const uint8_t *x,
+                          unsigned long long seed, unsigned long long frame0, int B, void *y, void *stream);
+
+/* bit_errs[b] = #{v : x_hat[b,v] != x[v]} (src/main.py:41; an undecoded BEC symbol counts); x NULL = all-zero word. */
+int ldpc_count_errors(ldpc_t *h, const uint8_t *x_hat, const uint8_t *x, int B, int32_t *bit_errs, void *stream);
+
 /* One isolated sweep on caller-supplied messages in the reference's own layout
  * (teacher-forced parity): device [B,E] row-major, edge order of np.where(H).
  *   which = 0: check-node sweep   c2v = CN(v2c)            (src/bpa.py:71-75 / 86-102)

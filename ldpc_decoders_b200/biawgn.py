@@ -41,6 +41,29 @@ class LLR:
         return (x_hat, iters, reason) if return_reason else (x_hat, iters)
 
 
+    def simulate_batch(self, x, B, seed, frame0=0):
+        """Draw B received frames of the word x on the GPU (global frame indices frame0 ..), decode, count bit errors.
+        Returns numpy (bit_errs [B], iters [B]); nothing but these two vectors crosses PCIe."""
+        return _simulate(self, _lib.CH_BIAWGN, self.noise_var, x, B, seed, frame0)
+
+
+def _simulate(adapter, channel, param, x, B, seed, frame0):
+    import torch
+    dec = adapter.dec
+    eng = dec.engine
+    dt = _lib.F32 if adapter.dtype == np.float32 else _lib.F64
+    key = (np.asarray(x, np.uint8).tobytes(), eng.device)
+    if getattr(adapter, "_xkey", None) != key:
+        adapter._xdev = torch.from_numpy(np.ascontiguousarray(x, np.uint8)).to(eng._dev())
+        adapter._xkey = key
+        adapter._bufs = {}
+    out = eng.simulate(channel, dec._algo, dt, param, B, seed, frame0, x=adapter._xdev, max_iter=dec.max_iter,
+                       iter_cap=dec.iter_cap, bufs=adapter._bufs)
+    errs, iters = out["bit_errs"].cpu().numpy(), out["iters"].cpu().numpy()
+    dec._count(iters)
+    return errs, iters
+
+
 class SPA(LLR):
     id_keys = bpa.SPA.id_keys
 

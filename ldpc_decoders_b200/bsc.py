@@ -18,6 +18,7 @@ class LLR:
     """bsc.LLR (src/bsc.py:19-25): priors = llr * (1 - 2y), llr = log(1-p) - log(p)."""
 
     def __init__(self, p, dec, dtype=None):
+        self.p = p
         self.llr, self.dec = np.log(1 - p) - np.log(p), dec
         self.dtype = np.dtype(np.float64 if dtype is None else dtype)
         self.stats = self.dec.stats
@@ -35,6 +36,12 @@ class LLR:
         self.dec._count(iters)
         x_hat = x_hat.astype(np.int64)
         return (x_hat, iters, reason) if return_reason else (x_hat, iters)
+
+
+    def simulate_batch(self, x, B, seed, frame0=0):
+        """On-device Monte-Carlo round (see biawgn.LLR.simulate_batch)."""
+        from .biawgn import _simulate
+        return _simulate(self, _lib.CH_BSC, self.p, x, B, seed, frame0)
 
 
 class SPA(LLR):

@@ -1,0 +1,125 @@
+// channel_gen.cuh — on-device channel simulators: the reference's Channel.send of
+//   bec.py:15-18   y = clip(x + 10 * (u < p), 0, 2)          -> 2 where erased, else x
+//   bsc.py:15-16   y = (x + (u < p)) % 2
+//   biawgn.py:17-18  y = (2x - 1) + normal(0, sqrt(noise_var))   (float32 here)
+// with counter-based Philox4x32-10 noise instead of numpy's global Mersenne twister: statistically, not bit-,
+// equivalent (parity runs keep uploading numpy draws).  The stream of a received value depends only on
+// (seed, global frame index, variable index), so a Monte-Carlo run gives the same frames however it is cut
+// into batches or spread over GPUs.
+#pragma once
+#if defined(__CUDACC__)
+#include "common.cuh"
+#else
+#include "ldpc_math.cuh"      // host build (tests/host_emu): the generators only
+#endif
+
+namespace ldpc {
+
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+LDPC_HD uint32_t mulhi32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+// Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3), key (k0, k1).
+LDPC_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o;
+    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// The four 32-bit words of (seed, frame, group of 4 variables).
+LDPC_HD Philox4 channel_words(unsigned long long seed, unsigned long long frame, uint32_t group)
+{
+    return philox4x32_10((uint32_t)frame, (uint32_t)(frame >> 32), group, 0x4c445043u /* "LDPC" */,
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// Box-Muller on two words: u1 in (0, 1) with 32 bits of resolution (|z| up to 6.7 sigma), u2 in [0, 1).
+LDPC_HD void box_muller(uint32_t r1, uint32_t r2, float *z0, float *z1)
+{
+    const float u1 = fmaf((float)r1, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float u2 = (float)r2 * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float s, c;
+#if defined(__CUDA_ARCH__)
+    sincospif(2.0f * u2, &s, &c);
+#else
+    s = sinf(6.283185307179586f * u2); c = cosf(6.283185307179586f * u2);
+#endif
+    *z0 = rad * c;
+    *z1 = rad * s;
+}
+
+enum { GEN_BSC = 1, GEN_BIAWGN = 2, GEN_BEC = 3 };     // == LDPC_CH_*
+
+#if defined(__CUDACC__)
+// y [B][n] (reference layout): float32 for BIAWGN, uint8 for BSC / BEC.  Thread = (frame, group of 4 variables).
+// x: transmitted word [n] uint8 or NULL (all-zero word).  param: p (BSC, BEC) or sqrt(noise_var) (BIAWGN).
+template <int MODE>
+__global__ void channel_generate(void *__restrict__ y, const uint8_t *__restrict__ x, int B, int n, double param,
+                                 unsigned long long seed, unsigned long long frame0)
+{
+    const int groups = (n + 3) >> 2;
+    const long long total = (long long)B * groups;
+    const uint32_t thr = (param >= 1.0) ? 0xffffffffu : (uint32_t)(param * 4294967296.0);   // u < p  <=>  r < p * 2^32
+    const float sigma = (float)param;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i / groups), g = (int)(i % groups);
+        const Philox4 r = channel_words(seed, frame0 + (unsigned long long)f, (uint32_t)g);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (MODE == GEN_BIAWGN) {
+            box_muller(r.x, r.y, &z[0], &z[1]);
+            box_muller(r.z, r.w, &z[2], &z[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = 4 * g + j;
+            if (v >= n) break;
+            const uint32_t xb = (x != nullptr) ? (uint32_t)(x[v] != 0) : 0u;
+            const size_t o = (size_t)f * n + v;
+            if (MODE == GEN_BIAWGN) {
+                reinterpret_cast<float *>(y)[o] = fmaf(sigma, z[j], xb ? 1.0f : -1.0f);
+            } else {
+                const bool hit = (param >= 1.0) || (rr[j] < thr);
+                if (MODE == GEN_BSC) reinterpret_cast<uint8_t *>(y)[o] = (uint8_t)(xb ^ (hit ? 1u : 0u));
+                else reinterpret_cast<uint8_t *>(y)[o] = (uint8_t)(hit ? 2u : xb);
+            }
+        }
+    }
+}
+
+// bit_errs[b] = #{v : x_hat[b][v] != x[v]} (src/main.py:41; an undecoded BEC symbol 2 counts as an error).  One warp per frame.
+__global__ void count_errors(const uint8_t *__restrict__ x_hat, const uint8_t *__restrict__ x, int B, int n, int *__restrict__ bit_errs)
+{
+    const int lane = threadIdx.x & 31;
+    const int f = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (f >= B) return;
+    const uint8_t *row = x_hat + (size_t)f * n;
+    int e = 0;
+    for (int v = lane; v < n; v += 32) e += (row[v] != ((x != nullptr) ? x[v] : (uint8_t)0)) ? 1 : 0;
+    e = __reduce_add_sync(kFull, e);
+    if (lane == 0) bit_errs[f] = e;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace ldpc

@@ -4,11 +4,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
 
+#include "channel_gen.cuh"
 #include "common.cuh"
 #include "io_kernels.cuh"
 #include "res_layout.h"
@@ -979,6 +981,35 @@ int ldpc_llr_biawgn(ldpc_t *h, int y_dtype, int dtype, double noise_var, const v
     else if (y_dtype == LDPC_F32 && dtype == LDPC_F32) LAUNCH(h, (llr_flat<float, float, IN_BIAWGN>), blocks, 256, s, (const float *)y, (float *)priors, count, noise_var);
     else return fail(h, LDPC_EINVAL, "bad dtype");
     return check_launch(h, "llr_biawgn");
+}
+
+int ldpc_channel_generate(ldpc_t *h, int channel, double param, const uint8_t *x,
+                          unsigned long long seed, unsigned long long frame0, int B, void *y, void *stream)
+{
+    if (!h) return LDPC_EINVAL;
+    if (B <= 0 || !y) return fail(h, LDPC_EINVAL, "bad arguments");
+    if (!(param >= 0.0)) return fail(h, LDPC_EINVAL, "channel parameter must be >= 0");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const Tables &t = h->t;
+    const long long total = (long long)B * ((t.n + 3) / 4);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (channel) {
+    case LDPC_CH_BSC: LAUNCH(h, (channel_generate<GEN_BSC>), blocks, 256, s, y, x, B, t.n, param, seed, frame0); break;
+    case LDPC_CH_BEC: LAUNCH(h, (channel_generate<GEN_BEC>), blocks, 256, s, y, x, B, t.n, param, seed, frame0); break;
+    case LDPC_CH_BIAWGN: LAUNCH(h, (channel_generate<GEN_BIAWGN>), blocks, 256, s, y, x, B, t.n, sqrt(param), seed, frame0); break;
+    default: return fail(h, LDPC_EINVAL, "bad channel");
+    }
+    return check_launch(h, "channel_generate");
+}
+
+int ldpc_count_errors(ldpc_t *h, const uint8_t *x_hat, const uint8_t *x, int B, int32_t *bit_errs, void *stream)
+{
+    if (!h) return LDPC_EINVAL;
+    if (B <= 0 || !x_hat || !bit_errs) return fail(h, LDPC_EINVAL, "bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    LAUNCH(h, count_errors, (B + 7) / 8, 256, (cudaStream_t)stream, x_hat, x, B, h->t.n, bit_errs);
+    return check_launch(h, "count_errors");
 }
 
 int ldpc_debug_step(ldpc_t *h, int algo, int dtype, int which, int B, const void *prior, const void *msg_in,

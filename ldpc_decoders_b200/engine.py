@@ -187,6 +187,46 @@ class Engine:
         _lib.check(self.handle, rc)
         return dict(x_hat=x_hat, iters=iters, reason=reason, marg=None)
 
+    # ------------------------------------------------------------------ on-device Monte-Carlo round
+    def channel_generate(self, channel, param, B, seed, frame0=0, x=None, stream=None, out=None):
+        """Received block for B frames of the word x (CUDA uint8 [n], None = all-zero) drawn on the GPU
+        (ldpc_channel_generate): float32 [B,n] for BIAWGN (param = noise_var), uint8 for BSC / BEC (param = p)."""
+        torch = _torch()
+        t = self.tables
+        dt = torch.float32 if channel == _lib.CH_BIAWGN else torch.uint8
+        y = out if out is not None else torch.empty((int(B), t.n), dtype=dt, device=self._dev())
+        rc = self.lib.ldpc_channel_generate(self.handle, channel, float(param), None if x is None else x.data_ptr(),
+                                            int(seed) & (2 ** 64 - 1), int(frame0), int(B), y.data_ptr(),
+                                            self._stream_ptr(stream))
+        _lib.check(self.handle, rc)
+        return y
+
+    def count_errors(self, x_hat, x=None, stream=None):
+        """int32 [B]: bit errors of every decoded frame against the word x (None = all-zero)."""
+        torch = _torch()
+        errs = torch.empty(int(x_hat.shape[0]), dtype=torch.int32, device=x_hat.device)
+        rc = self.lib.ldpc_count_errors(self.handle, x_hat.data_ptr(), None if x is None else x.data_ptr(),
+                                        int(x_hat.shape[0]), errs.data_ptr(), self._stream_ptr(stream))
+        _lib.check(self.handle, rc)
+        return errs
+
+    def simulate(self, channel, algo, dtype, param, B, seed, frame0=0, x=None, max_iter=10, iter_cap=0, flags=0,
+                 stream=None, bufs=None):
+        """One Monte-Carlo round entirely on the GPU: draw B received frames (global indices frame0 ..), decode,
+        count bit errors.  `param` is the reference's channel parameter (p, or the SNR-derived noise_var for
+        BIAWGN; the BSC decoder gets llr = log(1-p) - log(p)).  Returns dict(bit_errs int32 [B], iters int32 [B],
+        reason uint8 [B], x_hat uint8 [B,n]) of CUDA tensors; only the two small vectors need to travel to the host."""
+        bufs = {} if bufs is None else bufs
+        y = self.channel_generate(channel, param, B, seed, frame0, x, stream, out=bufs.get("y"))
+        bufs["y"] = y
+        dec_param = float(np.log(1 - param) - np.log(param)) if channel == _lib.CH_BSC else param
+        out = self.decode_device_channel(channel, _lib.BEC if channel == _lib.CH_BEC else algo, dtype, dec_param, y,
+                                         max_iter=max_iter, iter_cap=iter_cap, flags=flags, stream=stream,
+                                         out=bufs.get("out"))
+        bufs["out"] = out
+        out["bit_errs"] = self.count_errors(out["x_hat"], x, stream)
+        return out
+
     # ------------------------------------------------------------------ host-buffer decode (e2e path)
     def decode_host(self, channel, algo, dtype, param, y, max_iter=10, iter_cap=0, chunk=0, flags=0,
                     x_hat=None, iters=None, reason=None):

@@ -41,6 +41,9 @@ def setup_parser():
     p.add_argument('--dtype', default='f64', choices=['f32', 'f64'], help='message arithmetic (f64 = the reference)')
     p.add_argument('--frames', default=0, type=int, help='fixed number of frames per parameter instead of --min-wec')
     p.add_argument('--seed', default=None, type=int, help='np.random.seed before each parameter (reference: unseeded)')
+    p.add_argument('--noise', default='host', choices=['host', 'device'],
+                   help="host: numpy's global RNG like the reference (parity runs); device: Philox on the GPU, keyed by "
+                        "(seed, global frame index) - same frames for any --batch / GPU count, nothing but counters crosses PCIe")
     p.add_argument('--codes-dir', default=None)
     return p
 
@@ -69,7 +72,8 @@ class Saver:
             json.dump(data, fp, indent=4)
 
 
-def run_param(decode_batch, send, x, comm, batch, min_wec, frames=0, max_iter=10, on_status=None, log_freq=5.):
+def run_param(decode_batch, send, x, comm, batch, min_wec, frames=0, max_iter=10, on_status=None, log_freq=5.,
+              simulate_batch=None, seed=0):
     """Monte-Carlo loop for one channel parameter.
 
     decode_batch(Y) -> (X_hat [b,n], iters [b]);  send(X) -> received block for X [b,n] (global RNG stream).
@@ -82,11 +86,15 @@ def run_param(decode_batch, send, x, comm, batch, min_wec, frames=0, max_iter=10
     rnd = 0
     start = time.time()
     while (wec < min_wec) if frames <= 0 else (tot < frames):
-        Y = send(np.tile(x, (comm.world * batch, 1)))
         g0, g1 = round_slice(rnd, comm.rank, comm.world, batch)
-        lo = g0 - rnd * comm.world * batch
-        X_hat, iters = decode_batch(Y[lo:lo + batch])
-        errs = (np.asarray(X_hat) != x[None, :]).sum(axis=1).astype(np.int64)
+        if simulate_batch is not None:                   # noise drawn on the GPU, keyed by the global frame index
+            errs, iters = simulate_batch(x, batch, seed, g0)
+            errs = np.asarray(errs, np.int64)
+        else:
+            Y = send(np.tile(x, (comm.world * batch, 1)))
+            lo = g0 - rnd * comm.world * batch
+            X_hat, iters = decode_batch(Y[lo:lo + batch])
+            errs = (np.asarray(X_hat) != x[None, :]).sum(axis=1).astype(np.int64)
         both = comm.allgather(np.concatenate([errs, np.asarray(iters, np.int64)]))
         errs_g = both[:, :batch].reshape(-1)
         iters_g = both[:, batch:].reshape(-1)
@@ -146,7 +154,9 @@ def main(argv=None):
             log.info('TOT:%d, WEC:%d, WER:%s, BEC:%d, BER:%s' % (tot, wec, wer, bec, ber))
 
         r = run_param(decoder.decode_batch, channel.send, x, comm, args.batch, args.min_wec, args.frames,
-                      args.max_iter, status, args.log_freq)
+                      args.max_iter, status, args.log_freq,
+                      simulate_batch=decoder.simulate_batch if args.noise == 'device' else None,
+                      seed=(args.seed or 0) * 1000003 + int(round(param * 1e6)))
         if comm.rank == 0:
             log.info('TOT:%d, WEC:%d, WER:%s, BEC:%d, BER:%s' % (r['tot'], r['wec'], r['wer'], r['bec'], r['ber']))
             saver.add(param, OrderedDict((k, r[k]) for k in ('tot', 'wec', 'wer', 'bec', 'ber', 'dec')))

@@ -11,6 +11,7 @@
 
 #include "../../ldpc_decoders_b200/csrc/ldpc_math.cuh"
 #include "../../ldpc_decoders_b200/csrc/res_layout.h"
+#include "../../ldpc_decoders_b200/csrc/channel_gen.cuh"
 
 using namespace ldpc;
 
@@ -343,6 +344,27 @@ int emu_llr_biawgn(size_t count, const double *y, double noise_var, float *fast,
         slow += llr_biawgn_fast_ok((-2.0 * y[i]) * inv) ? 0 : 1;
     }
     *slow_path = slow;
+    return 0;
+}
+
+
+// Philox4x32-10 block and the Box-Muller normals built on it (csrc/channel_gen.cuh).
+int emu_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out)
+{
+    const Philox4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+    return 0;
+}
+int emu_normals(unsigned long long seed, unsigned long long frame0, int frames, int n, float *z)
+{
+    for (int f = 0; f < frames; ++f)
+        for (int g = 0; g < (n + 3) / 4; ++g) {
+            const Philox4 r = channel_words(seed, frame0 + f, (uint32_t)g);
+            float zz[4];
+            box_muller(r.x, r.y, &zz[0], &zz[1]);
+            box_muller(r.z, r.w, &zz[2], &zz[3]);
+            for (int j = 0; j < 4 && 4 * g + j < n; ++j) z[(size_t)f * n + 4 * g + j] = zz[j];
+        }
     return 0;
 }
 

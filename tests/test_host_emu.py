@@ -23,7 +23,7 @@ EMU_DIR = os.path.join(HERE, "host_emu")
 def emu():
     so = os.path.join(EMU_DIR, "libhost_emu.so")
     src = os.path.join(EMU_DIR, "emu.cpp")
-    hdrs = [os.path.join(HERE, "..", "ldpc_decoders_b200", "csrc", h) for h in ("ldpc_math.cuh", "res_layout.h")]
+    hdrs = [os.path.join(HERE, "..", "ldpc_decoders_b200", "csrc", h) for h in ("ldpc_math.cuh", "res_layout.h", "channel_gen.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src],
                        check=True, cwd=EMU_DIR)
@@ -242,3 +242,34 @@ def test_biawgn_llr_without_division_is_exact(emu):
         assert (exact.view(np.uint32) == ref.view(np.uint32)).all()
         total_slow += slow.value
     assert total_slow < 120000          # the out-of-range test values, plus a handful of boundary cases
+
+
+# --------------------------------------------------------------------------------------------- on-device channel noise
+def test_philox_known_answers(emu):
+    """Philox4x32-10 against the Random123 known-answer vectors (kat_vectors)."""
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        c, k, o = np.array(ctr, np.uint32), np.array(key, np.uint32), np.zeros(4, np.uint32)
+        emu.emu_philox(ptr(c), ptr(k), ptr(o))
+        assert tuple(int(v) for v in o) == want
+
+
+def test_box_muller_normals(emu):
+    """The BIAWGN noise generator: standard normal moments, tails and independence between frames / variables."""
+    frames, n = 400, 1200
+    z = np.zeros((frames, n), np.float32)
+    emu.emu_normals(ctypes.c_ulonglong(7), ctypes.c_ulonglong(10 ** 12), frames, n, ptr(z))
+    N = z.size
+    assert abs(z.mean()) < 4 / np.sqrt(N) and abs(z.var() - 1) < 4 * np.sqrt(2 / N)
+    assert abs((z ** 3).mean()) < 4 * np.sqrt(15 / N) and abs((z ** 4).mean() - 3) < 4 * np.sqrt(96 / N)
+    for t, p in ((1.0, 0.31731), (2.0, 0.0455), (3.0, 0.0027)):
+        frac = (np.abs(z) > t).mean()
+        assert abs(frac - p) < 4 * np.sqrt(p / N)
+    assert abs(np.corrcoef(z[:-1].ravel(), z[1:].ravel())[0, 1]) < 4 / np.sqrt(N)       # frame f vs f+1
+    assert abs(np.corrcoef(z[:, :-1].ravel(), z[:, 1:].ravel())[0, 1]) < 4 / np.sqrt(N)  # variable v vs v+1
+    z2 = np.zeros((10, n), np.float32)
+    emu.emu_normals(ctypes.c_ulonglong(7), ctypes.c_ulonglong(10 ** 12 + 5), 10, n, ptr(z2))
+    assert (z2 == z[5:15]).all()                      # keyed by the global frame index only
