@@ -127,3 +127,20 @@ def test_two_process_gloo_run_matches_single_process(tmp_path):
     r = json.loads(line[7:])
     assert (r["tot"], r["wec"], r["bec"]) == (ref["tot"], ref["wec"], ref["bec"])
     assert r["sum_tot"] == 2 * ref["tot"] and r["ranks"] == 1      # all_reduce(SUM) over 2 ranks
+
+
+def test_named_simulation_cases_match_the_reference():
+    """ldpc_decoders_b200.simulations expands REG_ENS / IREG_ENS / REG_BAD / MAR / HMG to the same main.py command
+    lines as the reference's simulations.py (tests/golden/simulations_cases.txt = its own output, SPA / MSA lines)."""
+    import os
+    from ldpc_decoders_b200 import simulations, sim
+
+    def norm(tokens):
+        ap = sim.setup_parser()
+        a = ap.parse_args(tokens)
+        return (a.channel, a.code, a.decoder, a.codeword, a.max_iter, a.min_wec, tuple(round(v, 9) for v in a.params))
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = [norm(line.split()) for line in open(os.path.join(here, "golden", "simulations_cases.txt")) if line.strip()]
+    ours = [norm(c) for name in ("REG_ENS", "IREG_ENS", "REG_BAD", "MAR", "HMG") for c in simulations.all_cases[name]()]
+    assert len(gold) == 150 and ours == gold
