@@ -225,7 +225,7 @@ def extra_workloads(torch, lib, eng_mod, Tables, peak):
                     "step_hbm_frac": (cn_b + vn_b) * 3 / (ms / 1e3) / 1e9 / peak})
 
     tab = Tables(*load_code())
-    bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB SPA f32 (phi form), max_iter 10, cw=0", tab, lib.SPA, lib.F32, 2.0, 32768, cw=0)
+    bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB SPA f32 (hyperbolic-pair rule), max_iter 10, cw=0", tab, lib.SPA, lib.F32, 2.0, 32768, cw=0)
     bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB MSA f64, max_iter 10", tab, lib.MSA, lib.F64, 2.0, 16384)
     bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB SPA f64 (formula mirror), max_iter 10, cw=0", tab, lib.SPA, lib.F64, 2.0, 16384, cw=0)
     big = codes.random_regular(64800, 3, 6, seed=0).tables

@@ -48,7 +48,7 @@ extern "C" {
  * through priors.dtype).
  *   MSA: F32 / F64 are both bit-exact restatements at that dtype.
  *   SPA: F64 mirrors the reference formula (tanh / log / exp / atanh);
- *        F32 is the production form (phi-domain, numerically stable).
+ *        F32 is the production form (hyperbolic-pair rule, cancellation-free).
  *   BEC: dtype is ignored (bit-plane integer arithmetic). */
 #define LDPC_F32 0
 #define LDPC_F64 1

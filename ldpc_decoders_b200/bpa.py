@@ -11,7 +11,7 @@ plus the batch form the GPU exists for::
 
 The arithmetic type follows ``priors.dtype`` exactly like the reference (float32 priors ->
 float32 messages).  MSA is bit-exact at either type; SPA float64 mirrors the
-reference formula, SPA float32 uses the numerically stable phi form (see csrc/ldpc_math.cuh).
+reference formula, SPA float32 uses the cancellation-free hyperbolic-pair rule (csrc/ldpc_math.cuh cn_spa_sc).
 There is no CPU fallback: constructing a decoder without a CUDA device raises.
 """
 import numpy as np

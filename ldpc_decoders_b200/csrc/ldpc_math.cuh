@@ -4,7 +4,7 @@
 // one frame held in registers:
 //   cn_msa      bpa.MSA.decode_   /root/reference/src/bpa.py:86-102, math_utils.py:10,38-43,78-94
 //   cn_spa_ref  bpa.SPA.decode_   /root/reference/src/bpa.py:71-75,   math_utils.py:38-60   (formula mirror)
-//   cn_spa_phi  same function, evaluated in the phi domain for float32 (the mirror is unusable in fp32)
+//   cn_spa_sc   same function for float32, cancellation-free hyperbolic-pair rule (the mirror is unusable in fp32)
 //   vn_update   bpa.BPA.decode    /root/reference/src/bpa.py:35-37
 //   bec_*       bec.SPA.decode    /root/reference/src/bec.py:100-119, 32 frames per machine word (bit planes)
 //
@@ -31,9 +31,11 @@ template <> struct num<float> {
 #if defined(__CUDA_ARCH__)
     static LDPC_HD float add(float a, float b) { return __fadd_rn(a, b); }   // never contracted / reassociated
     static LDPC_HD float sub(float a, float b) { return __fsub_rn(a, b); }
+    static LDPC_HD float mul(float a, float b) { return __fmul_rn(a, b); }
 #else
     static LDPC_HD float add(float a, float b) { volatile float r = a + b; return r; }
     static LDPC_HD float sub(float a, float b) { volatile float r = a - b; return r; }
+    static LDPC_HD float mul(float a, float b) { volatile float r = a * b; return r; }
 #endif
 };
 template <> struct num<double> {
@@ -215,68 +217,121 @@ LDPC_HD void cn_spa_ref(const double (&v)[DCMAX], int dc, double (&out)[DCMAX])
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sum-product check node in float32, phi domain:
-//   |out_k| = phi( sum_{j != k} phi(|v_j|) ),  phi(x) = -log tanh(x/2) = log((1+e^-x)/(1-e^-x))
-//   sign    = (-1)^{#(v<0)} * sign(v_k)
-// phi is evaluated without cancellation: series for 1-e^-x when x is tiny, the
-// atanh series 2u(1+u^2/3+u^4/5), u = e^-x, when x > 3.  The sum over the OTHER
-// edges is built from prefix/suffix sums (total - own cancels catastrophically).
-// Degenerate inputs follow the reference: v_k == 0 gives NaN on that edge
-// (0/0, bpa.py:74) and 0 on the others; all others saturated gives +-inf.
-// Saturation is the reference's, not float32's: in float64 tanh(v/2) rounds to exactly 1 once
-// |v| > 55 ln 2 = 38.123 (2 e^-|v| < 2^-54), its log is then 0, and a check whose OTHER inputs are all
-// saturated emits +-inf (|q| == 1, math_utils.py:57-58) which turns the variable's "total minus own"
-// into inf - inf = NaN (bpa.py:37) and floods the frame.  With sat_llr = 38.123 a saturated input
-// contributes phi = 0 here too, so the float32 decoder leaves the well-conditioned regime at the same
-// point as the reference (its BER/WER curves depend on it: a flooded frame decodes to all-zero).
-// sat_llr = +inf switches the emulation off (numerically robust decoder).
-// Measured against the float64 reference formula: <= 6e-7 * max(1,|ref|) for |ref| < 20.
+// Saturation of the float64 reference, emulated by the float32 rule below.  In float64 tanh(v/2) rounds to exactly 1
+// once |v| > 55 ln 2 = 38.123 (2 e^-|v| < 2^-54), its log is then 0, and a check whose OTHER inputs are all saturated
+// emits +-inf (|q| == 1, math_utils.py:57-58), which turns the variable's "total minus own" into inf - inf = NaN
+// (bpa.py:37) and floods the frame.  With sat_llr = 38.123 a saturated input contributes u = e^-|v| = 0 here too, so
+// the float32 decoder leaves the well-conditioned regime at the same point as the reference (its BER/WER curves
+// depend on it: a flooded frame decodes to all-zero).  sat_llr = +inf switches the emulation off (robust decoder).
 // ---------------------------------------------------------------------------------------------
-LDPC_HD float phi_f32(float x)
+constexpr float kSpaSatLlr = 38.1230f;
+
+// ---------------------------------------------------------------------------------------------
+// Sum-product check node in float32, hyperbolic-pair form (the kernels' float32 SPA rule).
+// With u_j = e^-|v_j| the magnitude of bpa.py:71-75 is
+//   |out_k| = 2 atanh( prod_{j != k} tanh(|v_j| / 2) ) = log( S_k / C_k ),
+//   S_k = A + B, C_k = A - B,  A = prod_{j != k} (1 + u_j),  B = prod_{j != k} (1 - u_j).
+// (S, C) of a set grows by one element with two fused multiply-adds and never subtracts:
+//   (S, C) -> (S + u C, C + u S)        [the tanh addition theorem on C / S]
+// so both stay accurate to a few ulp whatever the inputs (no 1 - P, no total-minus-own), S >= C holds after
+// rounding (both are monotone in the same exact quantities), and an input v_j == 0 (u_j = 1) makes S == C bit for
+// bit from then on, i.e. |out| == 0 exactly like the reference's 0 * ... = 0 (bpa.py:74).
+// Cost for a degree-6 check: 6 ex2 + 14 pair steps (28 FFMA) + 12 lg2 — 18 MUFU and ~100 instructions, against 36 MUFU
+// and ~280 instructions for the phi-domain form phi(sum phi) it replaced (kept as a cross-check in tests/host_emu).  v_k == 0 gives NaN on its own edge (0/0), a check whose OTHER inputs are all
+// saturated (u = 0 beyond sat_llr, above) gives C == 0 -> +-inf: the reference's degenerate cases.
+// Measured against the float64 formula on the float32-rounded golden states: <= 1e-6 * max(1,|ref|) for |ref| < 20.
+// ---------------------------------------------------------------------------------------------
+LDPC_HD float spa_ex2(float x)
 {
 #if defined(__CUDA_ARCH__)
-    const float u = __expf(-x);
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
-    const float u = expf(-x);
+    return exp2f(x);
 #endif
-    const float series = x * (1.0f - x * 0.5f * (1.0f - x * (1.0f / 3.0f) * (1.0f - x * 0.25f)));
-    const float den = (x < 0.05f) ? series : (1.0f - u);
+}
+LDPC_HD float spa_lg2(float x)
+{
 #if defined(__CUDA_ARCH__)
-    const float big = __logf(__fdividef(1.0f + u, den));
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
-    const float big = logf((1.0f + u) / den);
+    return log2f(x);
 #endif
-    const float u2 = u * u;
-    const float small = 2.0f * u * (1.0f + u2 * ((1.0f / 3.0f) + u2 * 0.2f));
-    return (x > 3.0f) ? small : big;
+}
+struct SpaPair { float s, c; };
+LDPC_HD SpaPair sc_one(float u) { SpaPair r; r.s = 1.0f; r.c = u; return r; }
+LDPC_HD SpaPair sc_step(SpaPair a, float u)
+{
+    SpaPair r;
+    r.s = fmaf(u, a.c, a.s);
+    r.c = fmaf(u, a.s, a.c);
+    return r;
+}
+// Union of two disjoint sets.  Products and sums are rounded separately so that a side with s == c yields s == c.
+LDPC_HD SpaPair sc_join(SpaPair a, SpaPair b)
+{
+    SpaPair r;
+    r.s = num<float>::add(num<float>::mul(a.s, b.s), num<float>::mul(a.c, b.c));
+    r.c = num<float>::add(num<float>::mul(a.s, b.c), num<float>::mul(a.c, b.s));
+    return r;
+}
+// xs = (xor of all sign bits) | bits(ln 2): the check's parity riding on the scale factor, applied by one multiplication
+// like the reference's literal sign * magnitude.  Sign BITS instead of (v < 0) only changes the sign of zero and
+// NaN results (an input of -0.0 makes every other output a zero, a NaN input makes every output NaN).
+template <bool CLAMP>
+LDPC_HD float sc_out(SpaPair a, float v, uint32_t xs)
+{
+    float d = spa_lg2(a.s) - spa_lg2(a.c);                         // >= 0: S >= C after rounding when built from steps only
+    if (CLAMP) d = (d < 0.0f) ? 0.0f : d;                          // sc_join may round S one ulp below C; NaN stays NaN
+    const float r = d * bits_f32(xs ^ (f32_bits(v) & 0x80000000u));
+    return (v == 0.0f) ? NAN : r;
 }
 
-constexpr float kSpaSatLlr = 38.1230f;       // 55 ln 2: float64 tanh(v/2) == 1 beyond this |v|
-
 template <int DCMAX>
-LDPC_HD void cn_spa_phi(const float (&v)[DCMAX], int dc, float (&out)[DCMAX], float sat_llr = kSpaSatLlr)
+LDPC_HD void cn_spa_sc(const float (&v)[DCMAX], int dc, float (&out)[DCMAX], float sat_llr = kSpaSatLlr)
 {
-    float a[DCMAX], pre[DCMAX];
-    unsigned par = 0u;
-    float run = 0.0f;
+    float u[DCMAX];
+    uint32_t x = 0u;
 #pragma unroll
     for (int k = 0; k < DCMAX; ++k)
         if (k < dc) {
             const float av = fabsf(v[k]);
-            a[k] = (av > sat_llr) ? 0.0f : phi_f32(av);
-            par ^= (v[k] < 0.0f) ? 1u : 0u;
-            pre[k] = run;
-            run += a[k];
+            u[k] = (av > sat_llr) ? 0.0f : spa_ex2(av * -1.44269504088896f);
+            x ^= f32_bits(v[k]);
         }
-    float suf = 0.0f;
+    const uint32_t xs = (x & 0x80000000u) | 0x3f317218u;            // +-ln 2
+    if (DCMAX >= 6 && dc == 6) {
+        // all-but-one sets of {0..5} from the two halves, single-element steps only (14 of them)
+        const SpaPair L = sc_step(sc_step(sc_one(u[0]), u[1]), u[2]);
+        const SpaPair R = sc_step(sc_step(sc_one(u[3]), u[4]), u[5]);
+        const SpaPair R0 = sc_step(R, u[0]), R1 = sc_step(R, u[1]);
+        const SpaPair L3 = sc_step(L, u[3]), L4 = sc_step(L, u[4]);
+        out[0] = sc_out<false>(sc_step(R1, u[2]), v[0], xs);
+        out[1] = sc_out<false>(sc_step(R0, u[2]), v[1], xs);
+        out[2] = sc_out<false>(sc_step(R0, u[1]), v[2], xs);
+        out[3] = sc_out<false>(sc_step(L4, u[5]), v[3], xs);
+        out[4] = sc_out<false>(sc_step(L3, u[5]), v[4], xs);
+        out[5] = sc_out<false>(sc_step(L3, u[4]), v[5], xs);
+        return;
+    }
+    // general degree: prefix sets by steps, suffix sets by steps, joined
+    SpaPair pre[DCMAX];
+    SpaPair run = sc_one(0.0f);                                     // the empty set: (1, 0)
+#pragma unroll
+    for (int k = 0; k < DCMAX; ++k)
+        if (k < dc) {
+            pre[k] = run;
+            run = sc_step(run, u[k]);
+        }
+    SpaPair suf = sc_one(0.0f);
 #pragma unroll
     for (int k = DCMAX - 1; k >= 0; --k)
         if (k < dc) {
-            const float mag = phi_f32(pre[k] + suf);
-            suf += a[k];
-            const unsigned neg = par ^ ((v[k] < 0.0f) ? 1u : 0u);
-            const float r = neg ? -mag : mag;
-            out[k] = (v[k] == 0.0f) ? NAN : r;
+            out[k] = sc_out<true>(sc_join(pre[k], suf), v[k], xs);
+            suf = sc_step(suf, u[k]);
         }
 }
 

@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const R
                         if (UDC) cn_msa_lean<DCP>(a, o);
                         else cn_msa_bits<DCP>(a, dc, o);
                     } else {
-                        cn_spa_phi<DCP>(a, dc, o, p.sat_llr);
+                        cn_spa_sc<DCP>(a, UDC ? DCP : dc, o, p.sat_llr);
                     }
 #pragma unroll
                     for (int k = 0; k < DCP; ++k) (&mg[k].x)[j] = o[k];

@@ -46,7 +46,7 @@ template <int DCMAX> struct CnMath<double, ALGO_SPA_REF, DCMAX> {
     static __device__ __forceinline__ void run(const double (&v)[DCMAX], int dc, double (&o)[DCMAX]) { cn_spa_ref<DCMAX>(v, dc, o); }
 };
 template <int DCMAX> struct CnMath<float, ALGO_SPA_PHI, DCMAX> {
-    static __device__ __forceinline__ void run(const float (&v)[DCMAX], int dc, float (&o)[DCMAX]) { cn_spa_phi<DCMAX>(v, dc, o); }
+    static __device__ __forceinline__ void run(const float (&v)[DCMAX], int dc, float (&o)[DCMAX]) { cn_spa_sc<DCMAX>(v, dc, o); }
 };
 
 // ------------------------------------------------------------------------------------------------

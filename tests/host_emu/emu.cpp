@@ -12,6 +12,7 @@
 #include "../../ldpc_decoders_b200/csrc/ldpc_math.cuh"
 #include "../../ldpc_decoders_b200/csrc/res_layout.h"
 #include "../../ldpc_decoders_b200/csrc/channel_gen.cuh"
+#include "spa_phi_alt.h"
 
 using namespace ldpc;
 
@@ -60,6 +61,18 @@ void cn_spa_phi_all(const G &g, const float *v2c, float *c2v)
         for (int k = 0; k < dc; ++k) c2v[e0 + k] = o[k];
     }
 }
+int g_spa_rule = 1;            // 1: hyperbolic-pair rule (the kernels'), 0: phi-domain form
+// the float32 sum-product rule the kernels use (hyperbolic-pair form)
+void cn_spa_sc_all(const G &g, const float *v2c, float *c2v, float sat = kSpaSatLlr)
+{
+    for (int c = 0; c < g.m; ++c) {
+        const int e0 = g.chk_ptr[c], dc = g.chk_ptr[c + 1] - e0;
+        float a[DMAX], o[DMAX];
+        for (int k = 0; k < dc; ++k) a[k] = v2c[e0 + k];
+        cn_spa_sc<DMAX>(a, dc, o, sat);
+        for (int k = 0; k < dc; ++k) c2v[e0 + k] = o[k];
+    }
+}
 
 template <typename T>
 void decode_bp(const G &g, int algo, const T *prior, const uint8_t *y_hard, int max_iter,
@@ -83,6 +96,7 @@ void decode_bp(const G &g, int algo, const T *prior, const uint8_t *y_hard, int 
         if (algo == 0) cn_msa_all<T>(g, msg.data(), tmp.data());
         else if (algo == 2) cn_msa_bits_all(g, (const float *)msg.data(), (float *)tmp.data());
         else if (sizeof(T) == 8) cn_spa_ref_all(g, (const double *)msg.data(), (double *)tmp.data());
+        else if (g_spa_rule) cn_spa_sc_all(g, (const float *)msg.data(), (float *)tmp.data());
         else cn_spa_phi_all(g, (const float *)msg.data(), (float *)tmp.data());
         for (int v = 0; v < g.n; ++v) {
             const int p0 = g.var_ptr[v], dv = g.var_ptr[v + 1] - p0;
@@ -126,6 +140,15 @@ int emu_cn_msa_bits(int n, int m, int E, const int32_t *cp, const int32_t *ev, c
 {
     G g{n, m, E, cp, ev, nullptr, nullptr};
     cn_msa_bits_all(g, v2c, c2v);
+    return 0;
+}
+
+void emu_set_spa_rule(int r) { g_spa_rule = r; }
+
+int emu_cn_sc(int n, int m, int E, const int32_t *cp, const int32_t *ev, const float *v2c, float *c2v, float sat)
+{
+    G g{n, m, E, cp, ev, nullptr, nullptr};
+    cn_spa_sc_all(g, v2c, c2v, sat);
     return 0;
 }
 

@@ -24,6 +24,7 @@ def emu():
     so = os.path.join(EMU_DIR, "libhost_emu.so")
     src = os.path.join(EMU_DIR, "emu.cpp")
     hdrs = [os.path.join(HERE, "..", "ldpc_decoders_b200", "csrc", h) for h in ("ldpc_math.cuh", "res_layout.h", "channel_gen.cuh")]
+    hdrs.append(os.path.join(EMU_DIR, "spa_phi_alt.h"))
     if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src],
                        check=True, cwd=EMU_DIR)
@@ -94,16 +95,27 @@ def test_msa_bit_pattern_variant_is_identical(emu, rec):
     assert (a.view(np.uint32) == b.view(np.uint32)).all()
 
 
-def test_spa_phi_f32_teacher_forced(emu):
-    """float32 phi-domain check node vs the float64 reference formula on the same (f32-rounded) inputs:
+def cn_sc(emu, g, v32, sat=38.1230):
+    out = np.zeros_like(v32)
+    emu.emu_cn_sc(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(v32), ptr(out), ctypes.c_float(sat))
+    return out
+
+
+@pytest.mark.parametrize("rule", ["sc", "phi"])
+def test_spa_f32_teacher_forced(emu, rule):
+    """float32 check node (the kernels' hyperbolic-pair rule, and the phi-domain form it replaced) vs the float64
+    reference formula on the same (f32-rounded) inputs:
     |d| <= 1e-4 * max(1,|ref|) for |ref| < 20 (north_star tolerance); sign + large magnitude beyond."""
     worst = 0.0
     for rec, v2c, _ in G.spa_tf():
         g = graph(rec["code"])
         v32 = np.ascontiguousarray(v2c, np.float32)
         ref = O.cn_sweep(g, O.SPA, v32.astype(np.float64))
-        out = np.zeros_like(v32)
-        emu.emu_cn_phi(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(v32), ptr(out))
+        if rule == "sc":
+            out = cn_sc(emu, g, v32)
+        else:
+            out = np.zeros_like(v32)
+            emu.emu_cn_phi(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(v32), ptr(out))
         a = np.abs(ref)
         m = a < 20
         err = np.abs(out[m] - ref[m]) / np.maximum(1, a[m])
@@ -114,19 +126,30 @@ def test_spa_phi_f32_teacher_forced(emu):
     assert worst < 5e-6        # measured ~6e-7; the stated tolerance is 1e-4
 
 
-def test_spa_phi_degenerate_inputs(emu):
+def test_spa_f32_degenerate_inputs(emu):
     g = graph("7_4_hamming")
     v = np.array([0.0, 1.0, -2.0, 3.0,   50.0, 60.0, -70.0, 0.5,   1e-6, -1e-6, 30., 2.], np.float32)
-    out = np.zeros_like(v)
-    emu.emu_cn_phi(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(v), ptr(out))
+    out = cn_sc(emu, g, v, sat=np.inf)                      # saturation emulation off
     ref = O.cn_sweep(g, O.SPA, v.astype(np.float64))
     assert np.isnan(out[0]) and np.isnan(ref[0])            # v == 0: 0/0 on its own edge (bpa.py:74)
     assert (out[1:4] == 0).all() and (ref[1:4] == 0).all()  # and 0 on the others
-    # all OTHER inputs saturated: the float64 formula overflows to -inf (tanh == 1 beyond |v| = 38),
-    # the phi form returns the true value ~ -50; both count as "certain" under the stated metric
-    assert ref[7] == -np.inf and out[7] < -15
+    # all OTHER inputs saturated: the float64 formula overflows to -inf (tanh == 1 beyond |v| = 38); without the
+    # saturation emulation the float32 rule returns the true value ~ -50, with it (the default) -inf like the reference
+    assert ref[7] == -np.inf and -51 < out[7] < -49
+    assert cn_sc(emu, g, v)[7] == -np.inf
     keep = [4, 5, 6, 8, 9, 10, 11]
-    np.testing.assert_allclose(out[keep], ref[keep], rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(out[keep], ref[keep], rtol=1e-5, atol=1e-7)     # stated tolerance: 1e-4 * max(1, |ref|)
+    # degree-6 checks take the step-only tree: a zero input still zeroes the others exactly and NaNs its own edge
+    g6 = graph("1200_3_6_rand_ldpc_1")
+    v6 = np.random.RandomState(5).normal(size=g6.E).astype(np.float32) * 4
+    zeros = np.arange(0, g6.E, 7)
+    v6[zeros] = 0.0
+    o6 = cn_sc(emu, g6, v6)
+    r6 = O.cn_sweep(g6, O.SPA, v6.astype(np.float64))
+    assert (np.isnan(o6) == np.isnan(r6)).all() and np.isnan(o6[zeros]).all()
+    assert ((o6 == 0) == (r6 == 0)).all()
+    ok = np.isfinite(r6)
+    assert (np.abs(o6[ok] - r6[ok]) <= 1e-5 * np.maximum(1, np.abs(r6[ok]))).all()
 
 
 BEC_RUNS = [r for r in G.runs() if r["channel"] == "bec"]
