@@ -12,7 +12,10 @@ A step = one pass of the hot path over one batch of FRAMES frames per GPU: LLR f
   value     frames/s with the received block already resident in HBM (CUDA events on the launching stream)
   e2e       the same through the host-buffer entry point (ldpc_decode_host behind decode_batch): pinned
             host y in, x_hat / iteration counts out, copies inside the timed region
-  roofline  the dominant sweep kernel: algorithmic bytes / its event-timed launch durations vs measured HBM peak
+  roofline  the dominant kernel: algorithmic bytes / its event-timed launch durations vs measured HBM peak
+            (on-chip path: an EFFECTIVE figure, plus `shared` = its shared-memory roofline and `traffic` = real DRAM bytes)
+  roofline_streaming   the HBM-streaming path on the same workload (results asserted identical)
+  spa       the other half of the metric: float32 sum-product on the same code / SNR / frames
   cpu_baseline / --impl reference: the oracle port (oracle/ldpc_oracle.c, scalar C restatement of src/bpa.py)
             on the host cores — the reference itself is Python and does not travel to the GPU box.
 """
@@ -225,7 +228,6 @@ def extra_workloads(torch, lib, eng_mod, Tables, peak):
                     "step_hbm_frac": (cn_b + vn_b) * 3 / (ms / 1e3) / 1e9 / peak})
 
     tab = Tables(*load_code())
-    bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB SPA f32 (hyperbolic-pair rule), max_iter 10, cw=0", tab, lib.SPA, lib.F32, 2.0, 32768, cw=0)
     bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB MSA f64, max_iter 10", tab, lib.MSA, lib.F64, 2.0, 16384)
     bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB SPA f64 (formula mirror), max_iter 10, cw=0", tab, lib.SPA, lib.F64, 2.0, 16384, cw=0)
     big = codes.random_regular(64800, 3, 6, seed=0).tables
@@ -308,12 +310,12 @@ def main():
     # ---- synthetic received block, resident in HBM: y = (2x-1) + sigma * N(0,1), x = all ones; seed by global rank
     g = torch.Generator(device="cuda").manual_seed(1000 + rank)
     y = 1.0 + nv ** .5 * torch.randn((B, tab.n), generator=g, device="cuda", dtype=torch.float32)
-    def measure(flags):
+    def measure(flags, algo=lib.MSA, y=y):
         """K timed steps of the device-resident hot path under `flags`; per-launch events recorded inside."""
         res = {}
 
         def step():
-            res["o"] = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, y, max_iter=MAX_ITER,
+            res["o"] = eng.decode_device_channel(lib.CH_BIAWGN, algo, lib.F32, nv, y, max_iter=MAX_ITER,
                                                  out=res.get("o"), flags=flags)
 
         for _ in range(args.warmup):
@@ -366,36 +368,68 @@ def main():
             "bytes_per_edge_iteration": 17.5,
         }
 
-    streaming = None
-    if resident:
-        # The on-chip kernel keeps every frame in shared memory for all iterations: the algorithmic bytes of the
-        # streaming layout (63 000 B per frame-iteration) never touch HBM, so "achieved" is an
-        # EFFECTIVE bandwidth and may exceed the HBM peak; `traffic` / `dram_bytes_per_frame` is what DRAM really sees.
-        cn_bytes, vn_bytes = algorithmic_bytes(tab.E, tab.n, 4, iters, MAX_ITER)
-        k_ms = prof["cn_ms"]
+    def resident_roofline(m_, kernel_note):
+        """The on-chip kernel keeps every frame in shared memory for all iterations: the algorithmic bytes of the
+        streaming layout (63 000 B per frame-iteration) never touch HBM, so "achieved" is an EFFECTIVE
+        bandwidth and may exceed the HBM peak; `traffic` is what DRAM really sees, and `shared` is the kernel's own
+        (shared-memory) roofline."""
+        pr, it_ = m_["prof"], m_["iters"]
+        cn_bytes, vn_bytes = algorithmic_bytes(tab.E, tab.n, 4, it_, MAX_ITER)
+        k_ms = pr["cn_ms"]
         eff = (cn_bytes + vn_bytes) * args.steps / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
         io_bytes = B * (tab.n * 4 + tab.n + 5)
-        roofline = {
+        fi_per_s = float(it_.sum()) * args.steps / (k_ms / 1e3) if k_ms > 0 else 0.0
+        # shared-memory roofline: per frame-iteration the formulation moves 3E + 2n floats through shared memory
+        # (E marginal gathers + E message stores in the check phase, E message gathers + n prior loads + n marginal
+        # stores in the variable phase); peak = 128 B/clk/SM (B300_MICROARCH.md, LDS/STS) x SMs x the SM clock.
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        smem_bytes = (3 * tab.E + 2 * tab.n) * 4
+        return {
             "bound": "hbm", "kernel": "resident_bp", "achieved": eff, "peak": peak, "unit": "GB/s", "frac": eff / peak,
             "peak_source": peak_src, "traffic": traffic_per_launch("resident_bp"),
             "note": "EFFECTIVE GB/s: algorithmic bytes of the streaming layout (SURVEY 8d, 63 000 B per frame-iteration) / "
                     "kernel time.  frac > 1 is by design, not skipped work: the kernel keeps every frame in shared memory "
-                    "and registers for all its iterations, so DRAM only sees `traffic` (= compulsory_hbm_bytes_per_launch, "
-                    "ncu: 1.9 % DRAM throughput); it is bound by the shared-memory pipe (65 %) and instruction issue (55 %), "
-                    "profiles/README.md.  roofline_streaming is the HBM-bound path on the same workload, results asserted identical.",
-            "algorithmic_bytes_per_launch": (cn_bytes + vn_bytes), "avg_launch_ms": k_ms / max(1, prof["cn_launches"]),
+                    "and registers for all its iterations, so DRAM only sees `traffic` (= compulsory_hbm_bytes_per_launch). "
+                    + kernel_note + "  roofline_streaming is the HBM-bound path on the same workload, results asserted identical.",
+            "algorithmic_bytes_per_launch": (cn_bytes + vn_bytes), "avg_launch_ms": k_ms / max(1, pr["cn_launches"]),
             "compulsory_hbm_bytes_per_launch": io_bytes,
             "compulsory_hbm_GBps": io_bytes * args.steps / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0,
-            "kernel_share_of_step": k_ms / ms,
-            "frame_iterations_per_s": it_sum * args.steps / (k_ms / 1e3) if k_ms > 0 else 0.0,
-            "shared_memory_plan": eng.resident_plan(),
+            "kernel_share_of_step": k_ms / m_["ms"],
+            "frame_iterations_per_s": fi_per_s,
+            "shared": {"bound": "shared-memory pipe", "bytes_per_frame_iteration": smem_bytes,
+                       "achieved_GBps": smem_bytes * fi_per_s / 1e9, "sm_count": sm_count,
+                       "peak_bytes_per_clk_per_sm": 128},
         }
+
+    streaming = None
+    if resident:
+        roofline = resident_roofline(main, "It is bound by the shared-memory pipe (65 %) and instruction issue (55 %), profiles/README.md.")
+        roofline["shared_memory_plan"] = eng.resident_plan()
         sm = measure(args.flags | lib.PATH_STREAMING)
         assert (sm["iters"] == iters).all() and bool((sm["x_hat"] == x_hat).all()), "streaming and resident paths disagree"
         streaming = {"value": total_frames / (sm["ms"] / 1e3), "unit": UNIT, "ms_per_step": sm["ms"] / args.steps,
                      "gpu_launches": int(sm["launches"]), "roofline": streaming_roofline(sm)}
     else:
         roofline = streaming_roofline(main)
+
+    # ---- the other half of the metric: sum-product (float32), same code / SNR / frames, all-zero codeword
+    # (src/simulations.py:36 runs SPA with --codeword 0)
+    y_spa = y - 2.0
+    sp = measure(args.flags, algo=lib.SPA, y=y_spa)
+    sp_it = float(sp["iters"].sum())
+    if dist is not None:
+        t = torch.tensor([sp_it], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        sp_it_all = float(t.item())
+    else:
+        sp_it_all = sp_it
+    spa = {"workload": "same code, BIAWGN %.1f dB, sum-product float32 (hyperbolic-pair rule), max_iter %d, codeword=0" % (SNR_DB, MAX_ITER),
+           "value": total_frames / (sp["ms"] / 1e3), "unit": UNIT, "ms_per_step": sp["ms"] / args.steps,
+           "mean_iters": sp_it / B, "edge_updates_per_s": 2 * tab.E * sp_it_all * args.steps / (sp["ms"] / 1e3),
+           "wer": float((sp["x_hat"] != 0).any(dim=1).float().mean().item()), "gpu_launches": int(sp["launches"]),
+           "roofline": (resident_roofline(sp, "Sum-product adds the MUFU pipe (18 ex2/lg2 per check and frame, 45 %) to the limiters.")
+                        if sp["prof"]["vn_launches"] == 0 else streaming_roofline(sp))}
+    del y_spa
 
     # ---- e2e: host buffers through the host entry point (what decode_batch calls), copies inside the timed region
     Yh = pinned_empty((B, tab.n), np.float32)
@@ -429,6 +463,13 @@ def main():
            "timer": "host perf_counter around blocking calls, max over ranks"}
 
     clocks = sampler.stop() if sampler is not None else None
+    for rf in (roofline, spa["roofline"]):
+        sh = rf.get("shared") if isinstance(rf, dict) else None
+        if sh is not None:
+            mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            sh["peak_GBps"] = sh["peak_bytes_per_clk_per_sm"] * sh["sm_count"] * mhz * 1e6 / 1e9
+            sh["frac"] = sh["achieved_GBps"] / sh["peak_GBps"]
+            sh["sm_mhz"] = mhz
 
     if rank == 0:
         line = {
@@ -438,7 +479,7 @@ def main():
             "config": workload_config(B, world),
             "edge_updates_per_s": edge_updates, "mean_iters": it_sum / B, "wer": wer,
             "path": "resident (on-chip, LDPC_PATH_AUTO)" if resident else "streaming",
-            "roofline": roofline, "roofline_streaming": streaming, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "roofline_streaming": streaming, "spa": spa, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "gpu_launches_e2e": int(e_launches),
         }
         if world == 1 and not args.no_cpu_baseline:

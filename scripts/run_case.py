@@ -50,8 +50,9 @@ def main():
         ch, par = lib.CH_BIAWGN, nv
     else:
         flip = torch.rand((args.frames, tab.n), generator=g, device="cuda") < args.snr
+        import math
         y = (flip ^ bool(args.cw)).to(torch.uint8)
-        ch, par = lib.CH_BSC, args.snr
+        ch, par = lib.CH_BSC, math.log(1 - args.snr) - math.log(args.snr)      # the C ABI takes the LLR magnitude
     res = {}
 
     def step():
