@@ -162,7 +162,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT, flush=True)
 
 
 def workload_config(frames, world):
@@ -264,7 +264,21 @@ def extra_workloads(torch, lib, eng_mod, Tables, peak):
     return out
 
 
+RESULT = sys.stdout
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner on fd 1 at
+    communicator creation, whatever NCCL_DEBUG_FILE says), so keep a private copy of fd 1 for the result and point fd 1
+    itself at stderr for everybody else."""
+    global RESULT
+    sys.stdout.flush()
+    RESULT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -277,8 +291,6 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-        os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line (NCCL prints its version there)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -287,10 +299,13 @@ def main():
         run_reference(args, rank, world)
         return
 
+    from ldpc_decoders_b200 import dist as ldist
+    ldist.quiet_nccl_stdout()                         # keep stdout to the one JSON line (NCCL prints its version there)
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = ldist.bind_near_gpu(local_rank)       # pinned host buffers and the feeding thread on the GPU's NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -460,7 +475,8 @@ def main():
     e2e = {"value": total_frames / e_el, "unit": UNIT, "h2d_bytes_per_step": int(Yh.nbytes),
            "d2h_bytes_per_step": int(xh.nbytes + ith.nbytes + rsh.nbytes), "ms_per_step": 1e3 * e_el / args.steps,
            "api": "Engine.decode_host -> ldpc_decode_host (pinned float32 y in; x_hat, iters, reason out)",
-           "timer": "host perf_counter around blocking calls, max over ranks"}
+           "timer": "host perf_counter around blocking calls, max over ranks",
+           "host_cpus_bound": (len(numa_cpus) if numa_cpus else None)}
 
     clocks = sampler.stop() if sampler is not None else None
     for rf in (roofline, spa["roofline"]):
@@ -495,7 +511,7 @@ def main():
                 line["extra"] = extra_workloads(torch, lib, eng_mod, Tables, peak)
             except Exception as exc:        # side measurements must not lose the headline line
                 line["extra_error"] = repr(exc)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

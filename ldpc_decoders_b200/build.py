@@ -13,8 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libldpc_b200.so")
 SOURCES = ["ldpc_b200.cu"]
-HEADERS = ["common.cuh", "ldpc_math.cuh", "stream_bp.cuh", "stream_bp_tma.cuh", "stream_bec.cuh", "resident_bp.cuh", "io_kernels.cuh",
-           os.path.join("..", "..", "include", "ldpc_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "ldpc_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]

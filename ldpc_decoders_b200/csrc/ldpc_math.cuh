@@ -286,22 +286,34 @@ LDPC_HD float sc_out(SpaPair a, float v, uint32_t xs)
 {
     float d = spa_lg2(a.s) - spa_lg2(a.c);                         // >= 0: S >= C after rounding when built from steps only
     if (CLAMP) d = (d < 0.0f) ? 0.0f : d;                          // sc_join may round S one ulp below C; NaN stays NaN
-    const float r = d * bits_f32(xs ^ (f32_bits(v) & 0x80000000u));
-    return (v == 0.0f) ? NAN : r;
+    return d * bits_f32(xs ^ (f32_bits(v) & 0x80000000u));          // v == 0: patched to NaN by the caller
 }
 
+// The two degenerate inputs — a saturated one (u = 0) and an exact zero (NaN on its own edge) — are found with one
+// min / max over the check (3-input FMNMX) and patched on rarely taken branches, instead of a compare + select on
+// every edge: the common path is ex2 -> pair steps -> lg2 and nothing else.  A NaN input needs no help: it makes
+// every u, S, C and output of the check NaN by itself, like the reference's tanh / log / exp chain.
 template <int DCMAX>
 LDPC_HD void cn_spa_sc(const float (&v)[DCMAX], int dc, float (&out)[DCMAX], float sat_llr = kSpaSatLlr)
 {
     float u[DCMAX];
     uint32_t x = 0u;
+    float lo = INFINITY, hi = 0.0f;
 #pragma unroll
     for (int k = 0; k < DCMAX; ++k)
         if (k < dc) {
             const float av = fabsf(v[k]);
-            u[k] = (av > sat_llr) ? 0.0f : spa_ex2(av * -1.44269504088896f);
+            u[k] = spa_ex2(av * -1.44269504088896f);
             x ^= f32_bits(v[k]);
+            lo = fminf(lo, av);
+            hi = fmaxf(hi, av);
         }
+    if (hi > sat_llr) {
+#pragma unroll
+        for (int k = 0; k < DCMAX; ++k)
+            if (k < dc && fabsf(v[k]) > sat_llr) u[k] = 0.0f;
+    }
+    const bool has_zero = !(lo > 0.0f);
     const uint32_t xs = (x & 0x80000000u) | 0x3f317218u;            // +-ln 2
     if (DCMAX >= 6 && dc == 6) {
         // all-but-one sets of {0..5} from the two halves, single-element steps only (14 of them)
@@ -315,6 +327,11 @@ LDPC_HD void cn_spa_sc(const float (&v)[DCMAX], int dc, float (&out)[DCMAX], flo
         out[3] = sc_out<false>(sc_step(L4, u[5]), v[3], xs);
         out[4] = sc_out<false>(sc_step(L3, u[5]), v[4], xs);
         out[5] = sc_out<false>(sc_step(L3, u[4]), v[5], xs);
+        if (has_zero) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                if (v[k] == 0.0f) out[k] = NAN;
+        }
         return;
     }
     // general degree: prefix sets by steps, suffix sets by steps, joined
@@ -333,6 +350,11 @@ LDPC_HD void cn_spa_sc(const float (&v)[DCMAX], int dc, float (&out)[DCMAX], flo
             out[k] = sc_out<true>(sc_join(pre[k], suf), v[k], xs);
             suf = sc_step(suf, u[k]);
         }
+    if (has_zero) {
+#pragma unroll
+        for (int k = 0; k < DCMAX; ++k)
+            if (k < dc && v[k] == 0.0f) out[k] = NAN;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

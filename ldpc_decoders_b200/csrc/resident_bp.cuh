@@ -419,8 +419,7 @@ __global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const R
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float mv = (&mg[k].x)[j];
-                        if (ALGO == ALGO_MSA) sx[j] ^= f32_bits(mv);                   // sign bit == (marg < 0): no NaN, no -0.0
-                        else sx[j] ^= (mv < 0.0f) ? 0x80000000u : 0u;
+                        sx[j] ^= f32_bits(mv);           // sign bit == (marg < 0): marg is never -0.0, and a NaN is the FADD's +NaN
                         (&mg[k].x)[j] = (UDC || k < dc) ? __fsub_rn(mv, (&ov.x)[j]) : INFINITY;
                     }
                 }
@@ -485,7 +484,7 @@ __global__ void __launch_bounds__(res_max_threads(Q), 3 - Q) resident_bp(const R
                     for (int k = 0; k < DVP; ++k) s = __fadd_rn(s, (&c[k].x)[j]);      // padding edges add +0.0: exact
                     const float mj = __fadd_rn((&pr.x)[j], s);                         // bpa.py:35
                     (&mgv.x)[j] = mj;
-                    hb4 |= (mj < 0.0f ? 1u : 0u) << j;
+                    hb4 |= (f32_bits(mj) >> 31) << j;                                  // == (mj < 0), see the CN phase
                 }
                 hbits = (hbits & ~(0xFu << (4 * ps))) | (hb4 << (4 * ps));
                 marg[item] = mgv;

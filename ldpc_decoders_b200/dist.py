@@ -11,6 +11,45 @@ import os
 import numpy as np
 
 
+def quiet_nccl_stdout():
+    """NCCL writes its version banner (NCCL_DEBUG >= VERSION) and warnings to stdout; route them to stderr so that
+    stdout carries results only (bench.py prints exactly one JSON line).  An explicit NCCL_DEBUG_FILE wins."""
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+def bind_near_gpu(index):
+    """Restrict this process to the CPUs local to CUDA device `index` (sysfs `local_cpulist` of its PCI function), so
+    that the pinned host buffers it allocates afterwards, and the thread that feeds the copy engines, sit on the
+    GPU's own NUMA node — with one process per GPU the host side of decode_host otherwise crosses the socket link.
+    Returns the CPU set applied, or None when the topology is not visible (containers) or LDPC_NUMA_BIND=0."""
+    if os.environ.get("LDPC_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as fp:
+            cpus = parse_cpulist(fp.read())
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> {0,1,2,3,8,10,11} (the kernel's cpulist format)."""
+    out = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        out.update(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
 class Comm:
     """Thin wrapper over torch.distributed that also works as a 1-rank no-op."""
 
@@ -27,7 +66,9 @@ class Comm:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
             if not dist.is_initialized():
                 if backend == "nccl":
+                    quiet_nccl_stdout()
                     torch.cuda.set_device(self.local_rank)
+                    bind_near_gpu(self.local_rank)
                     dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
                 else:
                     dist.init_process_group(backend)

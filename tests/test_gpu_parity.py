@@ -358,6 +358,33 @@ def test_resident_and_streaming_paths_agree(mods, code):
     assert bool((a["iters"] == b["iters"]).all()) and bool((a["reason"] == b["reason"]).all()) and bool((a["x_hat"] == b["x_hat"]).all())
 
 
+@pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_3", "12_3_4_ldpc"])
+def test_spa_degenerate_messages_agree_between_paths(mods, code):
+    """Saturation (|v2c| beyond the float64 tanh saturation point -> +-inf -> the NaN flood of bpa.py:37), exact
+    zeros (0/0 = NaN on the edge's own output) and NaN priors take the rarely executed fix-up branches of cn_spa_sc;
+    the on-chip kernel additionally reads hard decisions off sign bits.  Both paths must still agree bit for bit."""
+    torch, lib = mods["torch"], mods["lib"]
+    tab = tables(mods, code)
+    eng = mods["engine"].engine_for(tab)
+    B = 600
+    Y = G.channel_send("biawgn", 1.0, np.zeros((B, tab.n), np.int64), 4242)
+    pri = O.llr_biawgn(1.0, Y).astype(np.float32)
+    pri[100:300] *= 12.0                                   # confidently wrong bits: saturates within a few iterations
+    pri[300:400, ::7] = 0.0                                # exact zeros -> NaN messages
+    pri[400:420, 3] = np.nan
+    pri[420:440, 5] = -0.0
+    d = torch.from_numpy(pri).cuda()
+    for mi in (10, 40):
+        a = eng.decode_device(lib.SPA, d, max_iter=mi, flags=lib.PATH_STREAMING)
+        a = {k: (v.clone() if v is not None else None) for k, v in a.items()}
+        b = eng.decode_device(lib.SPA, d, max_iter=mi, flags=lib.PATH_RESIDENT)
+        assert bool((a["iters"] == b["iters"]).all()) and bool((a["reason"] == b["reason"]).all())
+        assert bool((a["x_hat"] == b["x_hat"]).all())
+    if tab.n >= 1200:
+        xs = a["x_hat"].cpu().numpy()[100:300]             # a flooded frame (NaN marginals) decodes to the all-zero word
+        assert (xs == 0).all(axis=1).mean() > 0.5 and (a["iters"].cpu().numpy()[100:300] < 10).mean() > 0.5
+
+
 def test_resident_path_is_refused_where_it_cannot_run(mods):
     torch, lib = mods["torch"], mods["lib"]
     from ldpc_decoders_b200 import LdpcError

@@ -144,3 +144,10 @@ def test_named_simulation_cases_match_the_reference():
     gold = [norm(line.split()) for line in open(os.path.join(here, "golden", "simulations_cases.txt")) if line.strip()]
     ours = [norm(c) for name in ("REG_ENS", "IREG_ENS", "REG_BAD", "MAR", "HMG") for c in simulations.all_cases[name]()]
     assert len(gold) == 150 and ours == gold
+
+
+def test_parse_cpulist_and_bind_is_harmless_without_gpu():
+    from ldpc_decoders_b200 import dist as D
+    assert D.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert D.parse_cpulist("") == set()
+    assert D.bind_near_gpu(0) is None or isinstance(D.bind_near_gpu(0), set)     # no CUDA device here: a no-op
