@@ -40,6 +40,10 @@ struct ResidentInfo {                        // position-indexed tables of the o
     uint8_t *cdeg = nullptr, *vdeg = nullptr;
     uint16_t *vposmap = nullptr, *vinvmap = nullptr;
     long plan[7] = {0, 0, 0, 0, 0, 0, 0};    // predicted wavefronts: cn ideal/file/plan-natural/plan, vn ideal/file/plan
+    // variable-plane variant (resident_vp.cuh, regular codes): one placement per edge order, [0] min-sum, [1] natural
+    bool vp = false;
+    uint16_t *vp_cw[2] = {nullptr, nullptr};                    // [mp][8]: (variable position << 4) | (edge rank at the variable + 1)
+    uint16_t *vp_vposmap[2] = {nullptr, nullptr}, *vp_vinvmap[2] = {nullptr, nullptr};
 };
 
 struct ProfEvent {                           // one timed launch (ldpc_profile_*)

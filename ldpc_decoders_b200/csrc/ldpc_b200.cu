@@ -15,6 +15,7 @@
 #include "io_kernels.cuh"
 #include "res_layout.h"
 #include "resident_bp.cuh"
+#include "resident_vp.cuh"
 #include "stream_bec.cuh"
 #include "stream_bp.cuh"
 #include "stream_bp_tma.cuh"
@@ -525,6 +526,25 @@ int launch_resident_t(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid
     return LDPC_OK;
 }
 
+template <int ALGO, int TT>
+int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
+{
+    auto kern = resident_vp<ALGO, 6, 3, TT>;
+    static size_t opted = 0;
+    if (lc.smem > opted) {
+        int rc = opt_in_smem(h, kern, lc.smem);
+        if (rc) return rc;
+        opted = lc.smem;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lc.threads, lc.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int grid = std::max(1, std::min(max_grid, h->sm_count * per_sm));
+    kern<<<grid, lc.threads, lc.smem, s>>>(rp);
+    h->launches++;
+    return LDPC_OK;
+}
+
 // Shared memory one resident CTA may use: two CTAs share an SM (1 KB each is reserved by the system).
 size_t resident_budget(const ldpc_t *h)
 {
@@ -551,6 +571,8 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     rp.n = r.np; rp.m = r.mp; rp.nref = t.n; rp.planes = r.planes;
     rp.cvar = r.cvar[tb]; rp.vrow = r.vrow[tb]; rp.cdeg = r.cdeg; rp.vdeg = r.vdeg;
     rp.vposmap = r.vposmap; rp.vinvmap = r.vinvmap;
+    rp.cw = nullptr;
+    if (r.vp) { rp.cw = r.vp_cw[tb]; rp.vposmap = r.vp_vposmap[tb]; rp.vinvmap = r.vp_vinvmap[tb]; }
     rp.cn_items = r.mp * Q; rp.vn_items = r.np * Q;
     rp.src = in.src;
     rp.y_hard = in.y_hard;
@@ -573,7 +595,7 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     const size_t stride = align_up(row_bytes, 16);
     const size_t budget = resident_budget(h);
     const int vtw = r.regular36 ? 2 : 0;                     // (3,6) variant keeps the variable-edge table in shared memory
-    const size_t state = resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, 0, 0).total;
+    const size_t state = r.vp ? vp_smem_layout(r.np, 3, 0, 0).total : resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, 0, 0).total;
     int ring = 0;
     if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(in.src) & 15u) == 0 && budget > state)
         ring = (int)std::min<size_t>(kResRingMax, (budget - state) / stride);
@@ -581,13 +603,21 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     rp.stage_stride = (int)stride;
     ResLaunch lc;
     lc.threads = r.threads;
-    lc.smem = resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, ring, (int)stride).total;
+    lc.smem = r.vp ? vp_smem_layout(r.np, 3, ring, (int)stride).total
+                   : resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, ring, (int)stride).total;
     const int max_grid = (B + 4 * Q - 1) / (4 * Q);
 
     CUDA_TRY(h, cudaMemsetAsync(rp.counter, 0, sizeof(int), s));
     ProfEvent *pe = prof_begin(h, 0, s);
     int rc;
-    if (r.regular36)
+    if (r.vp) {
+        if (lc.threads == 320)
+            rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vp<ALGO_SPA_PHI, 320>(h, rp, lc, max_grid, s);
+        else
+            rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 0>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vp<ALGO_SPA_PHI, 0>(h, rp, lc, max_grid, s);
+    } else if (r.regular36)
         rc = (algo == LDPC_MSA) ? launch_resident_t<Q, ALGO_MSA, 6, true, 3, true, true, true>(h, rp, lc, max_grid, s)
                                 : launch_resident_t<Q, ALGO_SPA_PHI, 6, true, 3, true, true, true>(h, rp, lc, max_grid, s);
     else
@@ -622,14 +652,47 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
     if (T > maxT) return LDPC_OK;
     r.threads = T; r.Q = Q; r.np = np; r.mp = mp;
 
+    std::vector<int> edge_chk((size_t)t.E);
+    for (int c = 0; c < t.m; ++c)
+        for (int e = chk_ptr[c]; e < chk_ptr[c + 1]; ++e) edge_chk[e] = c;
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = cudaSuccess;
+
+    // ---- variable-plane variant for regular (3,6) codes: its own placement per edge order (res_layout.h, vn_contiguous)
+    const char *lay = getenv("LDPC_RESIDENT_LAYOUT");
+    if (r.regular36 && np % 4 == 0 && np * 16 <= 0xfff0 && !(lay && std::string(lay) == "check") &&
+        vp_smem_layout(np, 3, 0, 0).total <= resident_budget(h)) {
+        std::vector<int> slot((size_t)t.E, 0);
+        for (int v = 0; v < t.n; ++v)
+            for (int p0 = var_ptr[v], k = 0; p0 < var_ptr[v + 1]; ++p0, ++k) slot[var_edges[p0]] = k;
+        for (int tb = 0; tb < 2 && e == cudaSuccess; ++tb) {
+            ResPlanner pl2(t.n, t.m, t.E, chk_ptr, edge_var, var_ptr, var_edges, G);
+            const ResLayout V = pl2.plan(12345u, h->plan_effort, true, tb == 1);
+            std::vector<uint16_t> cw((size_t)mp * 8, 0), vpm((size_t)t.n), vim((size_t)np, 0xffffu);
+            for (int ed = 0; ed < t.E; ++ed)
+                cw[(size_t)V.cpos[edge_chk[ed]] * 8 + V.eord[ed]] = (uint16_t)((V.vpos[edge_var[ed]] << 4) | (slot[ed] + 1));
+            for (int v = 0; v < t.n; ++v) { vpm[v] = (uint16_t)V.vpos[v]; vim[V.vpos[v]] = (uint16_t)v; }
+            if ((e = up((void **)&r.vp_cw[tb], cw.data(), cw.size() * 2)) != cudaSuccess) break;
+            if ((e = up((void **)&r.vp_vposmap[tb], vpm.data(), vpm.size() * 2)) != cudaSuccess) break;
+            if ((e = up((void **)&r.vp_vinvmap[tb], vim.data(), vim.size() * 2)) != cudaSuccess) break;
+            if (tb == 0) { r.plan[0] = V.cn_ideal; r.plan[1] = V.cn_file; r.plan[3] = V.cn_plan; r.plan[4] = V.vn_ideal; r.plan[5] = V.vn_file; r.plan[6] = V.vn_plan; }
+            else r.plan[2] = V.cn_plan;
+        }
+        if (e != cudaSuccess) return fail(nullptr, LDPC_ECUDA, std::string("resident table upload: ") + cudaGetErrorString(e));
+        r.vp = true;
+        r.ok = true;
+        return LDPC_OK;
+    }
+
     ResPlanner planner(t.n, t.m, t.E, chk_ptr, edge_var, var_ptr, var_edges, G);
     const ResLayout L = planner.plan(12345u, h->plan_effort);
     const long pl[7] = {L.cn_ideal, L.cn_file, L.cn_plan_natural, L.cn_plan, L.vn_ideal, L.vn_file, L.vn_plan};
     std::copy(pl, pl + 7, r.plan);
 
-    std::vector<int> edge_chk((size_t)t.E);
-    for (int c = 0; c < t.m; ++c)
-        for (int e = chk_ptr[c]; e < chk_ptr[c + 1]; ++e) edge_chk[e] = c;
     std::vector<uint8_t> cdeg((size_t)mp, 0), vdeg((size_t)np, 0);
     std::vector<uint16_t> vposmap((size_t)t.n), vinvmap((size_t)np, 0xffffu);
     for (int c = 0; c < t.m; ++c) cdeg[L.cpos[c]] = (uint8_t)(chk_ptr[c + 1] - chk_ptr[c]);
@@ -638,12 +701,6 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
         vposmap[v] = (uint16_t)L.vpos[v];
         vinvmap[L.vpos[v]] = (uint16_t)v;
     }
-    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
-        cudaError_t e = cudaMalloc(dst, bytes);
-        if (e != cudaSuccess) return e;
-        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
-    };
-    cudaError_t e = cudaSuccess;
     for (int tb = 0; tb < 2 && e == cudaSuccess; ++tb) {
         const std::vector<uint8_t> &plane = tb == 0 ? L.eord : L.enat;
         std::vector<uint16_t> cvar((size_t)mp * 8, (uint16_t)np), vrow((size_t)np * 8, 0);
@@ -903,6 +960,11 @@ void ldpc_destroy(ldpc_t *h)
     for (int tb = 0; tb < 2; ++tb) {
         if (h->res.cvar[tb]) cudaFree(h->res.cvar[tb]);
         if (h->res.vrow[tb]) cudaFree(h->res.vrow[tb]);
+    }
+    for (int tb = 0; tb < 2; ++tb) {
+        if (h->res.vp_cw[tb]) cudaFree(h->res.vp_cw[tb]);
+        if (h->res.vp_vposmap[tb]) cudaFree(h->res.vp_vposmap[tb]);
+        if (h->res.vp_vinvmap[tb]) cudaFree(h->res.vp_vinvmap[tb]);
     }
     if (h->res.vposmap) cudaFree(h->res.vposmap);
     if (h->res.vinvmap) cudaFree(h->res.vinvmap);

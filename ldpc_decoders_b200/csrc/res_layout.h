@@ -51,8 +51,15 @@ class ResPlanner {
         np_ = (n + G - 1) / G * G;
     }
 
-    ResLayout plan(unsigned seed = 12345u, double effort = 1.0)
+    // vn_contiguous: the variable phase reads contiguous cells whatever the placement (resident_vp.cuh stores a message
+    // where its variable reads it), and the check phase scatters to the bank group it gathered from, so only the check
+    // gathers count; they are annealed on their exact cost in the NATURAL edge order, which serves the order-sensitive
+    // sum-product rule as well as min-sum.
+    // natural_order (with vn_contiguous): the edges of a check keep their np.where order (sum-product); the placement is
+    // then a balanced colouring of the variables, see colour_variables.
+    ResLayout plan(unsigned seed = 12345u, double effort = 1.0, bool vn_contiguous = false, bool natural_order = false)
     {
+        vn_free_ = vn_contiguous;
         ResLayout L;
         L.G = G_; L.mp = mp_; L.np = np_;
         cpos_.resize(m_); vpos_.resize(n_);
@@ -68,11 +75,15 @@ class ResPlanner {
         L.cn_file = L.cn_ideal + cn_extra_exact_all();
         L.vn_file = L.vn_ideal + vn_cost_all();
 
-        anneal(seed, effort);
+        if (vn_free_) colour_variables(seed, effort, natural_order);
+        else anneal(seed, effort);
         L.cn_plan_natural = L.cn_ideal + cn_extra_exact_all();
-        order_edges(seed ^ 0x9e3779b9u, effort);
+        if (!(vn_free_ && natural_order)) {
+            if (vn_free_) match_edges();
+            order_edges(seed ^ 0x9e3779b9u, effort);
+        }
         L.cn_plan = L.cn_ideal + cn_extra_exact_all();
-        L.vn_plan = L.vn_ideal + vn_cost_all();
+        L.vn_plan = L.vn_ideal + (vn_free_ ? 0 : vn_cost_all());
         L.cpos = cpos_; L.vpos = vpos_; L.cinv = cinv_; L.vinv = vinv_; L.eord = eord_;
         return L;
     }
@@ -83,6 +94,7 @@ class ResPlanner {
     std::vector<int> edge_chk_, cpos_, vpos_, cinv_, vinv_;
     std::vector<uint8_t> eord_;
     std::vector<int> vgc_, cgc_;        // cached group costs
+    bool vn_free_ = false;
     uint64_t rng_ = 88172645463325252ull;
 
     uint32_t rnd()
@@ -150,20 +162,23 @@ class ResPlanner {
     // Exact extra wavefronts of one check group for the current edge planes.
     int cn_group_exact(int g) const
     {
-        int cost = 0;
-        for (int k = 0; k < 8; ++k) {
-            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
-            bool any = false;
-            for (int i = 0; i < G_; ++i) {
-                const int c = cinv_[g * G_ + i];
-                if (c < 0) continue;
-                for (int e = chk_ptr_[c]; e < chk_ptr_[c + 1]; ++e)
-                    if (eord_[e] == k) { any = true; mx = std::max(mx, ++cnt[vpos_[edge_var_[e]] % G_]); }
+        uint8_t cnt[8][8] = {};
+        uint8_t mx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < G_; ++i) {
+            const int c = cinv_[g * G_ + i];
+            if (c < 0) continue;
+            for (int e = chk_ptr_[c]; e < chk_ptr_[c + 1]; ++e) {
+                const int k = eord_[e] & 7;
+                const uint8_t v = ++cnt[k][vpos_[edge_var_[e]] % G_];
+                if (v > mx[k]) mx[k] = v;
             }
-            if (any) cost += mx - 1;
         }
+        int cost = 0;
+        for (int k = 0; k < 8; ++k) cost += mx[k] ? mx[k] - 1 : 0;
         return cost;
     }
+    int vn_cost(int g) const { return vn_free_ ? 0 : vn_group_cost(g); }
+    int cn_cost(int g) const { return cn_group_cost(g); }
     long vn_cost_all() const { long s = 0; for (int g = 0; g < np_ / G_; ++g) s += vn_group_cost(g); return s; }
     long cn_extra_exact_all() const { long s = 0; for (int g = 0; g < mp_ / G_; ++g) s += cn_group_exact(g); return s; }
 
@@ -183,8 +198,8 @@ class ResPlanner {
     {
         rng_ ^= (uint64_t)seed * 0x9e3779b97f4a7c15ull;
         vgc_.resize(np_ / G_); cgc_.resize(mp_ / G_);
-        for (int g = 0; g < np_ / G_; ++g) vgc_[g] = vn_group_cost(g);
-        for (int g = 0; g < mp_ / G_; ++g) cgc_[g] = cn_group_cost(g);
+        for (int g = 0; g < np_ / G_; ++g) vgc_[g] = vn_cost(g);
+        for (int g = 0; g < mp_ / G_; ++g) cgc_[g] = cn_cost(g);
         const long moves = (long)(effort * 60.0 * (mp_ + np_)) * 10;
         const double t0 = 0.8, t1 = 0.05;
         std::vector<int> vg, cg, oldv, oldc;
@@ -211,14 +226,80 @@ class ResPlanner {
             swap_pos(move_check, a, b);
             oldv.clear(); oldc.clear();
             int after = 0;
-            for (int g : vg) { oldv.push_back(vgc_[g]); vgc_[g] = vn_group_cost(g); after += vgc_[g]; }
-            for (int g : cg) { oldc.push_back(cgc_[g]); cgc_[g] = cn_group_cost(g); after += cgc_[g]; }
+            for (int g : vg) { oldv.push_back(vgc_[g]); vgc_[g] = vn_cost(g); after += vgc_[g]; }
+            for (int g : cg) { oldc.push_back(cgc_[g]); cgc_[g] = cn_cost(g); after += cgc_[g]; }
             const int d = after - before;
             if (d > 0 && rnd01() >= std::exp(-(double)d / T)) {                         // reject: undo
                 swap_pos(move_check, a, b);
                 for (size_t i = 0; i < vg.size(); ++i) vgc_[vg[i]] = oldv[i];
                 for (size_t i = 0; i < cg.size(); ++i) cgc_[cg[i]] = oldc[i];
             }
+        }
+    }
+    // vn_contiguous placement.  Checks stay in file order (group = 8 consecutive checks); what is left is a balanced
+    // 8-colouring of the variables (colour = position mod 8), found by annealing colour swaps on a squared deviation:
+    //   natural order (sum-product): the variables read in the same step by the checks of a group should all differ
+    //     (every colour once per (group, step): 8-cliques, so 8 colours are the bare minimum and a few conflicts stay);
+    //   free order (min-sum): every colour should occur exactly `degree` times among the variables of a group; the
+    //     edges of each check are then ordered into conflict-free steps by match_edges.
+    void colour_variables(unsigned seed, double effort, bool natural)
+    {
+        rng_ ^= (uint64_t)seed * 0x9e3779b97f4a7c15ull;
+        const int ngroups = mp_ / G_;
+        const int nsets = natural ? ngroups * 8 : ngroups;
+        std::vector<int> cnt((size_t)nsets * 8, 0), target((size_t)nsets, 1);
+        std::vector<std::vector<int>> sets_of((size_t)n_);
+        for (int c = 0; c < m_; ++c)
+            for (int e = chk_ptr_[c]; e < chk_ptr_[c + 1]; ++e)
+                sets_of[edge_var_[e]].push_back(natural ? (c / G_) * 8 + ((e - chk_ptr_[c]) & 7) : c / G_);
+        if (!natural)
+            for (int g = 0; g < ngroups; ++g) {                        // steps of the group = its largest check degree
+                int d = 0;
+                for (int c = g * G_; c < std::min(m_, (g + 1) * G_); ++c) d = std::max(d, chk_ptr_[c + 1] - chk_ptr_[c]);
+                target[g] = d;
+            }
+        std::vector<int> col((size_t)n_);
+        for (int v = 0; v < n_; ++v) col[v] = v % G_;                  // balanced to start with, and swaps keep it so
+        auto sq = [](long x) { return x * x; };
+        auto add = [&](int v, int a) { long d = 0; for (int st : sets_of[v]) { int &x = cnt[(size_t)st * 8 + a]; d += sq(x + 1 - target[st]) - sq(x - target[st]); ++x; } return d; };
+        auto del = [&](int v, int a) { long d = 0; for (int st : sets_of[v]) { int &x = cnt[(size_t)st * 8 + a]; d += sq(x - 1 - target[st]) - sq(x - target[st]); --x; } return d; };
+        for (int v = 0; v < n_; ++v) add(v, col[v]);
+        auto excess = [&]() { long t = 0; for (int st = 0; st < nsets; ++st) for (int a = 0; a < 8; ++a) t += std::max(0, cnt[(size_t)st * 8 + a] - target[st]); return t; };
+        std::vector<std::vector<int>> members((size_t)nsets);
+        for (int v = 0; v < n_; ++v)
+            for (int st : sets_of[v]) members[st].push_back(v);
+        // Annealing with targeted proposals: take a set that violates its target, a member v of an over-represented
+        // colour a, an under-represented colour b of the same set, and any variable w of colour b; swap their colours.
+        const long moves = (long)(effort * 6000.0 * n_) + 1;
+        const double t0 = 0.6, t1 = 0.08;
+        for (long it = 0; it < moves; ++it) {
+            if ((it & 1023) == 0 && excess() == 0) break;
+            const double T = t0 * std::pow(t1 / t0, (double)it / (double)moves);
+            const int st = (int)(rnd() % (unsigned)nsets);
+            int over[8], under[8], no = 0, nu = 0;
+            for (int c = 0; c < 8; ++c) {
+                if (cnt[(size_t)st * 8 + c] > target[st]) over[no++] = c;
+                if (cnt[(size_t)st * 8 + c] < target[st]) under[nu++] = c;
+            }
+            if (no == 0 || nu == 0 || members[st].empty()) continue;
+            const int a = over[rnd() % (unsigned)no], b = under[rnd() % (unsigned)nu];
+            int v = -1, w = -1;
+            for (int t = 0; t < 64 && v < 0; ++t) { const int x = members[st][rnd() % members[st].size()]; if (col[x] == a) v = x; }
+            for (int t = 0; t < 256 && w < 0; ++t) { const int x = (int)(rnd() % (unsigned)n_); if (col[x] == b) w = x; }
+            if (v < 0 || w < 0) continue;
+            const long d = del(v, a) + del(w, b) + add(v, b) + add(w, a);
+            if (d > 0 && rnd01() >= std::exp(-(double)d / T)) {        // reject: undo
+                del(v, b); del(w, a); add(v, a); add(w, b);
+            } else {
+                col[v] = b; col[w] = a;
+            }
+        }
+        // positions: the i-th variable of colour a sits at 8 * i + a (the np_ - n_ < 8 holes end up at the top)
+        std::vector<int> next((size_t)G_, 0);
+        std::fill(vinv_.begin(), vinv_.end(), -1);
+        for (int v = 0; v < n_; ++v) {
+            const int pos = next[col[v]]++ * G_ + col[v];
+            vpos_[v] = pos; vinv_[pos] = v;
         }
     }
     void swap_pos(bool check, int a, int b)
@@ -232,6 +313,56 @@ class ResPlanner {
             if (vinv_[a] >= 0) vpos_[vinv_[a]] = a;
             if (vinv_[b] >= 0) vpos_[vinv_[b]] = b;
         }
+    }
+
+    // Per check group: the edges of its checks against the colours of their variables form a bipartite multigraph; when
+    // every colour occurs exactly `steps` times (proxy cost 0) it is regular and splits into `steps` perfect matchings
+    // (Koenig), i.e. into conflict-free steps.  Step by step: a maximum matching of checks to colours over the edges not
+    // yet placed (Kuhn's augmenting paths on an 8 x 8 graph); a check left unmatched takes any of its remaining edges.
+    void match_edges()
+    {
+        for (int g = 0; g < mp_ / G_; ++g) {
+            std::vector<int> rem[8];                                   // unplaced edges per check of the group
+            int steps = 0;
+            for (int i = 0; i < G_; ++i) {
+                const int c = cinv_[g * G_ + i];
+                if (c < 0) continue;
+                for (int e = chk_ptr_[c]; e < chk_ptr_[c + 1]; ++e) rem[i].push_back(e);
+                steps = std::max(steps, chk_ptr_[c + 1] - chk_ptr_[c]);
+            }
+            // checks of lower degree only take part in the first dc steps (their planes are 0..dc-1)
+            for (int k = 0; k < steps; ++k) {
+                int owner[8];                                          // colour -> check index matched to it
+                int pick[8];                                           // check index -> chosen edge
+                std::fill(owner, owner + 8, -1);
+                std::fill(pick, pick + 8, -1);
+                for (int i = 0; i < G_; ++i) {
+                    if (rem[i].empty()) continue;
+                    bool seen[8] = {false, false, false, false, false, false, false, false};
+                    augment(i, rem, owner, pick, seen);
+                }
+                for (int i = 0; i < G_; ++i) {
+                    if (rem[i].empty()) continue;
+                    int e = pick[i];
+                    if (e < 0) e = rem[i].back();
+                    eord_[e] = (uint8_t)k;
+                    rem[i].erase(std::find(rem[i].begin(), rem[i].end(), e));
+                }
+            }
+        }
+    }
+    bool augment(int i, std::vector<int> (&rem)[8], int (&owner)[8], int (&pick)[8], bool (&seen)[8])
+    {
+        for (int e : rem[i]) {
+            const int a = vpos_[edge_var_[e]] % G_;
+            if (seen[a]) continue;
+            seen[a] = true;
+            if (owner[a] < 0 || augment(owner[a], rem, owner, pick, seen)) {
+                owner[a] = i; pick[i] = e;
+                return true;
+            }
+        }
+        return false;
     }
 
     // Per check group: permute the planes of each check's edges to make every step's colours distinct.

@@ -53,6 +53,7 @@ struct ResParams {
     const uint8_t *cdeg, *vdeg;        // [m], [n] degrees by position (0 = hole)
     const uint16_t *vposmap;           // [nref] position of variable v
     const uint16_t *vinvmap;           // [n]    variable at a position (0xffff = hole)
+    const uint16_t *cw;                // resident_vp.cuh: [m][8] (variable position << 4) | (edge rank at the variable + 1)
     int cn_items, vn_items;            // m * Q, n * Q
     const void *src;                   // [B][n] received block (or priors)
     int in_mode;                       // IN_COPY / IN_BSC / IN_BIAWGN

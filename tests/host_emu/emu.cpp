@@ -259,29 +259,40 @@ int emu_bec(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int
 //   -0.0 priors folded to +0.0; exit rules per frame as in the kernel's book-keeping.
 // Driven with the placement of res_layout.h, so the permutation tables are exercised on the CPU too.
 // ---------------------------------------------------------------------------------------------------------------
-int emu_resident_msa(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
-                     double effort, int B, const float *priors, const uint8_t *y_hard, int limit,
-                     uint8_t *x_hat, int32_t *iters, uint8_t *decoded)
+// vplane: the variable-plane variant (csrc/resident_vp.cuh): placement with vn_contiguous, messages stored at
+// plane[rank of the edge at its variable][variable position], the sum starts from c0 instead of 0 + c0, and the word
+// is read off the sign bits of marg.
+static int emu_resident_msa_impl(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+                                 double effort, int B, const float *priors, const uint8_t *y_hard, int limit,
+                                 uint8_t *x_hat, int32_t *iters, uint8_t *decoded, bool vplane)
 {
     ResPlanner planner(n, m, E, cp, ev, vp, ve, 8);
-    const ResLayout L = planner.plan(12345u, effort);
+    const ResLayout L = planner.plan(12345u, effort, vplane, false);
+    std::vector<int> slot_of((size_t)E, 0);                                       // rank of an edge among its variable's edges
+    for (int v = 0; v < n; ++v)
+        for (int p0 = vp[v], k = 0; p0 < vp[v + 1]; ++p0, ++k) slot_of[ve[p0]] = k;
+    std::vector<int> cslot((size_t)L.mp * 8, 0);
     std::vector<int> edge_chk((size_t)E);
     for (int c = 0; c < m; ++c)
         for (int e = cp[c]; e < cp[c + 1]; ++e) edge_chk[e] = c;
     // position-indexed tables, exactly what build_resident uploads
     std::vector<int> cvar((size_t)L.mp * 8, -1), vrow((size_t)L.np * 8, -1), cdeg((size_t)L.mp, 0), vdeg((size_t)L.np, 0);
     for (int c = 0; c < m; ++c) cdeg[L.cpos[c]] = cp[c + 1] - cp[c];
-    for (int e = 0; e < E; ++e) cvar[(size_t)L.cpos[edge_chk[e]] * 8 + L.eord[e]] = L.vpos[ev[e]];
+    for (int e = 0; e < E; ++e) {
+        cvar[(size_t)L.cpos[edge_chk[e]] * 8 + L.eord[e]] = L.vpos[ev[e]];
+        cslot[(size_t)L.cpos[edge_chk[e]] * 8 + L.eord[e]] = slot_of[e];
+    }
     for (int v = 0; v < n; ++v) {
         vdeg[L.vpos[v]] = vp[v + 1] - vp[v];
         for (int p0 = vp[v], k = 0; p0 < vp[v + 1]; ++p0, ++k)
             vrow[(size_t)L.vpos[v] * 8 + k] = L.eord[ve[p0]] * L.mp + L.cpos[edge_chk[ve[p0]]];
     }
-    std::vector<float> marg((size_t)L.np), prior((size_t)L.np), c2v((size_t)8 * L.mp);
+    std::vector<float> marg((size_t)L.np), prior((size_t)L.np), c2v((size_t)8 * L.mp), plane((size_t)8 * L.np);
     std::vector<uint8_t> hb((size_t)L.np);
     for (int b = 0; b < B; ++b) {
         std::fill(marg.begin(), marg.end(), 0.f);
         std::fill(c2v.begin(), c2v.end(), 0.f);
+        std::fill(plane.begin(), plane.end(), 0.f);
         for (int v = 0; v < n; ++v) {
             volatile float val = priors[(size_t)b * n + v] + 0.0f;                 // -0.0 -> +0.0
             marg[L.vpos[v]] = prior[L.vpos[v]] = val;
@@ -324,30 +335,70 @@ int emu_resident_msa(int n, int m, int E, const int32_t *cp, const int32_t *ev, 
                 } else {
                     cn_msa_bits<8>(a, dc, o);
                 }
-                for (int k = 0; k < dc; ++k) c2v[(size_t)k * L.mp + c] = o[k];
+                for (int k = 0; k < dc; ++k) {
+                    c2v[(size_t)k * L.mp + c] = o[k];                              // the kernel keeps these in registers
+                    plane[(size_t)cslot[(size_t)c * 8 + k] * L.np + cvar[(size_t)c * 8 + k]] = o[k];
+                }
             }
             if (!fresh && !unsat) { done = true; break; }                          // syndrome of the last hard decisions
             fresh = false;
             ++it;
             for (int p0 = 0; p0 < L.np; ++p0) {
-                float s = 0.0f;
-                for (int k = 0; k < vdeg[p0]; ++k) s = num<float>::add(s, c2v[vrow[(size_t)p0 * 8 + k]]);
-                marg[p0] = num<float>::add(prior[p0], s);
+                if (vplane) {
+                    float s = vdeg[p0] > 0 ? plane[p0] : 0.0f;
+                    for (int k = 1; k < vdeg[p0]; ++k) s = num<float>::add(s, plane[(size_t)k * L.np + p0]);
+                    marg[p0] = num<float>::add(prior[p0], s);
+                } else {
+                    float s = 0.0f;
+                    for (int k = 0; k < vdeg[p0]; ++k) s = num<float>::add(s, c2v[vrow[(size_t)p0 * 8 + k]]);
+                    marg[p0] = num<float>::add(prior[p0], s);
+                }
             }
             if (it >= limit) break;
         }
-        for (int v = 0; v < n; ++v) x_hat[(size_t)b * n + v] = (uint8_t)(marg[L.vpos[v]] < 0.0f);
+        for (int v = 0; v < n; ++v)
+            x_hat[(size_t)b * n + v] = vplane ? (uint8_t)(f32_bits(marg[L.vpos[v]]) >> 31) : (uint8_t)(marg[L.vpos[v]] < 0.0f);
         iters[b] = it; decoded[b] = done ? 1 : 0;
     }
     return 0;
 }
 
+int emu_resident_msa(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+                     double effort, int B, const float *priors, const uint8_t *y_hard, int limit,
+                     uint8_t *x_hat, int32_t *iters, uint8_t *decoded)
+{
+    return emu_resident_msa_impl(n, m, E, cp, ev, vp, ve, effort, B, priors, y_hard, limit, x_hat, iters, decoded, false);
+}
+int emu_resident_vp_msa(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+                        double effort, int B, const float *priors, const uint8_t *y_hard, int limit,
+                        uint8_t *x_hat, int32_t *iters, uint8_t *decoded)
+{
+    return emu_resident_msa_impl(n, m, E, cp, ev, vp, ve, effort, B, priors, y_hard, limit, x_hat, iters, decoded, true);
+}
+
 // Placement statistics and tables of res_layout.h (stats[7] as ldpc_resident_plan).
+static int emu_plan_impl(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+                         int G, double effort, long *stats, int32_t *cpos, int32_t *vpos, uint8_t *eord, int mode);
 int emu_plan(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
              int G, double effort, long *stats, int32_t *cpos, int32_t *vpos, uint8_t *eord)
 {
+    return emu_plan_impl(n, m, E, cp, ev, vp, ve, G, effort, stats, cpos, vpos, eord, 0);
+}
+int emu_plan_vp(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+                int G, double effort, long *stats, int32_t *cpos, int32_t *vpos, uint8_t *eord)
+{
+    return emu_plan_impl(n, m, E, cp, ev, vp, ve, G, effort, stats, cpos, vpos, eord, 1);
+}
+int emu_plan_vp_natural(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+                        int G, double effort, long *stats, int32_t *cpos, int32_t *vpos, uint8_t *eord)
+{
+    return emu_plan_impl(n, m, E, cp, ev, vp, ve, G, effort, stats, cpos, vpos, eord, 2);
+}
+static int emu_plan_impl(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+                         int G, double effort, long *stats, int32_t *cpos, int32_t *vpos, uint8_t *eord, int mode)
+{
     ResPlanner planner(n, m, E, cp, ev, vp, ve, G);
-    const ResLayout L = planner.plan(12345u, effort);
+    const ResLayout L = planner.plan(12345u, effort, mode != 0, mode == 2);
     const long st[9] = {L.cn_ideal, L.cn_file, L.cn_plan_natural, L.cn_plan, L.vn_ideal, L.vn_file, L.vn_plan, L.mp, L.np};
     for (int i = 0; i < 9; ++i) stats[i] = st[i];
     for (int c = 0; c < m; ++c) cpos[c] = L.cpos[c];

@@ -195,7 +195,8 @@ def test_bec_bitplanes_arbitrary_symbols(emu, nb):
                                                    ("bsc", "1200_3_6_rand_ldpc_1", .05, 1),
                                                    ("biawgn", "7_4_hamming", 1.0, 1),
                                                    ("biawgn", "512_3_6_rand_ldpc_1", 2.0, 0)])
-def test_resident_formulation_matches_oracle(emu, channel, code, param, cw):
+@pytest.mark.parametrize("variant", ["check_major", "variable_plane"])
+def test_resident_formulation_matches_oracle(emu, channel, code, param, cw, variant):
     """The on-chip kernel's restructured decode (marginal gathers, v2c = marg - c2v_old never stored, syndrome from the
     sign bits of marg, lean 3-input-min min-sum, -0.0 priors folded, graph positions and per-check edge order from
     res_layout.h) gives the oracle's words, iteration counts and exit reasons bit for bit."""
@@ -216,8 +217,11 @@ def test_resident_formulation_matches_oracle(emu, channel, code, param, cw):
     x_hat = np.zeros((frames, g.n), np.uint8)
     iters = np.zeros(frames, np.int32)
     dec = np.zeros(frames, np.uint8)
-    emu.emu_resident_msa(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(g.var_ptr), ptr(g.var_edges),
-                         ctypes.c_double(0.05), frames, ptr(pri), ptr(yh), 10, ptr(x_hat), ptr(iters), ptr(dec))
+    # variable_plane = csrc/resident_vp.cuh: messages stored by (edge rank at the variable, variable position), the
+    # ordered sum starts from c0 instead of 0 + c0, the word is the sign bits of marg
+    fn = emu.emu_resident_msa if variant == "check_major" else emu.emu_resident_vp_msa
+    fn(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(g.var_ptr), ptr(g.var_edges),
+       ctypes.c_double(0.05), frames, ptr(pri), ptr(yh), 10, ptr(x_hat), ptr(iters), ptr(dec))
     assert (iters == ref["iters"]).all()
     assert (x_hat == ref["x_hat"]).all()
     assert ((dec == 1) == (ref["reason"] == 0)).all()
@@ -245,6 +249,31 @@ def test_shared_memory_placement(emu, code):
     if code == "1200_3_6_rand_ldpc_1":
         assert cn_file > 2.3 * cn_ideal and vn_file > 2.3 * vn_ideal        # file order: random gathers
         assert cn_plan < 1.35 * cn_ideal and vn_plan < 2.0 * vn_ideal
+
+
+@pytest.mark.parametrize("natural", [False, True])
+def test_shared_memory_placement_variable_plane(emu, natural):
+    """res_layout.h with vn_contiguous (resident_vp.cuh): the variable phase is contiguous whatever the placement, only
+    the check gathers (and the scatters, same bank groups) count.  Min-sum may order the edges of a check: the balanced
+    colouring + matching decomposition is conflict-free or within a few wavefronts of it.  Sum-product keeps the natural
+    order (8-cliques against 8 colours): well below file order, not ideal."""
+    g = graph("1200_3_6_rand_ldpc_1")
+    stats = (ctypes.c_long * 9)()
+    cpos, vpos, eord = np.zeros(g.m, np.int32), np.zeros(g.n, np.int32), np.zeros(g.E, np.uint8)
+    fn = emu.emu_plan_vp_natural if natural else emu.emu_plan_vp
+    fn(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(g.var_ptr), ptr(g.var_edges), 8,
+       ctypes.c_double(0.4), stats, ptr(cpos), ptr(vpos), ptr(eord))
+    cn_ideal, cn_file, cn_nat, cn_plan, vn_ideal, vn_file, vn_plan, mp, npos = list(stats)
+    assert sorted(cpos.tolist()) == list(range(g.m)) and sorted(vpos.tolist()) == list(range(g.n))
+    for c in range(g.m):
+        e0, e1 = g.chk_ptr[c], g.chk_ptr[c + 1]
+        assert sorted(eord[e0:e1].tolist()) == list(range(e1 - e0))
+    assert vn_plan == vn_ideal and cn_ideal <= cn_plan <= cn_nat <= cn_file
+    if natural:
+        assert (eord == np.concatenate([np.arange(g.chk_ptr[c + 1] - g.chk_ptr[c]) for c in range(g.m)])).all()
+        assert cn_plan == cn_nat < 0.6 * cn_file
+    else:
+        assert cn_plan <= 1.03 * cn_ideal
 
 
 def test_biawgn_llr_without_division_is_exact(emu):
