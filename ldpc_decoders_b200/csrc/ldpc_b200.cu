@@ -526,10 +526,10 @@ int launch_resident_t(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid
     return LDPC_OK;
 }
 
-template <int ALGO, int TT>
+template <int ALGO, int TT, int NPC>
 int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
-    auto kern = resident_vp<ALGO, 6, 3, TT>;
+    auto kern = resident_vp<ALGO, 6, 3, TT, NPC>;
     static size_t opted = 0;
     if (lc.smem > opted) {
         int rc = opt_in_smem(h, kern, lc.smem);
@@ -611,12 +611,15 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     ProfEvent *pe = prof_begin(h, 0, s);
     int rc;
     if (r.vp) {
-        if (lc.threads == 320)
-            rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320>(h, rp, lc, max_grid, s)
-                                    : launch_resident_vp<ALGO_SPA_PHI, 320>(h, rp, lc, max_grid, s);
+        if (lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200)      // the reference's (1200,3,6) ensemble
+            rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320, 1200>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vp<ALGO_SPA_PHI, 320, 1200>(h, rp, lc, max_grid, s);
+        else if (lc.threads == 320)
+            rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320, 0>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vp<ALGO_SPA_PHI, 320, 0>(h, rp, lc, max_grid, s);
         else
-            rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 0>(h, rp, lc, max_grid, s)
-                                    : launch_resident_vp<ALGO_SPA_PHI, 0>(h, rp, lc, max_grid, s);
+            rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 0, 0>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vp<ALGO_SPA_PHI, 0, 0>(h, rp, lc, max_grid, s);
     } else if (r.regular36)
         rc = (algo == LDPC_MSA) ? launch_resident_t<Q, ALGO_MSA, 6, true, 3, true, true, true>(h, rp, lc, max_grid, s)
                                 : launch_resident_t<Q, ALGO_SPA_PHI, 6, true, 3, true, true, true>(h, rp, lc, max_grid, s);

@@ -113,14 +113,17 @@ __device__ __forceinline__ void vp_load4(const unsigned char *row, int i4, int i
 // ALGO: ALGO_MSA / ALGO_SPA_PHI.  DC: degree of every check.  DV: degree of every variable (<= 3: two slot bits).
 // TT: threads per CTA when known at compile time (0 = blockDim.x).  np and mp are multiples of 8 without holes,
 // mp <= 2 * T, np <= 4 * T, np % 4 == 0.
-template <int ALGO, int DC, int DV, int TT>
+// NPC: number of variable positions when known at compile time (0 = p.n); the shipped ensemble is n = 1200, and with
+// np, mp and T constant every shared-memory address of the variable phase is base + immediate and the pass bounds
+// fold away.
+template <int ALGO, int DC, int DV, int TT, int NPC>
 __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
 {
     static_assert(DV >= 1 && DV <= 3 && DC >= 2 && DC <= 8, "slot field is two bits; index words hold two edges");
     constexpr int F = 4, CH = (DC + 1) / 2;
     constexpr uint32_t ALL = 0xFu;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int np = p.n, mp = p.m;
+    const int np = NPC ? NPC : p.n, mp = NPC ? NPC * DV / DC : p.m;
     const uint32_t S = (uint32_t)np * 16u;                            // bytes per plane
     const VpSmem L = vp_smem_layout(np, DV, p.ring, p.stage_stride);
     float4 *marg = reinterpret_cast<float4 *>(smem + L.marg);
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
     const int tid = threadIdx.x, T = TT ? TT : (int)blockDim.x, lane = tid & 31;
     const bool async = p.ring > 0;
     const bool have_hard = (p.in_mode == IN_BSC) || (p.in_mode == IN_COPY && p.y_hard != nullptr);
-    const int nref = p.nref;                                         // == np
+    const int nref = NPC ? NPC : p.nref;                             // == np
     const size_t row_bytes = (size_t)nref * p.in_es;
     const bool src_vec = ((reinterpret_cast<uintptr_t>(p.src) | row_bytes) & 15u) == 0;
     const double nscale = -2.0 * p.inv_param;

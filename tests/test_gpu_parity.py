@@ -452,3 +452,66 @@ def test_bec_round_trip_property(mods):
     assert ((x_hat == 2).sum(axis=1)[reason == 0] == 0).all()
     assert ((x_hat == 2).sum(axis=1)[reason == 2] > 0).all()
     assert (reason == 0).mean() > 0.8
+
+
+# --------------------------------------------------------------------------------------------- config 5: n = 64800
+_long = {}
+
+
+def long_code(mods):
+    """The synthetic (3,6) code of BASELINE.json config 5 (seeded configuration model, O(E))."""
+    if "code" not in _long:
+        from ldpc_decoders_b200 import codes
+        _long["code"] = codes.random_regular(64800, 3, 6, seed=0)
+    return _long["code"]
+
+
+@pytest.mark.parametrize("snr,dt", [(1.0, np.float32), (2.5, np.float32), (2.5, np.float64)])
+def test_long_code_msa_bit_exact(mods, snr, dt):
+    """n = 64800 (streaming path, 194400 edges): words, iteration counts and exit reasons of min-sum are
+    bit-identical with the oracle at the same dtype; 1.0 dB never converges (fixed work), 2.5 dB exits early."""
+    tab = long_code(mods).tables
+    assert (tab.n, tab.m, tab.E) == (64800, 32400, 194400)
+    og = O.Graph(tab.m, tab.n, tab.edge_chk, tab.edge_var)
+    B = 24
+    rng = np.random.RandomState(64800)
+    Y = 1.0 + np.sqrt(O.noise_var(snr)) * rng.standard_normal((B, tab.n))
+    dec = mods["biawgn"].MSA(snr, tab, max_iter=10, dtype=dt)
+    x_hat, iters = dec.decode_batch(Y)
+    ref = O.bp_decode(og, O.MSA, O.llr_biawgn(snr, Y).astype(dt), max_iter=10, nthreads=8)
+    assert (iters == ref["iters"]).all()
+    assert (x_hat == ref["x_hat"]).all()
+    if snr == 1.0:
+        assert (iters == 10).all()
+    else:
+        assert iters.min() < 10 and (x_hat == 1).all()
+
+
+def test_long_code_full_batch_properties(mods):
+    """BASELINE-size batch of the long code (2048 frames, 1.6 GB of messages): sign symmetry (all-ones is a
+    codeword of a code with even check degree), every frame reported decoded satisfies every check, and the
+    result does not depend on where in the batch a frame sits."""
+    torch, lib = mods["torch"], mods["lib"]
+    tab = long_code(mods).tables
+    eng = mods["engine"].engine_for(tab)
+    B = 2048
+    g = torch.Generator(device="cuda").manual_seed(5)
+    nv = 10 ** (-2.5 / 10)
+    y = 1.0 + nv ** .5 * torch.randn((B, tab.n), generator=g, device="cuda", dtype=torch.float32)
+    pri = eng.llr_biawgn(nv, y, lib.F32)
+    a = eng.decode_device(lib.MSA, pri, max_iter=10)
+    xa, ia, ra = a["x_hat"].clone(), a["iters"].clone(), a["reason"].clone()
+    b = eng.decode_device(lib.MSA, -pri, max_iter=10)
+    assert bool((ia == b["iters"]).all()) and bool(((xa ^ 1) == b["x_hat"]).all())
+    # syndrome of every word through the edge list (no dense H at this length)
+    rows = torch.from_numpy(np.asarray(tab.edge_chk, np.int64)).cuda()
+    cols = torch.from_numpy(np.asarray(tab.edge_var, np.int64)).cuda()
+    syn = torch.zeros((B, tab.m), dtype=torch.int32, device="cuda")
+    syn.index_add_(1, rows, xa[:, cols].to(torch.int32))
+    ok = ((syn & 1) == 0).all(dim=1)
+    assert bool(ok[ra == 0].all())
+    assert bool((ia[ra == 1] == 10).all()) and bool((ia[ra == 0] < 10).any())
+    # a permuted batch decodes to the permuted result
+    perm = torch.randperm(B, generator=torch.Generator(device="cuda").manual_seed(6), device="cuda")
+    c = eng.decode_device(lib.MSA, pri[perm].contiguous(), max_iter=10)
+    assert bool((c["iters"] == ia[perm]).all()) and bool((c["x_hat"] == xa[perm]).all())
