@@ -1,0 +1,14 @@
+# Event-timed throughput of the named decoder configurations on one B200 (run under gpurun): quick A/B aid.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+{
+python scripts/run_case.py --algo MSA --steps 10
+python scripts/run_case.py --algo SPA --cw 0 --steps 10
+python scripts/run_case.py --code 1200_rho_x5_rand_ldpc_1 --channel bsc --snr 0.06 --algo SPA --cw 0 --max-iter 10
+python scripts/run_case.py --code 1200_rho_x5_rand_ldpc_1 --channel bsc --snr 0.06 --algo SPA --cw 0 --max-iter 100
+python scripts/run_case.py --code 1200_rho_x5_rand_ldpc_1 --channel biawgn --snr 2.0 --algo MSA --cw 0 --max-iter 10
+python scripts/run_case.py --code 1200_rho_x5_rand_ldpc_1 --channel biawgn --snr 2.0 --algo MSA --cw 0 --max-iter 10 --streaming
+python scripts/run_case.py --code margulis --algo MSA --snr 2.0 --cw 0 --frames 16384
+python scripts/run_case.py --n 64800 --algo MSA --snr 2.5 --frames 2048
+} 2>&1 | tee gpurun_out/cases.txt
