@@ -400,8 +400,8 @@ def main():
         sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
         smem_bytes = (3 * tab.E + 2 * tab.n) * 4
         return {
-            "bound": "hbm", "kernel": "resident_bp", "achieved": eff, "peak": peak, "unit": "GB/s", "frac": eff / peak,
-            "peak_source": peak_src, "traffic": traffic_per_launch("resident_bp"),
+            "bound": "hbm", "kernel": eng.resident_kernel, "achieved": eff, "peak": peak, "unit": "GB/s", "frac": eff / peak,
+            "peak_source": peak_src, "traffic": traffic_per_launch(eng.resident_kernel),
             "note": "EFFECTIVE GB/s: algorithmic bytes of the streaming layout (SURVEY 8d, 63 000 B per frame-iteration) / "
                     "kernel time.  frac > 1 is by design, not skipped work: the kernel keeps every frame in shared memory "
                     "and registers for all its iterations, so DRAM only sees `traffic` (= compulsory_hbm_bytes_per_launch). "
@@ -418,7 +418,7 @@ def main():
 
     streaming = None
     if resident:
-        roofline = resident_roofline(main, "It is bound by the shared-memory pipe (65 %) and instruction issue (55 %), profiles/README.md.")
+        roofline = resident_roofline(main, "It is latency-limited between the shared-memory pipe (64 % of peak wavefronts), instruction issue (50 %) and the ALU pipe (44 %), profiles/README.md.")
         roofline["shared_memory_plan"] = eng.resident_plan()
         sm = measure(args.flags | lib.PATH_STREAMING)
         assert (sm["iters"] == iters).all() and bool((sm["x_hat"] == x_hat).all()), "streaming and resident paths disagree"

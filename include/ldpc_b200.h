@@ -203,6 +203,11 @@ int ldpc_resident_frames(const ldpc_t *h);
  * (default 0.4; 0 keeps file order) before ldpc_create. */
 int ldpc_resident_plan(const ldpc_t *h, long *out);
 
+/* Name of the on-chip kernel LDPC_PATH_RESIDENT launches for this code: "resident_vp" (regular codes, variable-plane
+ * message layout, csrc/resident_vp.cuh), "resident_bp" (any degree profile <= 8, csrc/resident_bp.cuh) or "" when the
+ * code has no on-chip path.  The string is static. */
+const char *ldpc_resident_kernel(const ldpc_t *h);
+
 /* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
 unsigned long long ldpc_launch_count(const ldpc_t *h);
 

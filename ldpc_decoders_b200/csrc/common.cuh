@@ -44,6 +44,10 @@ struct ResidentInfo {                        // position-indexed tables of the o
     bool vp = false;
     uint16_t *vp_cw[2] = {nullptr, nullptr};                    // [mp][8]: (variable position << 4) | (edge rank at the variable + 1)
     uint16_t *vp_vposmap[2] = {nullptr, nullptr}, *vp_vinvmap[2] = {nullptr, nullptr};
+    // ... for irregular codes (IRR = true): one word per edge, planes are prefixes of the positions (res_layout.h, VxTables)
+    bool vx = false;
+    uint32_t *vx_cwx[2] = {nullptr, nullptr};
+    int vx_pcnt[2][8] = {}, vx_pbase[2][8] = {}, vx_cells[2] = {0, 0};
 };
 
 struct ProfEvent {                           // one timed launch (ldpc_profile_*)

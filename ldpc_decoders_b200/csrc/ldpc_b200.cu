@@ -526,10 +526,10 @@ int launch_resident_t(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid
     return LDPC_OK;
 }
 
-template <int ALGO, int TT, int NPC>
+template <int ALGO, int TT, int NPC, bool IRR = false>
 int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
-    auto kern = resident_vp<ALGO, 6, 3, TT, NPC>;
+    auto kern = resident_vp<ALGO, 6, IRR ? 8 : 3, TT, NPC, IRR>;
     static size_t opted = 0;
     if (lc.smem > opted) {
         int rc = opt_in_smem(h, kern, lc.smem);
@@ -572,7 +572,15 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     rp.cvar = r.cvar[tb]; rp.vrow = r.vrow[tb]; rp.cdeg = r.cdeg; rp.vdeg = r.vdeg;
     rp.vposmap = r.vposmap; rp.vinvmap = r.vinvmap;
     rp.cw = nullptr;
+    rp.cwx = nullptr;
+    rp.plane_cells = 0;
+    for (int k = 0; k < 8; ++k) { rp.pcnt[k] = 0; rp.pbase[k] = 0; }
     if (r.vp) { rp.cw = r.vp_cw[tb]; rp.vposmap = r.vp_vposmap[tb]; rp.vinvmap = r.vp_vinvmap[tb]; }
+    if (r.vx) {
+        rp.cwx = r.vx_cwx[tb]; rp.vposmap = r.vp_vposmap[tb]; rp.vinvmap = r.vp_vinvmap[tb];
+        rp.plane_cells = r.vx_cells[tb];
+        for (int k = 0; k < 8; ++k) { rp.pcnt[k] = r.vx_pcnt[tb][k]; rp.pbase[k] = r.vx_pbase[tb][k]; }
+    }
     rp.cn_items = r.mp * Q; rp.vn_items = r.np * Q;
     rp.src = in.src;
     rp.y_hard = in.y_hard;
@@ -595,7 +603,8 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     const size_t stride = align_up(row_bytes, 16);
     const size_t budget = resident_budget(h);
     const int vtw = r.regular36 ? 2 : 0;                     // (3,6) variant keeps the variable-edge table in shared memory
-    const size_t state = r.vp ? vp_smem_layout(r.np, 3, 0, 0).total : resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, 0, 0).total;
+    const size_t state = r.vx ? vx_smem_layout(r.np, r.vx_cells[tb], 0, 0).total
+                       : r.vp ? vp_smem_layout(r.np, 3, 0, 0).total : resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, 0, 0).total;
     int ring = 0;
     if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(in.src) & 15u) == 0 && budget > state)
         ring = (int)std::min<size_t>(kResRingMax, (budget - state) / stride);
@@ -603,14 +612,22 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     rp.stage_stride = (int)stride;
     ResLaunch lc;
     lc.threads = r.threads;
-    lc.smem = r.vp ? vp_smem_layout(r.np, 3, ring, (int)stride).total
+    lc.smem = r.vx ? vx_smem_layout(r.np, r.vx_cells[tb], ring, (int)stride).total
+            : r.vp ? vp_smem_layout(r.np, 3, ring, (int)stride).total
                    : resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, ring, (int)stride).total;
     const int max_grid = (B + 4 * Q - 1) / (4 * Q);
 
     CUDA_TRY(h, cudaMemsetAsync(rp.counter, 0, sizeof(int), s));
     ProfEvent *pe = prof_begin(h, 0, s);
     int rc;
-    if (r.vp) {
+    if (r.vx) {
+        if (lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200)      // the reference's irregular n = 1200 ensemble
+            rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320, 1200, true>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vp<ALGO_SPA_PHI, 320, 1200, true>(h, rp, lc, max_grid, s);
+        else
+            rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 0, 0, true>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vp<ALGO_SPA_PHI, 0, 0, true>(h, rp, lc, max_grid, s);
+    } else if (r.vp) {
         if (lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200)      // the reference's (1200,3,6) ensemble
             rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320, 1200>(h, rp, lc, max_grid, s)
                                     : launch_resident_vp<ALGO_SPA_PHI, 320, 1200>(h, rp, lc, max_grid, s);
@@ -689,6 +706,36 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
         r.vp = true;
         r.ok = true;
         return LDPC_OK;
+    }
+
+    // ---- the same layout for irregular codes (resident_vp IRR = true): check degrees 2..6, variable degrees 0..8
+    if (!r.regular36 && t.max_dc <= 6 && t.max_dv <= 8 && !(lay && std::string(lay) == "check")) {
+        bool fits = true;
+        for (int tb = 0; tb < 2 && fits && e == cudaSuccess; ++tb) {
+            ResPlanner pl2(t.n, t.m, t.E, chk_ptr, edge_var, var_ptr, var_edges, G);
+            const ResLayout V = pl2.plan(12345u, h->plan_effort, true, tb == 1);
+            VxTables X;
+            if (!build_vx_tables(V, t.n, t.m, t.E, chk_ptr, edge_var, var_ptr, var_edges, 6, &X) ||
+                vx_smem_layout(np, X.plane_cells, 0, 0).total > resident_budget(h)) { fits = false; break; }
+            if ((e = up((void **)&r.vx_cwx[tb], X.cwx.data(), X.cwx.size() * 4)) != cudaSuccess) break;
+            if ((e = up((void **)&r.vp_vposmap[tb], X.vposmap.data(), X.vposmap.size() * 2)) != cudaSuccess) break;
+            if ((e = up((void **)&r.vp_vinvmap[tb], X.vinvmap.data(), X.vinvmap.size() * 2)) != cudaSuccess) break;
+            r.vx_cells[tb] = X.plane_cells;
+            for (int k = 0; k < 8; ++k) { r.vx_pcnt[tb][k] = X.pcnt[k]; r.vx_pbase[tb][k] = X.pbase[k]; }
+            if (tb == 0) { r.plan[0] = V.cn_ideal; r.plan[1] = V.cn_file; r.plan[3] = V.cn_plan; r.plan[4] = V.vn_ideal; r.plan[5] = V.vn_file; r.plan[6] = V.vn_plan; }
+            else r.plan[2] = V.cn_plan;
+        }
+        if (e != cudaSuccess) return fail(nullptr, LDPC_ECUDA, std::string("resident table upload: ") + cudaGetErrorString(e));
+        if (fits) {
+            r.vx = true;
+            r.ok = true;
+            return LDPC_OK;
+        }
+        for (int tb = 0; tb < 2; ++tb) {                              // does not fit: the check-major kernel below
+            if (r.vx_cwx[tb]) { cudaFree(r.vx_cwx[tb]); r.vx_cwx[tb] = nullptr; }
+            if (r.vp_vposmap[tb]) { cudaFree(r.vp_vposmap[tb]); r.vp_vposmap[tb] = nullptr; }
+            if (r.vp_vinvmap[tb]) { cudaFree(r.vp_vinvmap[tb]); r.vp_vinvmap[tb] = nullptr; }
+        }
     }
 
     ResPlanner planner(t.n, t.m, t.E, chk_ptr, edge_var, var_ptr, var_edges, G);
@@ -824,6 +871,12 @@ const char *ldpc_last_error(const ldpc_t *h) { return h ? h->err.c_str() : g_cre
 unsigned long long ldpc_launch_count(const ldpc_t *h) { return h ? h->launches : 0ull; }
 
 int ldpc_resident_frames(const ldpc_t *h) { return (h && h->res.ok) ? 4 * h->res.Q : 0; }
+
+const char *ldpc_resident_kernel(const ldpc_t *h)
+{
+    if (!h || !h->res.ok) return "";
+    return (h->res.vp || h->res.vx) ? "resident_vp" : "resident_bp";
+}
 
 int ldpc_resident_plan(const ldpc_t *h, long *out)
 {
@@ -966,6 +1019,7 @@ void ldpc_destroy(ldpc_t *h)
     }
     for (int tb = 0; tb < 2; ++tb) {
         if (h->res.vp_cw[tb]) cudaFree(h->res.vp_cw[tb]);
+        if (h->res.vx_cwx[tb]) cudaFree(h->res.vx_cwx[tb]);
         if (h->res.vp_vposmap[tb]) cudaFree(h->res.vp_vposmap[tb]);
         if (h->res.vp_vinvmap[tb]) cudaFree(h->res.vp_vinvmap[tb]);
     }

@@ -38,6 +38,83 @@ struct ResLayout {
     long vn_ideal = 0, vn_file = 0, vn_plan = 0;
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tables of the variable-plane kernel for IRREGULAR codes (resident_vp.cuh, IRR = true), from a vn_contiguous layout.
+// Shared memory, in 16-byte cells: marg [np] + 8 padding cells (+inf) | plane 0 .. plane max_dv-1, plane k = the first
+// pcnt[k] positions | 8 scratch cells | prior ...   (vx_planes_offset is the one definition of where the planes start).
+// ---------------------------------------------------------------------------------------------------------------
+inline int vx_planes_offset(int np) { return (np + 8) * 16; }
+
+struct VxTables {
+    int plane_cells = 0;
+    int pcnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // cells of plane k: 8 * (largest number of variables of one colour with > k edges)
+    int pbase[8] = {0, 0, 0, 0, 0, 0, 0, 0};    // byte offset of plane k from the start of shared memory
+    std::vector<uint32_t> cwx;                  // [mp][8]: (message cell << 16) | (variable position << 4), word 0 also | degree
+    std::vector<uint16_t> vposmap, vinvmap;     // [n] position of a variable, [np] variable at a position (0xffff = hole)
+};
+
+// dc_pad: edges per check in the kernel (every check is padded to it).  Returns false when the code does not fit the
+// 16-bit fields (np <= 4088, cells < 65536) or a degree is out of range (checks 0 or 2..dc_pad, variables <= 8).
+inline bool build_vx_tables(const ResLayout &V, int n, int m, int E, const int32_t *chk_ptr, const int32_t *edge_var,
+                            const int32_t *var_ptr, const int32_t *var_edges, int dc_pad, VxTables *out)
+{
+    const int np = V.np, mp = V.mp, G = 8;
+    if (np > 4088 || dc_pad > 8) return false;
+    VxTables T;
+    int cnt[8][8] = {};                                                 // [k][colour]
+    for (int v = 0; v < n; ++v) {
+        const int d = var_ptr[v + 1] - var_ptr[v];
+        if (d > 8) return false;
+        for (int k = 0; k < d; ++k) cnt[k][V.vpos[v] % G] += 1;
+    }
+    int off = vx_planes_offset(np);
+    for (int k = 0; k < 8; ++k) {
+        int mx = 0;
+        for (int a = 0; a < G; ++a) mx = std::max(mx, cnt[k][a]);
+        T.pcnt[k] = mx * G;
+        T.pbase[k] = off;
+        off += T.pcnt[k] * 16;
+        T.plane_cells += T.pcnt[k];
+    }
+    const int scratch_cell = off / 16;
+    if (scratch_cell + 8 > 65535) return false;
+    std::vector<int> slot((size_t)E, 0);                                // rank of an edge among its variable's edges
+    for (int v = 0; v < n; ++v)
+        for (int p0 = var_ptr[v], k = 0; p0 < var_ptr[v + 1]; ++p0, ++k) slot[var_edges[p0]] = k;
+    T.cwx.assign((size_t)mp * 8, 0u);
+    std::vector<uint8_t> have((size_t)mp * 8, 0);
+    for (int c = 0; c < m; ++c) {
+        const int d = chk_ptr[c + 1] - chk_ptr[c];
+        if (d > dc_pad || d == 1) return false;
+        for (int e = chk_ptr[c]; e < chk_ptr[c + 1]; ++e) {
+            const int vp = V.vpos[edge_var[e]], k = V.eord[e];
+            if (vp >= T.pcnt[slot[e]]) return false;                    // cannot happen: positions are degree-sorted per colour
+            T.cwx[(size_t)V.cpos[c] * 8 + k] = ((uint32_t)(T.pbase[slot[e]] / 16 + vp) << 16) | ((uint32_t)vp << 4);
+            have[(size_t)V.cpos[c] * 8 + k] = 1;
+        }
+        T.cwx[(size_t)V.cpos[c] * 8] |= (uint32_t)d;
+    }
+    // padding edges: per (group of 8 check positions, step) a bank group (colour) no real edge of the step uses
+    for (int g = 0; g < mp / G; ++g)
+        for (int k = 0; k < dc_pad; ++k) {
+            bool used[8] = {false, false, false, false, false, false, false, false};
+            for (int i = 0; i < G; ++i)
+                if (have[(size_t)(g * G + i) * 8 + k]) used[(T.cwx[(size_t)(g * G + i) * 8 + k] >> 4) & 7u] = true;
+            for (int i = 0; i < G; ++i) {
+                if (have[(size_t)(g * G + i) * 8 + k]) continue;
+                int a = 0;
+                while (a < 7 && used[a]) ++a;
+                used[a] = true;
+                T.cwx[(size_t)(g * G + i) * 8 + k] |= ((uint32_t)(scratch_cell + a) << 16) | ((uint32_t)(np + a) << 4);
+            }
+        }
+    T.vposmap.resize((size_t)n);
+    T.vinvmap.assign((size_t)np, 0xffffu);
+    for (int v = 0; v < n; ++v) { T.vposmap[v] = (uint16_t)V.vpos[v]; T.vinvmap[V.vpos[v]] = (uint16_t)v; }
+    *out = T;
+    return true;
+}
+
 class ResPlanner {
   public:
     ResPlanner(int n, int m, int E, const int32_t *chk_ptr, const int32_t *edge_var, const int32_t *var_ptr,
@@ -294,10 +371,18 @@ class ResPlanner {
                 col[v] = b; col[w] = a;
             }
         }
-        // positions: the i-th variable of colour a sits at 8 * i + a (the np_ - n_ < 8 holes end up at the top)
+        // positions: the i-th variable of colour a sits at 8 * i + a (the np_ - n_ < 8 holes end up at the top); within
+        // a colour the variables are ordered by DESCENDING degree (stable: a regular code keeps file order), so that
+        // the variables with more than k edges are a prefix of the positions and plane k of resident_vp.cuh (the k-th
+        // message of every variable) is a prefix too — irregular codes then need E + a few cells, not max_dv * n.
+        std::vector<int> order((size_t)n_);
+        for (int v = 0; v < n_; ++v) order[v] = v;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return var_ptr_[a + 1] - var_ptr_[a] > var_ptr_[b + 1] - var_ptr_[b];
+        });
         std::vector<int> next((size_t)G_, 0);
         std::fill(vinv_.begin(), vinv_.end(), -1);
-        for (int v = 0; v < n_; ++v) {
+        for (int v : order) {
             const int pos = next[col[v]]++ * G_ + col[v];
             vpos_[v] = pos; vinv_[pos] = v;
         }

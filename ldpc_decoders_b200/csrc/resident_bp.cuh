@@ -54,6 +54,9 @@ struct ResParams {
     const uint16_t *vposmap;           // [nref] position of variable v
     const uint16_t *vinvmap;           // [n]    variable at a position (0xffff = hole)
     const uint16_t *cw;                // resident_vp.cuh: [m][8] (variable position << 4) | (edge rank at the variable + 1)
+    const uint32_t *cwx;               // resident_vp.cuh, irregular codes: [m][8] (message cell << 16) | (variable position << 4) [| degree, k = 0]
+    int pcnt[8], pbase[8];             // resident_vp.cuh, irregular codes: cells of plane k (a prefix of the positions), its byte offset
+    int plane_cells;                   //   and the cells of all planes together
     int cn_items, vn_items;            // m * Q, n * Q
     const void *src;                   // [B][n] received block (or priors)
     int in_mode;                       // IN_COPY / IN_BSC / IN_BIAWGN

@@ -23,6 +23,17 @@
 //     final marg = prior + s cannot tell -0.0 from +0.0 in s because priors are folded to +0.0 at refill;
 //   * hard decisions are the sign bits of marg (never -0.0, NaN comes out of FADD with a clear sign bit), read back
 //     from shared memory when a frame leaves instead of being tracked every iteration.
+//
+// IRR = true: the same kernel for IRREGULAR codes (check degrees 2..DC, variable degrees 0..8, holes allowed):
+//   * res_layout.h orders the positions of a colour by descending degree, so the variables with more than k edges are
+//     a prefix of the positions and plane k only has pcnt[k] cells (a multiple of 8) at byte offset pbase[k]: the
+//     planes of `1200_rho_x5_*` take E + ~3 % cells instead of 8 n.  Cells of a plane whose variable has fewer edges
+//     are never written and stay +0.0 (s + 0.0 == s up to the sign of zero, which marg = prior + s cannot see);
+//   * one 32-bit index word per edge: (message cell << 16) | (variable position << 4), the check's degree in the low
+//     bits of word 0; a check with fewer than DC edges is padded with edges that read a +inf marginal cell (neutral
+//     for the minimum and for the parity) and write to a scratch cell, each in a bank group its step leaves free;
+//   * sum-product runs cn_spa_sc with the check's real degree (natural edge order), so every message is bit-identical
+//     to the streaming sweeps whatever the degree.
 #pragma once
 #include "resident_bp.cuh"
 
@@ -46,6 +57,22 @@ __host__ __device__ inline VpSmem vp_smem_layout(int np, int dv, int ring, int s
     return L;
 }
 
+// Irregular codes: 8 padding cells (+inf) behind marg, 8 scratch cells behind the planes, one hard bit more per padding cell.
+__host__ __device__ inline VpSmem vx_smem_layout(int np, int plane_cells, int ring, int stage_stride)
+{
+    VpSmem L;
+    size_t o = 0;
+    L.marg = o;   o += ((size_t)np + 8) * 16;                   // == vx_planes_offset(np), res_layout.h
+    L.planes = o; o += ((size_t)plane_cells + 8) * 16;
+    L.prior = o;  o += (size_t)np * 16;
+    L.stage = o;  o += (size_t)ring * stage_stride;
+    L.bars = o;   o += (size_t)kResRingMax * 8;
+    L.hb = o;     o += ((size_t)np + 8 + 15) / 16 * 16;
+    L.imap = o;   o += ((size_t)np * 2 + 15) / 16 * 16;
+    L.total = o + 16;
+    return L;
+}
+
 // Fields of a packed index word (two edges of a check):  [pos1 << 4 : 16][pos0 << 4 | sl1 << 2 | sl0 : 16], sl = slot + 1.
 // volatile on purpose: the decoded offsets are loop-invariant, and hoisting them out of the iteration loop would need
 // a dozen registers the kernel does not have.
@@ -53,6 +80,14 @@ __device__ __forceinline__ uint32_t vp_off0(uint32_t w) { uint32_t r; asm volati
 __device__ __forceinline__ uint32_t vp_off1(uint32_t w) { uint32_t r; asm volatile("shr.u32 %0, %1, 16;" : "=r"(r) : "r"(w)); return r; }
 __device__ __forceinline__ uint32_t vp_sl0(uint32_t w) { uint32_t r; asm volatile("and.b32 %0, %1, 3;" : "=r"(r) : "r"(w)); return r; }
 __device__ __forceinline__ uint32_t vp_sl1x4(uint32_t w) { uint32_t r; asm volatile("and.b32 %0, %1, 12;" : "=r"(r) : "r"(w)); return r; }
+// Irregular codes, one word per edge: byte offset of the variable's marg cell / of the edge's message cell.
+__device__ __forceinline__ uint32_t vx_goff(uint32_t w) { uint32_t r; asm volatile("and.b32 %0, %1, 0xfff0;" : "=r"(r) : "r"(w)); return r; }
+__device__ __forceinline__ uint32_t vx_soff(uint32_t w)
+{
+    uint32_t r;
+    asm volatile("{\n.reg .b32 t;\nshr.u32 t, %1, 12;\nand.b32 %0, t, 0xffff0;\n}" : "=r"(r) : "r"(w));
+    return r;
+}
 
 // Four consecutive received values of a row -> channel LLRs (exactly the reference's float64 expression rounded to
 // float32, see res_llr) and hard input bits.  `vec`: the row is 16-byte aligned (always true for a staged row).
@@ -116,16 +151,17 @@ __device__ __forceinline__ void vp_load4(const unsigned char *row, int i4, int i
 // NPC: number of variable positions when known at compile time (0 = p.n); the shipped ensemble is n = 1200, and with
 // np, mp and T constant every shared-memory address of the variable phase is base + immediate and the pass bounds
 // fold away.
-template <int ALGO, int DC, int DV, int TT, int NPC>
+template <int ALGO, int DC, int DV, int TT, int NPC, bool IRR = false>
 __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
 {
-    static_assert(DV >= 1 && DV <= 3 && DC >= 2 && DC <= 8, "slot field is two bits; index words hold two edges");
-    constexpr int F = 4, CH = (DC + 1) / 2;
+    static_assert(DC >= 2 && DC <= 8 && DV >= 1 && (IRR ? (DV <= 8 && DC <= 6) : DV <= 3),
+                  "regular: slot field is two bits, index words hold two edges; irregular: c2v of two checks in registers");
+    constexpr int F = 4, CH = IRR ? DC : (DC + 1) / 2;
     constexpr uint32_t ALL = 0xFu;
     extern __shared__ __align__(128) unsigned char smem[];
     const int np = NPC ? NPC : p.n, mp = NPC ? NPC * DV / DC : p.m;
     const uint32_t S = (uint32_t)np * 16u;                            // bytes per plane
-    const VpSmem L = vp_smem_layout(np, DV, p.ring, p.stage_stride);
+    const VpSmem L = IRR ? vx_smem_layout(np, p.plane_cells, p.ring, p.stage_stride) : vp_smem_layout(np, DV, p.ring, p.stage_stride);
     float4 *marg = reinterpret_cast<float4 *>(smem + L.marg);
     float4 *planes = reinterpret_cast<float4 *>(smem + L.planes);
     float4 *prior = reinterpret_cast<float4 *>(smem + L.prior);
@@ -141,7 +177,7 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
     const int tid = threadIdx.x, T = TT ? TT : (int)blockDim.x, lane = tid & 31;
     const bool async = p.ring > 0;
     const bool have_hard = (p.in_mode == IN_BSC) || (p.in_mode == IN_COPY && p.y_hard != nullptr);
-    const int nref = NPC ? NPC : p.nref;                             // == np
+    const int nref = NPC ? NPC : p.nref;                             // == np (regular codes)
     const size_t row_bytes = (size_t)nref * p.in_es;
     const bool src_vec = ((reinterpret_cast<uintptr_t>(p.src) | row_bytes) & 15u) == 0;
     const double nscale = -2.0 * p.inv_param;
@@ -154,14 +190,24 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
 #pragma unroll
         for (int h = 0; h < CH; ++h) cw[ps][h] = 0u;
         if (c < mp) {
+            if (IRR) {
 #pragma unroll
-            for (int k = 0; k < DC; ++k) {
-                const uint32_t e = p.cw[(size_t)c * 8 + k];          // (position << 4) | (slot + 1)
-                if (k & 1) cw[ps][k >> 1] |= (e & 0xfff0u) << 16 | (e & 3u) << 2;
-                else cw[ps][k >> 1] |= e & 0xfff3u;
+                for (int k = 0; k < DC; ++k) cw[ps][k] = p.cwx[(size_t)c * 8 + k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < DC; ++k) {
+                    const uint32_t e = p.cw[(size_t)c * 8 + k];      // (position << 4) | (slot + 1)
+                    if (k & 1) cw[ps][k >> 1] |= (e & 0xfff0u) << 16 | (e & 3u) << 2;
+                    else cw[ps][k >> 1] |= e & 0xfff3u;
+                }
             }
         }
     }
+    auto goff = [&](int ps, int k) -> uint32_t {                     // byte offset of the marg cell read in step k
+        if (IRR) return vx_goff(cw[ps][k]);
+        const uint32_t w = cw[ps][k >> 1];
+        return (k & 1) ? vp_off1(w) : vp_off0(w);
+    };
     float4 old[kResCnPasses][DC];                                    // c2v of the thread's own checks
 #pragma unroll
     for (int ps = 0; ps < kResCnPasses; ++ps)
@@ -169,6 +215,14 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
         for (int k = 0; k < DC; ++k) old[ps][k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int i = tid; i < np; i += T) imap[i] = p.vinvmap[i];
+    if (IRR) {
+        // cells nobody writes must read as +0.0 (short planes, holes), the padding cells behind marg as +inf
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f), i4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+        for (int i = tid; i < (int)(L.stage / 16); i += T) reinterpret_cast<float4 *>(smem)[i] = z4;
+        for (int i = tid; i < np + 8; i += T) hb[i] = 0;
+        __syncthreads();
+        if (tid < 8) marg[np + tid] = i4;
+    }
     if (tid == 0) {
         s_unsat[0] = s_unsat[1] = s_maxed[0] = s_maxed[1] = 0u;
         s_unsat0 = 0u;
@@ -206,7 +260,10 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
 #pragma unroll
             for (int ps = 0; ps < kResVnPasses; ++ps) {
                 const int item = tid + ps * T;
-                if (item < np) dst[imap[item]] = (uint8_t)(mj[(size_t)item * 4] >> 31);
+                if (item < np) {
+                    const uint32_t v = imap[item];
+                    if (!IRR || v != 0xffffu) dst[v] = (uint8_t)(mj[(size_t)item * 4] >> 31);
+                }
             }
         }
         if (tid < F && ((mask >> tid) & 1u)) {
@@ -292,6 +349,19 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
                         }
                     }
                 }
+                if (IRR) {                                 // the last n % 4 values of the row
+                    for (int v = (nref & ~3) + tid; v < nref; v += T) {
+                        uint32_t hbit;
+                        const float val = res_llr(row, v, p.in_mode, p.in_es, p.param, p.inv_param, &hbit);
+                        const uint32_t pos = p.vposmap[v];
+                        mcol[(size_t)pos * 4] = val;
+                        pcol[(size_t)pos * 4] = val;
+                        if (have_hard) {
+                            if (hrow != nullptr) hbit = (uint32_t)(hrow[v] != 0);
+                            hb[pos] = (uint8_t)((hb[pos] & ~(1u << s)) | (hbit << s));
+                        }
+                    }
+                }
             }
             // ---- the new frames start from c2v = 0 (one new frame is the common case)
             if ((nm & (nm - 1u)) == 0u) {
@@ -328,10 +398,7 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
                     if (tid + ps * T < mp) {
                         uint32_t syn = 0u;
 #pragma unroll
-                        for (int k = 0; k < DC; ++k) {
-                            const uint32_t w = cw[ps][k >> 1];
-                            syn ^= hb[((k & 1) ? vp_off1(w) : vp_off0(w)) >> 4];
-                        }
+                        for (int k = 0; k < DC; ++k) syn ^= hb[goff(ps, k) >> 4];
                         u0 |= syn & ALL;
                     }
                 }
@@ -343,7 +410,10 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
                     if (!((z >> s) & 1u)) continue;
                     const int g = s_frame[s];
                     uint8_t *dst = p.x_hat + (size_t)g * nref;
-                    for (int i = tid; i < np; i += T) dst[imap[i]] = (uint8_t)((hb[i] >> s) & 1u);
+                    for (int i = tid; i < np; i += T) {
+                        const uint32_t v = imap[i];
+                        if (!IRR || v != 0xffffu) dst[v] = (uint8_t)((hb[i] >> s) & 1u);
+                    }
                     if (tid == 0) {
                         p.iters[g] = 0;
                         if (p.reason != nullptr) p.reason[g] = (uint8_t)LDPC_REASON_DECODED;
@@ -363,10 +433,7 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
             if (tid + ps * T < mp) {
                 float4 mg[DC];
 #pragma unroll
-                for (int k = 0; k < DC; ++k) {
-                    const uint32_t w = cw[ps][k >> 1];
-                    mg[k] = *reinterpret_cast<const float4 *>(smem + ((k & 1) ? vp_off1(w) : vp_off0(w)));
-                }
+                for (int k = 0; k < DC; ++k) mg[k] = *reinterpret_cast<const float4 *>(smem + goff(ps, k));
                 // v2c = marg - c2v_old (bpa.py:37); the sign bits of marg are the current hard decisions (bpa.py:62)
                 uint32_t sx[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -384,16 +451,28 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
                     float a[DC], o[DC];
 #pragma unroll
                     for (int k = 0; k < DC; ++k) a[k] = (&mg[k].x)[j];
-                    if (ALGO == ALGO_MSA) cn_msa_lean<DC>(a, o);
-                    else cn_spa_sc<DC>(a, DC, o, p.sat_llr);
+                    if (ALGO == ALGO_MSA) {
+                        cn_msa_lean<DC>(a, o);                               // padding edges read +inf: neutral
+                    } else if (IRR) {
+#pragma unroll
+                        for (int k = 0; k < DC; ++k) o[k] = 0.f;
+                        cn_spa_sc<DC>(a, (int)(cw[ps][0] & 15u), o, p.sat_llr);
+                    } else {
+                        cn_spa_sc<DC>(a, DC, o, p.sat_llr);
+                    }
 #pragma unroll
                     for (int k = 0; k < DC; ++k) (&old[ps][k].x)[j] = o[k];
                 }
                 // scatter: plane (slot) of the variable's edge, same bank group as the gather of the same step
 #pragma unroll
                 for (int k = 0; k < DC; ++k) {
-                    const uint32_t w = cw[ps][k >> 1];
-                    const uint32_t coff = (k & 1) ? vp_sl1x4(w) * (S >> 2) + vp_off1(w) : vp_sl0(w) * S + vp_off0(w);   // decoded again: registers
+                    uint32_t coff;
+                    if (IRR) {
+                        coff = vx_soff(cw[ps][k]);
+                    } else {
+                        const uint32_t w = cw[ps][k >> 1];
+                        coff = (k & 1) ? vp_sl1x4(w) * (S >> 2) + vp_off1(w) : vp_sl0(w) * S + vp_off0(w);   // decoded again: registers
+                    }
                     *reinterpret_cast<float4 *>(smem + coff) = old[ps][k];
                 }
                 unsat |= syn;
@@ -419,7 +498,22 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
 #pragma unroll
         for (int ps = 0; ps < kResVnPasses; ++ps) {
             const int item = tid + ps * T;
-            if (item < np) {
+            if (IRR) {
+                if (item < np) {
+                    // plane k = a prefix of the positions (descending degree): ascending edge order, bpa.py:35
+                    float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (item < p.pcnt[0]) sm = *reinterpret_cast<const float4 *>(smem + p.pbase[0] + (size_t)item * 16);
+#pragma unroll
+                    for (int k = 1; k < DV; ++k) {
+                        if (item >= p.pcnt[k]) break;
+                        const float4 c = *reinterpret_cast<const float4 *>(smem + p.pbase[k] + (size_t)item * 16);
+                        sm.x = __fadd_rn(sm.x, c.x); sm.y = __fadd_rn(sm.y, c.y);
+                        sm.z = __fadd_rn(sm.z, c.z); sm.w = __fadd_rn(sm.w, c.w);
+                    }
+                    const float4 pr = prior[item];
+                    marg[item] = make_float4(__fadd_rn(pr.x, sm.x), __fadd_rn(pr.y, sm.y), __fadd_rn(pr.z, sm.z), __fadd_rn(pr.w, sm.w));
+                }
+            } else if (item < np) {
                 float4 c[DV];
 #pragma unroll
                 for (int k = 0; k < DV; ++k) c[k] = planes[(size_t)k * np + item];

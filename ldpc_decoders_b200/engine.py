@@ -63,6 +63,11 @@ class Engine:
         """Frames per CTA of the on-chip path for this code; 0 = the code does not fit in shared memory."""
         return int(self.lib.ldpc_resident_frames(self.handle))
 
+    @property
+    def resident_kernel(self):
+        """Name of the on-chip kernel this code runs on ("resident_vp", "resident_bp") or "" (streaming only)."""
+        return self.lib.ldpc_resident_kernel(self.handle).decode()
+
     def resident_plan(self):
         """Predicted shared-memory wavefronts per iteration of the on-chip path (ldpc_resident_plan), or None."""
         out = (ctypes.c_long * 7)()

@@ -376,6 +376,101 @@ int emu_resident_vp_msa(int n, int m, int E, const int32_t *cp, const int32_t *e
     return emu_resident_msa_impl(n, m, E, cp, ev, vp, ve, effort, B, priors, y_hard, limit, x_hat, iters, decoded, true);
 }
 
+// The variable-plane kernel for IRREGULAR codes (resident_vp.cuh, IRR = true), driven by the very tables the library
+// uploads (res_layout.h build_vx_tables): one 32-bit word per edge, planes that are prefixes of the degree-sorted
+// positions, checks padded to 6 edges with +inf reads and scratch writes, lean min-sum on the padded check.
+// One lane of the kernel's float4 cells; returns -1 when the code has no such layout.
+int emu_resident_vx_msa(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
+                        double effort, int B, const float *priors, const uint8_t *y_hard, int limit,
+                        uint8_t *x_hat, int32_t *iters, uint8_t *decoded, int32_t *info)
+{
+    ResPlanner planner(n, m, E, cp, ev, vp, ve, 8);
+    const ResLayout L = planner.plan(12345u, effort, true, false);
+    VxTables X;
+    if (!build_vx_tables(L, n, m, E, cp, ev, vp, ve, 6, &X)) return -1;
+    const int np = L.np, mp = L.mp;
+    const int prior0 = vx_planes_offset(np) / 16 + X.plane_cells + 8;              // prior cells follow the scratch cells
+    if (info) { info[0] = X.plane_cells; for (int k = 0; k < 8; ++k) info[1 + k] = X.pcnt[k]; }
+    // structural checks of the tables: every real edge has its own message cell inside its plane, bank group of the
+    // message cell == bank group of the marginal cell it belongs to, padding edges stay in the padding / scratch cells
+    {
+        std::vector<int> seen((size_t)prior0, 0);
+        for (int c = 0; c < mp; ++c) {
+            const int dc = (int)(X.cwx[(size_t)c * 8] & 15u);
+            for (int k = 0; k < 6; ++k) {
+                const uint32_t w = X.cwx[(size_t)c * 8 + k];
+                const int g = (int)((w & 0xfff0u) >> 4), cell = (int)(w >> 16);
+                if ((g & 7) != (cell & 7)) return -2;
+                if (k < dc) { if (g >= np || cell < vx_planes_offset(np) / 16 || cell >= prior0 - 8 || seen[cell]++) return -3; }
+                else if (g < np || g >= np + 8 || cell < prior0 - 8 || cell >= prior0) return -4;
+            }
+        }
+    }
+    std::vector<float> cell((size_t)prior0 + np, 0.f), old((size_t)mp * 6, 0.f);
+    std::vector<uint8_t> hb((size_t)np + 8, 0);
+    for (int b = 0; b < B; ++b) {
+        std::fill(cell.begin(), cell.end(), 0.f);
+        std::fill(old.begin(), old.end(), 0.f);
+        std::fill(hb.begin(), hb.end(), 0);
+        for (int a = 0; a < 8; ++a) cell[np + a] = INFINITY;
+        for (int v = 0; v < n; ++v) {
+            volatile float val = priors[(size_t)b * n + v] + 0.0f;                 // -0.0 -> +0.0
+            cell[X.vposmap[v]] = cell[prior0 + X.vposmap[v]] = val;
+            hb[X.vposmap[v]] = y_hard ? y_hard[(size_t)b * n + v] : 0;
+        }
+        bool fresh = true, done = false;
+        int it = 0;
+        if (y_hard) {
+            bool unsat = false;
+            for (int c = 0; c < mp && !unsat; ++c) {
+                unsigned s = 0;
+                for (int k = 0; k < 6; ++k) s ^= hb[(X.cwx[(size_t)c * 8 + k] & 0xfff0u) >> 4];
+                unsat = s & 1u;
+            }
+            if (!unsat) {
+                for (int pz = 0; pz < np; ++pz)
+                    if (X.vinvmap[pz] != 0xffffu) x_hat[(size_t)b * n + X.vinvmap[pz]] = hb[pz];
+                iters[b] = 0; decoded[b] = 1;
+                continue;
+            }
+        }
+        for (;;) {
+            bool unsat = false;
+            for (int c = 0; c < mp; ++c) {
+                float a[6], o[6];
+                uint32_t sx = 0u;
+                for (int k = 0; k < 6; ++k) {
+                    const float mv = cell[(X.cwx[(size_t)c * 8 + k] & 0xfff0u) >> 4];
+                    sx ^= f32_bits(mv);
+                    a[k] = num<float>::sub(mv, old[(size_t)c * 6 + k]);
+                }
+                unsat |= (sx >> 31) != 0u;
+                cn_msa_lean<6>(a, o);
+                for (int k = 0; k < 6; ++k) {
+                    old[(size_t)c * 6 + k] = o[k];
+                    cell[X.cwx[(size_t)c * 8 + k] >> 16] = o[k];
+                }
+            }
+            if (!fresh && !unsat) { done = true; break; }
+            fresh = false;
+            ++it;
+            for (int pz = 0; pz < np; ++pz) {
+                float s = pz < X.pcnt[0] ? cell[X.pbase[0] / 16 + pz] : 0.0f;
+                for (int k = 1; k < 8; ++k) {
+                    if (pz >= X.pcnt[k]) break;
+                    s = num<float>::add(s, cell[X.pbase[k] / 16 + pz]);
+                }
+                cell[pz] = num<float>::add(cell[prior0 + pz], s);
+            }
+            if (it >= limit) break;
+        }
+        for (int pz = 0; pz < np; ++pz)
+            if (X.vinvmap[pz] != 0xffffu) x_hat[(size_t)b * n + X.vinvmap[pz]] = (uint8_t)(f32_bits(cell[pz]) >> 31);
+        iters[b] = it; decoded[b] = done ? 1 : 0;
+    }
+    return 0;
+}
+
 // Placement statistics and tables of res_layout.h (stats[7] as ldpc_resident_plan).
 static int emu_plan_impl(int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
                          int G, double effort, long *stats, int32_t *cpos, int32_t *vpos, uint8_t *eord, int mode);

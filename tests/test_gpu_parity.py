@@ -170,6 +170,54 @@ def test_bec_arbitrary_symbols(mods):
             assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all()
 
 
+def _code_names():
+    import os
+    z = np.load(os.path.join(G.GOLD, "codes.npz"))
+    return sorted({k.rsplit("__", 1)[0] for k in z.files})
+
+
+@pytest.mark.parametrize("code", _code_names())
+def test_every_shipped_code_bit_exact(mods, code):
+    """All 31 code files of data/codes (regular ensemble, irregular ensemble, n = 512, Margulis, toy codes): every code
+    gets its own shared-memory placement (res_layout.h) and its own kernel instance, so each one is held to the oracle —
+    min-sum float32 on BIAWGN and on BSC (hard input: iteration-0 exit), erasure decoding on BEC."""
+    frames = 384
+    tab, og = tables(mods, code), ograph(code)
+    zeros = np.zeros((frames, tab.n), np.int64)
+    small = tab.n < 100
+    snr, p, pe = (1.0, .08, .3) if small else (2.0, .04, .4)
+    Y = G.channel_send("biawgn", snr, zeros, 2024)
+    ref = O.bp_decode(og, O.MSA, O.llr_biawgn(snr, Y).astype(np.float32), max_iter=10, nthreads=8)
+    x_hat, iters, reason = mods["biawgn"].MSA(snr, tab, max_iter=10, dtype=np.float32).decode_batch(Y, return_reason=True)
+    assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all()
+    Yh = G.channel_send("bsc", p, zeros, 2025).astype(np.uint8)
+    ref = O.bp_decode(og, O.MSA, O.llr_bsc(p, Yh).astype(np.float32), y_hard=Yh, max_iter=10, nthreads=8)
+    x_hat, iters, reason = mods["bsc"].MSA(p, tab, max_iter=10, dtype=np.float32).decode_batch(Yh, return_reason=True)
+    assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all()
+    Ye = G.channel_send("bec", pe, zeros, 2026).astype(np.uint8)
+    ref = O.bec_decode(og, Ye, max_iter=100, nthreads=8)
+    x_hat, iters, reason = mods["bec"].SPA(pe, tab, max_iter=100).decode_batch(Ye, return_reason=True)
+    assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all()
+
+
+@pytest.mark.parametrize("mi", [1, 2, 3, 6, 10, 40, 100])
+def test_max_iter_sweep_irregular_bsc(mods, mi):
+    """BASELINE config 4 (src/simulations.py:77, IREG_ENS max_iter sweep on BSC): min-sum float32 bit-exact, float64
+    sum-product identical words / iteration counts on frames whose reference marginals stay finite."""
+    code, p, frames = "1200_rho_x5_rand_ldpc_4", .07, 512
+    tab, og = tables(mods, code), ograph(code)
+    Yh = G.channel_send("bsc", p, np.zeros((frames, tab.n), np.int64), 77 + mi).astype(np.uint8)
+    pri = O.llr_bsc(p, Yh)
+    ref = O.bp_decode(og, O.MSA, pri.astype(np.float32), y_hard=Yh, max_iter=mi, nthreads=8)
+    x_hat, iters, reason = mods["bsc"].MSA(p, tab, max_iter=mi, dtype=np.float32).decode_batch(Yh, return_reason=True)
+    assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all()
+    ref = O.bp_decode(og, O.SPA, pri, y_hard=Yh, max_iter=mi, want_marg=True, nthreads=8)
+    x_hat, iters = mods["bsc"].SPA(p, tab, max_iter=mi, dtype=np.float64).decode_batch(Yh)
+    fin = np.isfinite(ref["marg"]).all(axis=1)
+    assert fin.sum() > frames // 2
+    assert (iters[fin] == ref["iters"][fin]).all() and (x_hat[fin] == ref["x_hat"][fin]).all()
+
+
 # --------------------------------------------------------------------------------------------- SPA
 @pytest.mark.parametrize("case", G.spa_tf(), ids=lambda c: c[0]["slot"])
 def test_spa_teacher_forced(mods, case):

@@ -229,6 +229,40 @@ def test_resident_formulation_matches_oracle(emu, channel, code, param, cw, vari
         assert iters[0] == 0
 
 
+@pytest.mark.parametrize("channel,code,param", [("bsc", "1200_rho_x5_rand_ldpc_10", .045), ("biawgn", "1200_rho_x5_rand_ldpc_7", 2.0),
+                                                ("biawgn", "7_4_hamming", 1.0), ("bsc", "12_3_4_ldpc", .08),
+                                                ("biawgn", "4_2_test", 1.0), ("biawgn", "6_2_3_ldpc", 1.0),
+                                                ("biawgn", "1200_3_6_rand_ldpc_2", 2.0)])
+def test_irregular_variable_plane_tables_match_oracle(emu, channel, code, param):
+    """resident_vp.cuh with IRR = true, on the tables build_vx_tables hands the kernel: degree-sorted positions, planes
+    that are prefixes, checks padded to six edges (+inf reads, scratch writes), lean min-sum on the padded check.
+    Words, iteration counts and exit reasons are the oracle's, bit for bit; the planes take E cells plus a few."""
+    g = graph(code)
+    frames = 300
+    Y = G.channel_send(channel, param, np.zeros((frames, g.n), np.int64), 2027)
+    if channel == "bsc":
+        yh = np.ascontiguousarray(Y, np.uint8)
+        pri = O.llr_bsc(param, yh).astype(np.float32)
+        yh[0] = 0                                    # a clean word: iteration-0 exit
+        pri[0] = O.llr_bsc(param, yh[:1]).astype(np.float32)[0]
+    else:
+        yh = None
+        pri = O.llr_biawgn(param, Y).astype(np.float32)
+        pri[1, :4] = [0.0, -0.0, 0.0, 1.0]
+    ref = O.bp_decode(g, O.MSA, pri, y_hard=yh, max_iter=10, nthreads=4)
+    x_hat = np.zeros((frames, g.n), np.uint8)
+    iters = np.zeros(frames, np.int32)
+    dec = np.zeros(frames, np.uint8)
+    info = np.zeros(9, np.int32)
+    rc = emu.emu_resident_vx_msa(g.n, g.m, g.E, ptr(g.chk_ptr), ptr(g.edge_var), ptr(g.var_ptr), ptr(g.var_edges),
+                                 ctypes.c_double(0.05), frames, ptr(pri), ptr(yh), 10, ptr(x_hat), ptr(iters), ptr(dec), ptr(info))
+    assert rc == 0
+    assert (iters == ref["iters"]).all()
+    assert (x_hat == ref["x_hat"]).all()
+    assert ((dec == 1) == (ref["reason"] == 0)).all()
+    assert g.E <= info[0] <= 1.08 * g.E + 64 and (np.diff(info[1:]) <= 0).all() and (info[1:] % 8 == 0).all()
+
+
 @pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_10", "7_4_hamming", "12_3_4_ldpc"])
 def test_shared_memory_placement(emu, code):
     """res_layout.h: positions are permutations into a padded range, every check's edge planes are a permutation of
