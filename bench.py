@@ -233,6 +233,24 @@ def extra_workloads(torch, lib, eng_mod, Tables, peak):
     big = codes.random_regular(64800, 3, 6, seed=0).tables
     bp_case("synthetic (3,6) n=64800 BIAWGN 1.0 dB MSA f32, max_iter 10 (no convergence)", big, lib.MSA, lib.F32, 1.0, 2048)
     bp_case("synthetic (3,6) n=64800 BIAWGN 2.5 dB MSA f32, max_iter 10", big, lib.MSA, lib.F32, 2.5, 2048)
+    # config 4: the irregular n = 1200 ensemble on BSC (src/simulations.py:35,77), on-chip variable-plane kernel
+    import math
+    irr = Tables(*load_code("1200_rho_x5_rand_ldpc_1"))
+    eng = eng_mod.engine_for(irr)
+    frames, pflip = 32768, 0.06
+    g = torch.Generator(device="cuda").manual_seed(5)
+    yh = (torch.rand((frames, irr.n), generator=g, device="cuda") < pflip).to(torch.uint8)
+    for algo, nm in ((lib.SPA, "SPA"), (lib.MSA, "MSA")):
+        res = {}
+        def fi():
+            res["o"] = eng.decode_device_channel(lib.CH_BSC, algo, lib.F32, math.log(1 - pflip) - math.log(pflip), yh,
+                                                 max_iter=MAX_ITER, out=res.get("o"))
+        ms = timed_steps(torch, fi, 3, 2, None)
+        iters = res["o"]["iters"].cpu().numpy()
+        out.append({"workload": "irregular LDPC n=1200 (1200_rho_x5_rand_ldpc_1) BSC p=0.06 %s f32, max_iter 10, cw=0 (%s)"
+                                % (nm, eng.resident_kernel or "streaming"),
+                    "value": frames * 3 / (ms / 1e3), "unit": UNIT, "mean_iters": float(iters.mean()),
+                    "edge_updates_per_s": 2 * irr.E * float(iters.sum()) * 3 / (ms / 1e3)})
     # Monte-Carlo round entirely on the GPU (on-device Philox channel + decode + error count): what sim.py --noise device runs
     eng = eng_mod.engine_for(tab)
     frames = 32768

@@ -315,22 +315,36 @@ LDPC_HD void cn_spa_sc(const float (&v)[DCMAX], int dc, float (&out)[DCMAX], flo
     }
     const bool has_zero = !(lo > 0.0f);
     const uint32_t xs = (x & 0x80000000u) | 0x3f317218u;            // +-ln 2
-    if (DCMAX >= 6 && dc == 6) {
-        // all-but-one sets of {0..5} from the two halves, single-element steps only (14 of them)
-        const SpaPair L = sc_step(sc_step(sc_one(u[0]), u[1]), u[2]);
-        const SpaPair R = sc_step(sc_step(sc_one(u[3]), u[4]), u[5]);
-        const SpaPair R0 = sc_step(R, u[0]), R1 = sc_step(R, u[1]);
-        const SpaPair L3 = sc_step(L, u[3]), L4 = sc_step(L, u[4]);
-        out[0] = sc_out<false>(sc_step(R1, u[2]), v[0], xs);
-        out[1] = sc_out<false>(sc_step(R0, u[2]), v[1], xs);
-        out[2] = sc_out<false>(sc_step(R0, u[1]), v[2], xs);
-        out[3] = sc_out<false>(sc_step(L4, u[5]), v[3], xs);
-        out[4] = sc_out<false>(sc_step(L3, u[5]), v[4], xs);
-        out[5] = sc_out<false>(sc_step(L3, u[4]), v[5], xs);
+    if (dc <= 6) {
+        // Up to six edges: the all-but-one sets of {0..5} from the two halves, single-element steps only (14 of them).
+        // A check with fewer edges is padded with u = 0, the empty element — sc_one(0) is the empty set (1, 0) and a step
+        // with u = 0 is the exact identity — so every caller runs the same operations on the same check whatever its
+        // DCMAX and however it pads (the on-chip kernel pads with +inf inputs, which saturate to u = 0 above).
+        float w[6], vv[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const bool real = (k < DCMAX) && (k < dc);
+            w[k] = real ? u[k < DCMAX ? k : 0] : 0.0f;
+            vv[k] = real ? v[k < DCMAX ? k : 0] : 0.0f;
+        }
+        const SpaPair L = sc_step(sc_step(sc_one(w[0]), w[1]), w[2]);
+        const SpaPair R = sc_step(sc_step(sc_one(w[3]), w[4]), w[5]);
+        const SpaPair R0 = sc_step(R, w[0]), R1 = sc_step(R, w[1]);
+        const SpaPair L3 = sc_step(L, w[3]), L4 = sc_step(L, w[4]);
+        float o6[6];
+        o6[0] = sc_out<false>(sc_step(R1, w[2]), vv[0], xs);
+        o6[1] = sc_out<false>(sc_step(R0, w[2]), vv[1], xs);
+        o6[2] = sc_out<false>(sc_step(R0, w[1]), vv[2], xs);
+        o6[3] = sc_out<false>(sc_step(L4, w[5]), vv[3], xs);
+        o6[4] = sc_out<false>(sc_step(L3, w[5]), vv[4], xs);
+        o6[5] = sc_out<false>(sc_step(L3, w[4]), vv[5], xs);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (k < DCMAX && k < dc) out[k < DCMAX ? k : 0] = o6[k];
         if (has_zero) {
 #pragma unroll
             for (int k = 0; k < 6; ++k)
-                if (v[k] == 0.0f) out[k] = NAN;
+                if (k < DCMAX && k < dc && vv[k] == 0.0f) out[k < DCMAX ? k : 0] = NAN;
         }
         return;
     }

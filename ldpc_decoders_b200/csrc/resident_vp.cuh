@@ -32,8 +32,8 @@
 //   * one 32-bit index word per edge: (message cell << 16) | (variable position << 4), the check's degree in the low
 //     bits of word 0; a check with fewer than DC edges is padded with edges that read a +inf marginal cell (neutral
 //     for the minimum and for the parity) and write to a scratch cell, each in a bank group its step leaves free;
-//   * sum-product runs cn_spa_sc with the check's real degree (natural edge order), so every message is bit-identical
-//     to the streaming sweeps whatever the degree.
+//   * sum-product (natural edge order) sees the padding as saturated inputs, u = 0, which is exactly how cn_spa_sc pads a
+//     short check for every caller: messages are bit-identical to the streaming sweeps whatever the degree.
 #pragma once
 #include "resident_bp.cuh"
 
@@ -159,7 +159,10 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
     constexpr int F = 4, CH = IRR ? DC : (DC + 1) / 2;
     constexpr uint32_t ALL = 0xFu;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int np = NPC ? NPC : p.n, mp = NPC ? NPC * DV / DC : p.m;
+    // check positions that go with NPC: n dv / dc for a regular code; the irregular instance is only dispatched for the
+    // rate-1/2 ensemble (np = 1200, mp = 600, decode_bp_resident)
+    constexpr int MPC = IRR ? NPC / 2 : NPC * DV / DC;
+    const int np = NPC ? NPC : p.n, mp = NPC ? MPC : p.m;
     const uint32_t S = (uint32_t)np * 16u;                            // bytes per plane
     const VpSmem L = IRR ? vx_smem_layout(np, p.plane_cells, p.ring, p.stage_stride) : vp_smem_layout(np, DV, p.ring, p.stage_stride);
     float4 *marg = reinterpret_cast<float4 *>(smem + L.marg);
@@ -446,22 +449,19 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
                     }
                 }
                 const uint32_t syn = (sx[0] >> 31) | ((sx[1] >> 31) << 1) | ((sx[2] >> 31) << 2) | ((sx[3] >> 31) << 3);
+                // Irregular codes, sum-product: a padding edge reads +inf, which the rule saturates to the neutral u = 0
+                // (cn_spa_sc pads short checks the same way, so the streaming sweeps agree bit for bit); its own output
+                // is forced to 0 so that the next v2c = inf - old stays +inf.
+                const int dcr = (IRR && ALGO != ALGO_MSA) ? (int)(cw[ps][0] & 15u) : DC;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float a[DC], o[DC];
 #pragma unroll
                     for (int k = 0; k < DC; ++k) a[k] = (&mg[k].x)[j];
-                    if (ALGO == ALGO_MSA) {
-                        cn_msa_lean<DC>(a, o);                               // padding edges read +inf: neutral
-                    } else if (IRR) {
+                    if (ALGO == ALGO_MSA) cn_msa_lean<DC>(a, o);             // irregular: padding edges read +inf, neutral
+                    else cn_spa_sc<DC>(a, DC, o, p.sat_llr);
 #pragma unroll
-                        for (int k = 0; k < DC; ++k) o[k] = 0.f;
-                        cn_spa_sc<DC>(a, (int)(cw[ps][0] & 15u), o, p.sat_llr);
-                    } else {
-                        cn_spa_sc<DC>(a, DC, o, p.sat_llr);
-                    }
-#pragma unroll
-                    for (int k = 0; k < DC; ++k) (&old[ps][k].x)[j] = o[k];
+                    for (int k = 0; k < DC; ++k) (&old[ps][k].x)[j] = (IRR && ALGO != ALGO_MSA && k >= 2 && k >= dcr) ? 0.f : o[k];
                 }
                 // scatter: plane (slot) of the variable's edge, same bank group as the gather of the same step
 #pragma unroll
