@@ -526,10 +526,10 @@ int launch_resident_t(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid
     return LDPC_OK;
 }
 
-template <int ALGO, int TT, int NPC, bool IRR = false>
+template <int ALGO, int TT, int NPC, bool IRR = false, int MAXT = 320>
 int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
-    auto kern = resident_vp<ALGO, 6, IRR ? 8 : 3, TT, NPC, IRR>;
+    auto kern = resident_vp<ALGO, 6, IRR ? 8 : 3, TT, NPC, IRR, MAXT>;
     static size_t opted = 0;
     if (lc.smem > opted) {
         int rc = opt_in_smem(h, kern, lc.smem);
@@ -601,10 +601,10 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     // Ring of received rows landed by the bulk-copy engine: needs 16-byte aligned rows; as deep as shared memory allows.
     const size_t row_bytes = (size_t)t.n * rp.in_es;
     const size_t stride = align_up(row_bytes, 16);
-    const size_t budget = resident_budget(h);
+    const size_t budget = r.vp_big ? h->smem_optin - 1024 : resident_budget(h);
     const int vtw = r.regular36 ? 2 : 0;                     // (3,6) variant keeps the variable-edge table in shared memory
     const size_t state = r.vx ? vx_smem_layout(r.np, r.vx_cells[tb], 0, 0).total
-                       : r.vp ? vp_smem_layout(r.np, 3, 0, 0).total : resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, 0, 0).total;
+                       : r.vp ? vp_smem_layout(r.np, 3, 0, 0, !r.vp_big).total : resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, 0, 0).total;
     int ring = 0;
     if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(in.src) & 15u) == 0 && budget > state)
         ring = (int)std::min<size_t>(kResRingMax, (budget - state) / stride);
@@ -613,7 +613,7 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     ResLaunch lc;
     lc.threads = r.threads;
     lc.smem = r.vx ? vx_smem_layout(r.np, r.vx_cells[tb], ring, (int)stride).total
-            : r.vp ? vp_smem_layout(r.np, 3, ring, (int)stride).total
+            : r.vp ? vp_smem_layout(r.np, 3, ring, (int)stride, !r.vp_big).total
                    : resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, ring, (int)stride).total;
     const int max_grid = (B + 4 * Q - 1) / (4 * Q);
 
@@ -627,6 +627,9 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
         else
             rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 0, 0, true>(h, rp, lc, max_grid, s)
                                     : launch_resident_vp<ALGO_SPA_PHI, 0, 0, true>(h, rp, lc, max_grid, s);
+    } else if (r.vp_big) {
+        rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 0, 0, false, kVpBigThreads>(h, rp, lc, max_grid, s)
+                                : launch_resident_vp<ALGO_SPA_PHI, 0, 0, false, kVpBigThreads>(h, rp, lc, max_grid, s);
     } else if (r.vp) {
         if (lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200)      // the reference's (1200,3,6) ensemble
             rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320, 1200>(h, rp, lc, max_grid, s)
@@ -661,11 +664,20 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
     r.planes = t.max_dc;
     r.regular36 = (t.uni_dc == 6 && t.uni_dv == 3 && mp == t.m && np == t.n);
     const int vtw = r.regular36 ? 2 : 0;
-    if ((long long)r.planes * mp * Q + 1 > 65535) return LDPC_OK;                    // c2v float4 index must fit 16 bits
-    if (((long long)np * Q + 1) * 16 > 65535) return LDPC_OK;                        // marg byte offset must fit 16 bits
-    if (resident_smem_layout(Q, np, mp, r.planes, vtw, 0, 0).total > resident_budget(h)) return LDPC_OK;
+    const char *lay = getenv("LDPC_RESIDENT_LAYOUT");
+    const bool lay_check = lay && std::string(lay) == "check";
+    // Regular (3,6) codes too long for half an SM (Margulis, n = 2640): ONE variable-plane CTA per SM, all of its shared memory
+    const bool big = r.regular36 && !lay_check && np % 4 == 0 && np * 16 <= 0xfff0 &&
+                     vp_smem_layout(np, 3, 0, 0).total > resident_budget(h) &&
+                     vp_smem_layout(np, 3, 0, 0, false).total <= h->smem_optin - 1024 &&
+                     mp <= kResCnPasses * kVpBigThreads && np <= kResVnPasses * kVpBigThreads;
+    if (!big) {
+        if ((long long)r.planes * mp * Q + 1 > 65535) return LDPC_OK;                // c2v float4 index must fit 16 bits
+        if (((long long)np * Q + 1) * 16 > 65535) return LDPC_OK;                    // marg byte offset must fit 16 bits
+        if (resident_smem_layout(Q, np, mp, r.planes, vtw, 0, 0).total > resident_budget(h)) return LDPC_OK;
+    }
     // threads: check items (mp * Q) in at most 2 passes, variable items (np * Q) in at most 4
-    const int citems = mp * Q, vitems = np * Q, maxT = res_max_threads(Q);
+    const int citems = mp * Q, vitems = np * Q, maxT = big ? kVpBigThreads : res_max_threads(Q);
     int T = std::max((citems + kResCnPasses - 1) / kResCnPasses, (vitems + kResVnPasses - 1) / kResVnPasses);
     if (citems <= maxT && vitems <= 2 * maxT) T = std::max(citems, (vitems + 1) / 2);
     T = std::max(64, (T + 31) / 32 * 32);
@@ -683,9 +695,8 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
     cudaError_t e = cudaSuccess;
 
     // ---- variable-plane variant for regular (3,6) codes: its own placement per edge order (res_layout.h, vn_contiguous)
-    const char *lay = getenv("LDPC_RESIDENT_LAYOUT");
-    if (r.regular36 && np % 4 == 0 && np * 16 <= 0xfff0 && !(lay && std::string(lay) == "check") &&
-        vp_smem_layout(np, 3, 0, 0).total <= resident_budget(h)) {
+    if (r.regular36 && np % 4 == 0 && np * 16 <= 0xfff0 && !lay_check &&
+        (big || vp_smem_layout(np, 3, 0, 0).total <= resident_budget(h))) {
         std::vector<int> slot((size_t)t.E, 0);
         for (int v = 0; v < t.n; ++v)
             for (int p0 = var_ptr[v], k = 0; p0 < var_ptr[v + 1]; ++p0, ++k) slot[var_edges[p0]] = k;
@@ -704,12 +715,13 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
         }
         if (e != cudaSuccess) return fail(nullptr, LDPC_ECUDA, std::string("resident table upload: ") + cudaGetErrorString(e));
         r.vp = true;
+        r.vp_big = big;
         r.ok = true;
         return LDPC_OK;
     }
 
     // ---- the same layout for irregular codes (resident_vp IRR = true): check degrees 2..6, variable degrees 0..8
-    if (!r.regular36 && t.max_dc <= 6 && t.max_dv <= 8 && !(lay && std::string(lay) == "check")) {
+    if (!r.regular36 && t.max_dc <= 6 && t.max_dv <= 8 && !lay_check) {
         bool fits = true;
         for (int tb = 0; tb < 2 && fits && e == cudaSuccess; ++tb) {
             ResPlanner pl2(t.n, t.m, t.E, chk_ptr, edge_var, var_ptr, var_edges, G);

@@ -42,7 +42,9 @@ namespace ldpc {
 struct VpSmem {
     size_t marg, planes, prior, stage, bars, hb, imap, total;
 };
-__host__ __device__ inline VpSmem vp_smem_layout(int np, int dv, int ring, int stage_stride)
+// imap_in_smem = false: the position -> variable map of the output stays in global memory (the one-CTA-per-SM
+// geometry of codes up to n = 2688, where the 2 n bytes are what makes room for the row ring).
+__host__ __device__ inline VpSmem vp_smem_layout(int np, int dv, int ring, int stage_stride, bool imap_in_smem = true)
 {
     VpSmem L;
     size_t o = 0;
@@ -52,7 +54,7 @@ __host__ __device__ inline VpSmem vp_smem_layout(int np, int dv, int ring, int s
     L.stage = o;  o += (size_t)ring * stage_stride;
     L.bars = o;   o += (size_t)kResRingMax * 8;
     L.hb = o;     o += ((size_t)np + 15) / 16 * 16;
-    L.imap = o;   o += ((size_t)np * 2 + 15) / 16 * 16;
+    L.imap = o;   o += imap_in_smem ? ((size_t)np * 2 + 15) / 16 * 16 : 0;
     L.total = o + 16;
     return L;
 }
@@ -151,9 +153,14 @@ __device__ __forceinline__ void vp_load4(const unsigned char *row, int i4, int i
 // NPC: number of variable positions when known at compile time (0 = p.n); the shipped ensemble is n = 1200, and with
 // np, mp and T constant every shared-memory address of the variable phase is base + immediate and the pass bounds
 // fold away.
-template <int ALGO, int DC, int DV, int TT, int NPC, bool IRR = false>
-__global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
+// MAXT: 320 = two CTAs per SM (4 + 4 frames); 672 = ONE CTA per SM for codes whose 4 frames need the whole shared
+// memory (n up to 2688: the Margulis code, n = 2640), 96 registers per thread either way.
+constexpr int kVpBigThreads = 672;
+template <int ALGO, int DC, int DV, int TT, int NPC, bool IRR = false, int MAXT = 320>
+__global__ void __launch_bounds__(MAXT, MAXT > 320 ? 1 : 2) resident_vp(const ResParams p)
 {
+    static_assert(MAXT == 320 || (MAXT == kVpBigThreads && !IRR && TT == 0 && NPC == 0), "two geometries");
+    constexpr bool BIG = MAXT > 320;
     static_assert(DC >= 2 && DC <= 8 && DV >= 1 && (IRR ? (DV <= 8 && DC <= 6) : DV <= 3),
                   "regular: slot field is two bits, index words hold two edges; irregular: c2v of two checks in registers");
     constexpr int F = 4, CH = IRR ? DC : (DC + 1) / 2;
@@ -164,14 +171,14 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
     constexpr int MPC = IRR ? NPC / 2 : NPC * DV / DC;
     const int np = NPC ? NPC : p.n, mp = NPC ? MPC : p.m;
     const uint32_t S = (uint32_t)np * 16u;                            // bytes per plane
-    const VpSmem L = IRR ? vx_smem_layout(np, p.plane_cells, p.ring, p.stage_stride) : vp_smem_layout(np, DV, p.ring, p.stage_stride);
+    const VpSmem L = IRR ? vx_smem_layout(np, p.plane_cells, p.ring, p.stage_stride) : vp_smem_layout(np, DV, p.ring, p.stage_stride, !BIG);
     float4 *marg = reinterpret_cast<float4 *>(smem + L.marg);
     float4 *planes = reinterpret_cast<float4 *>(smem + L.planes);
     float4 *prior = reinterpret_cast<float4 *>(smem + L.prior);
     unsigned char *stage = smem + L.stage;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
     uint8_t *hb = smem + L.hb;                                       // hard input bits of the slots being loaded, by position
-    uint16_t *imap = reinterpret_cast<uint16_t *>(smem + L.imap);    // variable at a position (output)
+    const uint16_t *imap = BIG ? p.vinvmap : reinterpret_cast<const uint16_t *>(smem + L.imap);    // variable at a position (output)
 
     __shared__ int s_frame[F], s_it[F], s_assign[F];
     __shared__ int r_frame[kResRingMax], r_uses[kResRingMax];
@@ -217,7 +224,8 @@ __global__ void __launch_bounds__(320, 2) resident_vp(const ResParams p)
 #pragma unroll
         for (int k = 0; k < DC; ++k) old[ps][k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int i = tid; i < np; i += T) imap[i] = p.vinvmap[i];
+    if (!BIG)
+        for (int i = tid; i < np; i += T) reinterpret_cast<uint16_t *>(smem + L.imap)[i] = p.vinvmap[i];
     if (IRR) {
         // cells nobody writes must read as +0.0 (short planes, holes), the padding cells behind marg as +inf
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f), i4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);

@@ -375,12 +375,8 @@ def test_resident_and_streaming_paths_agree(mods, code):
     torch, lib = mods["torch"], mods["lib"]
     tab = tables(mods, code)
     eng = mods["engine"].engine_for(tab)
-    if code == "margulis":                  # n = 2640: 239 KB of state + tables, more than one SM's shared memory
-        assert eng.resident_frames == 0
-        pri = torch.zeros((4, tab.n), dtype=torch.float32, device="cuda")
-        with pytest.raises(mods["lib"].LdpcError):
-            eng.decode_device(lib.MSA, pri, max_iter=3, flags=lib.PATH_RESIDENT)
-        return
+    if code == "margulis":                  # n = 2640: one variable-plane CTA per SM (resident_vp, 672 threads)
+        assert eng.resident_kernel == "resident_vp"
     assert eng.resident_frames in (4, 8)
     for B in (1, 13, 700):
         Yg = G.channel_send("biawgn", 2.0, np.zeros((B, tab.n), np.int64), 77)
@@ -435,7 +431,11 @@ def test_spa_degenerate_messages_agree_between_paths(mods, code):
 
 def test_resident_path_is_refused_where_it_cannot_run(mods):
     torch, lib = mods["torch"], mods["lib"]
-    from ldpc_decoders_b200 import LdpcError
+    from ldpc_decoders_b200 import LdpcError, codes
+    long_eng = mods["engine"].engine_for(codes.random_regular(6000, 3, 6, seed=1).tables)    # 4 frames need > 227 KB
+    assert long_eng.resident_frames == 0 and long_eng.resident_kernel == ""
+    with pytest.raises(LdpcError):
+        long_eng.decode_device(lib.MSA, torch.zeros((4, 6000), dtype=torch.float32, device="cuda"), max_iter=3, flags=lib.PATH_RESIDENT)
     eng = mods["engine"].engine_for(tables(mods, "1200_3_6_rand_ldpc_1"))
     pri = torch.zeros((4, 1200), dtype=torch.float64, device="cuda")
     with pytest.raises(LdpcError):
