@@ -143,10 +143,33 @@ BecLayout bec_layout(const Tables &t, int B)
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch by degree profile
 // ------------------------------------------------------------------------------------------------
+// Raises the dynamic shared-memory limit of a kernel instance on the handle's device when a launch needs more than
+// what was opted in so far (per handle: the attribute belongs to the device, a process may hold handles on several).
 template <typename KernelT> int opt_in_smem(ldpc_t *h, KernelT kern, size_t bytes)
 {
+    auto &slot = h->smem_opted[reinterpret_cast<const void *>(kern)];
+    if (bytes <= slot.first) return LDPC_OK;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return fail(h, LDPC_ECUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
+    slot.first = bytes;
+    slot.second = 0;
+    return LDPC_OK;
+}
+
+// Opt-in + CTAs per SM of an on-chip kernel at this launch geometry (cached with the opt-in).
+template <typename KernelT> int resident_occupancy(ldpc_t *h, KernelT kern, int threads, size_t smem, int *per_sm)
+{
+    int rc = opt_in_smem(h, kern, smem);
+    if (rc) return rc;
+    auto &slot = h->smem_opted[reinterpret_cast<const void *>(kern)];
+    if (slot.second <= 0 || smem != slot.first) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int n = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess || n < 1) n = 1;
+        if (smem != slot.first) { *per_sm = n; return LDPC_OK; }     // a smaller launch than the opted-in size: not cached
+        slot.second = n;
+    }
+    *per_sm = slot.second;
     return LDPC_OK;
 }
 
@@ -165,8 +188,7 @@ int launch_cn(ldpc_t *h, BpParams<T> p, bool tma, cudaStream_t s)
 #define CN_TMA(DC, UNI)                                                                             \
         do {                                                                                        \
             auto kern = cn_sweep_tma<T, FPT, ALGO, DC, UNI>;                                        \
-            static bool ready = false;                                                              \
-            if (!ready) { int rc_ = opt_in_smem(h, kern, tma_smem_bytes<DC>()); if (rc_) return rc_; ready = true; } \
+            { int rc_ = opt_in_smem(h, kern, tma_smem_bytes<DC>()); if (rc_) return rc_; }          \
             kern<<<grid, kTmaThreads, tma_smem_bytes<DC>(), s>>>(p);                                \
             h->launches++;                                                                          \
         } while (0)
@@ -511,15 +533,9 @@ template <int Q, int ALGO, int DCP, bool UDC, int DVP, bool UDV, bool REGC, bool
 int launch_resident_t(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
     auto kern = resident_bp<Q, ALGO, DCP, UDC, DVP, UDV, REGC, VSM>;
-    static size_t opted = 0;               // the attribute is per kernel instance: raise it when a larger code comes along
-    if (lc.smem > opted) {
-        int rc = opt_in_smem(h, kern, lc.smem);
-        if (rc) return rc;
-        opted = lc.smem;
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    }
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lc.threads, lc.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int rc = resident_occupancy(h, kern, lc.threads, lc.smem, &per_sm);
+    if (rc) return rc;
     const int grid = std::max(1, std::min(max_grid, h->sm_count * per_sm));
     kern<<<grid, lc.threads, lc.smem, s>>>(rp);
     h->launches++;
@@ -530,15 +546,9 @@ template <int ALGO, int TT, int NPC, bool IRR = false, int MAXT = 320>
 int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
     auto kern = resident_vp<ALGO, 6, IRR ? 8 : 3, TT, NPC, IRR, MAXT>;
-    static size_t opted = 0;
-    if (lc.smem > opted) {
-        int rc = opt_in_smem(h, kern, lc.smem);
-        if (rc) return rc;
-        opted = lc.smem;
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    }
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lc.threads, lc.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int rc = resident_occupancy(h, kern, lc.threads, lc.smem, &per_sm);
+    if (rc) return rc;
     const int grid = std::max(1, std::min(max_grid, h->sm_count * per_sm));
     kern<<<grid, lc.threads, lc.smem, s>>>(rp);
     h->launches++;
