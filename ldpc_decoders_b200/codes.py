@@ -110,3 +110,35 @@ def random_regular(n, dv, dc, seed=0):
     else:
         raise RuntimeError("could not remove double edges")
     return Code(Tables(m, n, chk_sock, cols), "%d_%d_%d_cfg_seed%d" % (n, dv, dc, seed))
+
+
+def variable_degree_counts(tables):
+    """{degree: number of variables} of a code — the input of random_irregular for "another code like this one"."""
+    deg = np.asarray(tables.var_degrees)
+    return {int(d): int(c) for d, c in enumerate(np.bincount(deg)) if c}
+
+
+def random_irregular(degree_counts, dc, seed=0):
+    """Seeded irregular code in O(E), the construction of the reference's generator (src/ldpc.py:149-192,
+    gen_rand_irg_ldpc) without its dense matrix: one socket per edge end, variables of degree d get d sockets
+    (degree_counts = {d: how many}, in ascending-degree order of the variable index like add_sockets, ldpc.py:141-146),
+    the variable sockets are shuffled against check sockets dealt round-robin (sockets_chk = range(m) * dc), and
+    parallel edges cancel in pairs (parity_mtx += 1 per socket, even entries -> 0, ldpc.py:186-188), so a few
+    checks / variables end up two edges short — the shipped 1200_rho_x5 files show exactly that (dc in {4, 6}).
+    The degree distribution itself comes from the reference's density-evolution solver (out of scope, SURVEY.md 2);
+    variable_degree_counts() of an existing code is the usual source."""
+    degs = np.concatenate([np.full(int(c), int(d), np.int64) for d, c in sorted(degree_counts.items()) if int(c) > 0 and int(d) > 0]
+                          or [np.zeros(0, np.int64)])
+    n = int(sum(int(c) for c in degree_counts.values()))
+    zero = int(degree_counts.get(0, 0))
+    E = int(degs.sum())
+    if E == 0 or E % dc:
+        raise ValueError("the number of edges (%d) must be a positive multiple of dc" % E)
+    m = E // dc
+    var_sock = np.repeat(np.arange(zero, zero + degs.size, dtype=np.int64), degs)      # degree-0 variables come first
+    chk_sock = np.tile(np.arange(m, dtype=np.int64), dc)
+    rng = np.random.default_rng(seed)
+    cols = var_sock[rng.permutation(E)]
+    key, mult = np.unique(chk_sock * n + cols, return_counts=True)
+    key = key[mult % 2 == 1]
+    return Code(Tables(m, n, key // n, key % n), "%d_irr_dc%d_cfg_seed%d" % (n, dc, seed))

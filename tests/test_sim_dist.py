@@ -151,3 +151,37 @@ def test_parse_cpulist_and_bind_is_harmless_without_gpu():
     assert D.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
     assert D.parse_cpulist("") == set()
     assert D.bind_near_gpu(0) is None or isinstance(D.bind_near_gpu(0), set)     # no CUDA device here: a no-op
+
+
+def test_random_irregular_sampler_follows_the_reference_construction():
+    """codes.random_irregular (src/ldpc.py:149-192 without the dense matrix): seeded, the requested variable degrees up
+    to the pairwise cancellation of parallel edges, checks of degree dc or dc - 2k, and the result decodes."""
+    import _golden as G
+    from ldpc_decoders_b200 import Tables, codes
+    from oracle import oracle as O
+    ref = Tables(*G.code_tables("1200_rho_x5_rand_ldpc_1"))
+    want = codes.variable_degree_counts(ref)
+    # the shipped file lost a few edges to cancellation: top the profile up to a multiple of dc like the reference's `extra`
+    prof = dict(want)
+    short = (-sum(d * c for d, c in prof.items())) % 6
+    if short:
+        prof[2] -= 1
+        prof[2 + short] = prof.get(2 + short, 0) + 1
+    a = codes.random_irregular(prof, 6, seed=3).tables
+    b = codes.random_irregular(prof, 6, seed=3).tables
+    c = codes.random_irregular(prof, 6, seed=4).tables
+    assert (a.edge_chk == b.edge_chk).all() and (a.edge_var == b.edge_var).all()
+    assert a.E != c.E or (a.edge_var != c.edge_var).any()
+    assert a.n == 1200 and a.m == sum(d * k for d, k in prof.items()) // 6
+    dc = a.check_degrees
+    assert set(dc.tolist()) <= {6, 4, 2} and (dc == 6).mean() > 0.95
+    lost = sum(d * k for d, k in prof.items()) - a.E
+    assert 0 <= lost <= 60 and lost % 2 == 0
+    got = codes.variable_degree_counts(a)
+    assert sum(abs(got.get(d, 0) - prof.get(d, 0)) for d in set(got) | set(prof)) <= 2 * lost
+    # decodes: clean BSC words stay, a few flips are corrected
+    g = O.Graph(a.m, a.n, a.edge_chk.astype(np.int64), a.edge_var.astype(np.int64))
+    y = np.zeros((8, a.n), np.uint8)
+    y[1:, ::151] = 1
+    out = O.bp_decode(g, O.MSA, O.llr_bsc(.02, y), y_hard=y, max_iter=20)
+    assert out["iters"][0] == 0 and (out["x_hat"] == 0).all()
