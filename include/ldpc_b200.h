@@ -71,7 +71,8 @@ extern "C" {
 /* flags for ldpc_decode */
 #define LDPC_PATH_AUTO      0u   /* resident kernel when the code fits on chip, else streaming */
 #define LDPC_PATH_STREAMING 1u   /* edge-major [E][B] messages in HBM, one CN + one VN sweep per iteration */
-#define LDPC_PATH_RESIDENT  2u   /* whole frames kept in shared memory for all iterations (short codes) */
+#define LDPC_PATH_RESIDENT  2u   /* whole frames kept in shared memory for all iterations (short codes; float32 MSA / SPA,
+                                    float64 MSA on regular codes) */
 #define LDPC_PATH_MASK      3u
 #define LDPC_SPA_ROBUST     4u   /* float32 SPA: do not emulate the reference's float64 tanh saturation (|v| > 38.123
                                     contributes exactly 0, which is what floods a frame with inf/NaN in the reference);

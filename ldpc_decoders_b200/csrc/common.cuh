@@ -3,7 +3,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <map>
 #include <string>
 #include <vector>
 
@@ -67,9 +66,6 @@ struct ldpc_handle {
     HostStage *stage = nullptr;
     ResidentInfo res;
     double plan_effort = 0.4;                // annealing effort of the shared-memory placement (LDPC_PLAN_EFFORT)
-    // dynamic shared memory opted in per kernel instance ON THIS DEVICE (the attribute is per device and function), and the
-    // occupancy that went with it: kernel -> (bytes, CTAs per SM)
-    std::map<const void *, std::pair<size_t, int>> smem_opted;
     bool prof = false;
     std::vector<ProfEvent> prof_ev;
     size_t prof_used = 0;

@@ -7,7 +7,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "channel_gen.cuh"
@@ -16,6 +19,7 @@
 #include "res_layout.h"
 #include "resident_bp.cuh"
 #include "resident_vp.cuh"
+#include "resident_vd.cuh"
 #include "stream_bec.cuh"
 #include "stream_bp.cuh"
 #include "stream_bp_tma.cuh"
@@ -143,33 +147,42 @@ BecLayout bec_layout(const Tables &t, int B)
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch by degree profile
 // ------------------------------------------------------------------------------------------------
-// Raises the dynamic shared-memory limit of a kernel instance on the handle's device when a launch needs more than
-// what was opted in so far (per handle: the attribute belongs to the device, a process may hold handles on several).
+// The dynamic shared-memory limit of a kernel instance is an attribute of (device, function) and cudaFuncSetAttribute
+// SETS it (a smaller request lowers it), while a process may hold several handles on the same device (one per code)
+// and handles on several devices.  So the opted-in size lives in one process-wide table keyed by (device, kernel) and
+// only ever grows; the occupancy that goes with the current size is cached next to it.
+struct SmemOpt {
+    size_t bytes = 0;
+    int per_sm = 0;
+};
+std::mutex g_smem_mu;
+std::map<std::pair<int, const void *>, SmemOpt> g_smem_opted;
+
 template <typename KernelT> int opt_in_smem(ldpc_t *h, KernelT kern, size_t bytes)
 {
-    auto &slot = h->smem_opted[reinterpret_cast<const void *>(kern)];
-    if (bytes <= slot.first) return LDPC_OK;
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    SmemOpt &slot = g_smem_opted[{h->device, reinterpret_cast<const void *>(kern)}];
+    if (bytes <= slot.bytes) return LDPC_OK;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return fail(h, LDPC_ECUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
-    slot.first = bytes;
-    slot.second = 0;
+    slot.bytes = bytes;
+    slot.per_sm = 0;
     return LDPC_OK;
 }
 
-// Opt-in + CTAs per SM of an on-chip kernel at this launch geometry (cached with the opt-in).
+// Opt-in + CTAs per SM of an on-chip kernel at this launch geometry (cached for the opted-in size).
 template <typename KernelT> int resident_occupancy(ldpc_t *h, KernelT kern, int threads, size_t smem, int *per_sm)
 {
     int rc = opt_in_smem(h, kern, smem);
     if (rc) return rc;
-    auto &slot = h->smem_opted[reinterpret_cast<const void *>(kern)];
-    if (slot.second <= 0 || smem != slot.first) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        int n = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess || n < 1) n = 1;
-        if (smem != slot.first) { *per_sm = n; return LDPC_OK; }     // a smaller launch than the opted-in size: not cached
-        slot.second = n;
-    }
-    *per_sm = slot.second;
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    SmemOpt &slot = g_smem_opted[{h->device, reinterpret_cast<const void *>(kern)}];
+    if (smem == slot.bytes && slot.per_sm > 0) { *per_sm = slot.per_sm; return LDPC_OK; }
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess || n < 1) n = 1;
+    if (smem == slot.bytes) slot.per_sm = n;                       // smaller launches than the opted-in size are not cached
+    *per_sm = n;
     return LDPC_OK;
 }
 
@@ -555,18 +568,35 @@ int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_gri
     return LDPC_OK;
 }
 
+template <int TT, int NPC>
+int launch_resident_vd(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
+{
+    auto kern = resident_vd<6, 3, TT, NPC>;
+    int per_sm = 1;
+    int rc = resident_occupancy(h, kern, lc.threads, lc.smem, &per_sm);
+    if (rc) return rc;
+    const int grid = std::max(1, std::min(max_grid, h->sm_count * per_sm));
+    kern<<<grid, lc.threads, lc.smem, s>>>(rp);
+    h->launches++;
+    return LDPC_OK;
+}
+
 // Shared memory one resident CTA may use: two CTAs share an SM (1 KB each is reserved by the system).
 size_t resident_budget(const ldpc_t *h)
 {
     return h->smem_per_sm / 2 > 4096 ? std::min(h->smem_optin, h->smem_per_sm / 2 - 1536) : 0;
 }
 
+// float32: MSA / SPA on any on-chip kernel; float64 (the reference's own arithmetic): min-sum on the two-CTA
+// variable-plane geometry of regular codes (resident_vd.cuh).
 bool resident_eligible(const ldpc_t *h, int algo, int dtype, const void *marg_out)
 {
-    return h->res.ok && dtype == LDPC_F32 && (algo == LDPC_MSA || algo == LDPC_SPA) && marg_out == nullptr;
+    if (!h->res.ok || marg_out != nullptr) return false;
+    if (dtype == LDPC_F32) return algo == LDPC_MSA || algo == LDPC_SPA;
+    return dtype == LDPC_F64 && algo == LDPC_MSA && h->res.vp && !h->res.vp_big;
 }
 
-int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_iter, int iter_cap,
+int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_iter, int iter_cap,
                        uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *ws, size_t ws_bytes,
                        unsigned flags, cudaStream_t s)
 {
@@ -625,12 +655,16 @@ int decode_bp_resident(ldpc_t *h, int algo, const InSpec &in, int B, int max_ite
     lc.smem = r.vx ? vx_smem_layout(r.np, r.vx_cells[tb], ring, (int)stride).total
             : r.vp ? vp_smem_layout(r.np, 3, ring, (int)stride, !r.vp_big).total
                    : resident_smem_layout(Q, r.np, r.mp, r.planes, vtw, ring, (int)stride).total;
-    const int max_grid = (B + 4 * Q - 1) / (4 * Q);
+    const int slots = (dtype == LDPC_F64) ? 2 : 4 * Q;           // frames a CTA holds
+    const int max_grid = (B + slots - 1) / slots;
 
     CUDA_TRY(h, cudaMemsetAsync(rp.counter, 0, sizeof(int), s));
     ProfEvent *pe = prof_begin(h, 0, s);
     int rc;
-    if (r.vx) {
+    if (dtype == LDPC_F64) {                                        // resident_eligible: min-sum, r.vp, two CTAs per SM
+        if (lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200) rc = launch_resident_vd<320, 1200>(h, rp, lc, max_grid, s);
+        else rc = launch_resident_vd<0, 0>(h, rp, lc, max_grid, s);
+    } else if (r.vx) {
         if (lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200)      // the reference's irregular n = 1200 ensemble
             rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320, 1200, true>(h, rp, lc, max_grid, s)
                                     : launch_resident_vp<ALGO_SPA_PHI, 320, 1200, true>(h, rp, lc, max_grid, s);
@@ -814,9 +848,9 @@ int decode_any(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_
     if (in.channel == LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "MSA/SPA cannot take BEC symbols");
     const bool res_ok = resident_eligible(h, algo, dtype, marg_out);
     if (path == LDPC_PATH_RESIDENT && !res_ok)
-        return fail(h, LDPC_EUNSUPPORTED, "resident path needs float32 MSA/SPA, no marg_out, degrees <= 8 and a code that fits in shared memory");
+        return fail(h, LDPC_EUNSUPPORTED, "resident path needs float32 MSA/SPA (or float64 MSA on a regular code of n <= 1280), no marg_out, degrees <= 8 and a code that fits in shared memory");
     if (path == LDPC_PATH_RESIDENT || (path == LDPC_PATH_AUTO && res_ok))
-        return decode_bp_resident(h, algo, in, B, max_iter, iter_cap, x_hat, iters, reason, ws, ws_bytes, flags, s);
+        return decode_bp_resident(h, algo, dtype, in, B, max_iter, iter_cap, x_hat, iters, reason, ws, ws_bytes, flags, s);
     if (dtype == LDPC_F32)
         return decode_bp_stream<float>(h, algo, in, B, max_iter, iter_cap, x_hat, iters, reason, marg_out, ws, ws_bytes, flags, s);
     if (dtype == LDPC_F64)
@@ -1187,12 +1221,14 @@ int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
     default: return fail(h, LDPC_EINVAL, "bad channel");
     }
     if (chunk <= 0) {
-        // Enough chunks to overlap H2D / decode / D2H on the 3 slot streams, each chunk still filling the GPU
-        // (>= 4096 frames) and its message workspace bounded (~1 GiB per slot).
+        // Enough chunks to overlap H2D / decode / D2H on the 3 slot streams and keep the pipeline's ramp and tail short
+        // (B / 16; scripts/e2e_probe.py: 2048-frame chunks of the n = 1200 code reach 0.90 of a plain pinned H2D copy,
+        // 5461-frame chunks 0.87, one chunk 0.63), each chunk still filling the GPU (>= 2048 frames) and its message
+        // workspace bounded (~1 GiB per slot).
         const size_t per_frame = (size_t)t.E * elem_size(dtype) + (size_t)t.n * elem_size(dtype) * 2;
         size_t cap = ((size_t)1 << 30) / std::max<size_t>(per_frame, 1);
         cap = std::max<size_t>(256, std::min<size_t>(cap, 16384));
-        size_t c = std::max<size_t>((size_t)B / 6, 4096);
+        size_t c = std::max<size_t>((size_t)B / 16, 2048);
         c = std::min(c, cap);
         chunk = (int)std::max<size_t>(128, c / 128 * 128);
     }

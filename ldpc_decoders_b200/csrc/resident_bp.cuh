@@ -1,10 +1,13 @@
-// resident_bp.cuh — on-chip flooding BP for short codes, with continuous frame refill.
+// resident_bp.cuh — on-chip flooding BP for short codes, with continuous frame refill: the check-major
+// message layout.  Since resident_vp.cuh (variable-plane layout) took over every shipped code, this kernel serves the
+// degree profiles that one does not cover (check degree 7..8, degree-1 checks) and LDPC_RESIDENT_LAYOUT=check; it also
+// holds what both kernels share: ResParams, the LLR front end of the refill, the packed-index helpers.
 //
-// For n = 1200 one frame's decoder state is 19 KB, so a CTA keeps F = 8 frames ("slots") in shared memory
-// and registers for ALL their iterations: HBM sees the received row once on the way in and the hard
+// For n = 1200 one frame's decoder state is 19 KB, so a CTA keeps F = 4 Q frames ("slots", Q = 1 as shipped) in shared
+// memory and registers for ALL their iterations: HBM sees the received row once on the way in and the hard
 // decisions once on the way out (~6 KB per frame instead of 63 KB per frame-iteration).
 //
-// State of one slot (frames are the innermost dimension: a float4 = the 4 frames of one "quad", Q = 2 quads):
+// State of one slot (frames are the innermost dimension: a float4 = the 4 frames of one "quad", Q quads per CTA):
 //   marg [n][Q]        float4  shared   last marginal of every variable (bpa.py:35); before the first
 //                                       iteration it holds the prior, so v2c = marg - 0 = priors[yy] (bpa.py:19)
 //   prior[n][Q]        float4  shared

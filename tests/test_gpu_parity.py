@@ -439,7 +439,45 @@ def test_resident_path_is_refused_where_it_cannot_run(mods):
     eng = mods["engine"].engine_for(tables(mods, "1200_3_6_rand_ldpc_1"))
     pri = torch.zeros((4, 1200), dtype=torch.float64, device="cuda")
     with pytest.raises(LdpcError):
-        eng.decode_device(lib.MSA, pri, max_iter=3, flags=lib.PATH_RESIDENT)      # float64 has no resident kernel
+        eng.decode_device(lib.SPA, pri, max_iter=3, flags=lib.PATH_RESIDENT)      # float64 sum-product has no resident kernel
+    irr = mods["engine"].engine_for(tables(mods, "1200_rho_x5_rand_ldpc_1"))
+    with pytest.raises(LdpcError):
+        irr.decode_device(lib.MSA, pri, max_iter=3, flags=lib.PATH_RESIDENT)      # float64 min-sum: regular codes only
+
+
+@pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_2", "512_3_6_rand_ldpc_3", "1200_3_6_ldpc"])
+def test_float64_on_chip_min_sum(mods, code):
+    """resident_vd: float64 min-sum on chip (the reference's own arithmetic).  Same words, iteration counts and exit
+    reasons as the float64 streaming sweeps for every front end, and as the float64 oracle."""
+    torch, lib = mods["torch"], mods["lib"]
+    tab, og = tables(mods, code), ograph(code)
+    eng = mods["engine"].engine_for(tab)
+    B = 777
+    Yg = G.channel_send("biawgn", 2.0, np.ones((B, tab.n), np.int64), 515)
+    Yb = G.channel_send("bsc", .05, np.ones((B, tab.n), np.int64), 516).astype(np.uint8)
+    Yb[5] = 1                                                                    # a clean word: iteration-0 exit
+    nv = 10 ** (-2.0 / 10)
+    for mi in (10, 3, 40):
+        cases = [(lib.CH_BIAWGN, nv, torch.from_numpy(Yg).cuda()),
+                 (lib.CH_BIAWGN, nv, torch.from_numpy(Yg.astype(np.float32)).cuda()),
+                 (lib.CH_BSC, float(np.log(1 - .05) - np.log(.05)), torch.from_numpy(Yb).cuda())]
+        for ch, prm, y in cases:
+            a = eng.decode_device_channel(ch, lib.MSA, lib.F64, prm, y, max_iter=mi, flags=lib.PATH_STREAMING)
+            a = {k: (v.clone() if v is not None else None) for k, v in a.items()}
+            n0 = eng.launch_count
+            b = eng.decode_device_channel(ch, lib.MSA, lib.F64, prm, y, max_iter=mi, flags=lib.PATH_RESIDENT)
+            assert eng.launch_count - n0 == 1
+            assert bool((a["iters"] == b["iters"]).all()) and bool((a["reason"] == b["reason"]).all())
+            assert bool((a["x_hat"] == b["x_hat"]).all())
+        ref = O.bp_decode(og, O.MSA, O.llr_biawgn(2.0, Yg), max_iter=mi, nthreads=8)
+        c = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, lib.F64, nv, torch.from_numpy(Yg).cuda(), max_iter=mi)   # AUTO
+        assert (c["iters"].cpu().numpy() == ref["iters"]).all() and (c["x_hat"].cpu().numpy() == ref["x_hat"]).all()
+        assert (c["reason"].cpu().numpy() == ref["reason"]).all()
+        refb = O.bp_decode(og, O.MSA, O.llr_bsc(.05, Yb), y_hard=Yb, max_iter=mi, nthreads=8)
+        pri = torch.from_numpy(O.llr_bsc(.05, Yb)).cuda()
+        d = eng.decode_device(lib.MSA, pri, y_hard=torch.from_numpy(Yb).cuda(), max_iter=mi, flags=lib.PATH_RESIDENT)
+        assert (d["iters"].cpu().numpy() == refb["iters"]).all() and (d["x_hat"].cpu().numpy() == refb["x_hat"]).all()
+        assert d["iters"][5].item() == 0
 
 
 def test_register_and_bulk_async_check_node_sweeps_agree(mods):
