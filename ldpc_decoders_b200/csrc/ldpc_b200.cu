@@ -568,10 +568,10 @@ int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_gri
     return LDPC_OK;
 }
 
-template <int TT, int NPC>
+template <int TT, int NPC, bool IRR>
 int launch_resident_vd(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
-    auto kern = resident_vd<6, 3, TT, NPC>;
+    auto kern = resident_vd<6, IRR ? 8 : 3, TT, NPC, IRR>;
     int per_sm = 1;
     int rc = resident_occupancy(h, kern, lc.threads, lc.smem, &per_sm);
     if (rc) return rc;
@@ -588,12 +588,12 @@ size_t resident_budget(const ldpc_t *h)
 }
 
 // float32: MSA / SPA on any on-chip kernel; float64 (the reference's own arithmetic): min-sum on the two-CTA
-// variable-plane geometry of regular codes (resident_vd.cuh).
+// variable-plane geometries, regular or irregular (resident_vd.cuh).
 bool resident_eligible(const ldpc_t *h, int algo, int dtype, const void *marg_out)
 {
     if (!h->res.ok || marg_out != nullptr) return false;
     if (dtype == LDPC_F32) return algo == LDPC_MSA || algo == LDPC_SPA;
-    return dtype == LDPC_F64 && algo == LDPC_MSA && h->res.vp && !h->res.vp_big;
+    return dtype == LDPC_F64 && algo == LDPC_MSA && ((h->res.vp && !h->res.vp_big) || h->res.vx);
 }
 
 int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_iter, int iter_cap,
@@ -662,8 +662,9 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
     ProfEvent *pe = prof_begin(h, 0, s);
     int rc;
     if (dtype == LDPC_F64) {                                        // resident_eligible: min-sum, r.vp, two CTAs per SM
-        if (lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200) rc = launch_resident_vd<320, 1200>(h, rp, lc, max_grid, s);
-        else rc = launch_resident_vd<0, 0>(h, rp, lc, max_grid, s);
+        const bool ens = lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200;
+        if (r.vx) rc = ens ? launch_resident_vd<320, 1200, true>(h, rp, lc, max_grid, s) : launch_resident_vd<0, 0, true>(h, rp, lc, max_grid, s);
+        else rc = ens ? launch_resident_vd<320, 1200, false>(h, rp, lc, max_grid, s) : launch_resident_vd<0, 0, false>(h, rp, lc, max_grid, s);
     } else if (r.vx) {
         if (lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200)      // the reference's irregular n = 1200 ensemble
             rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320, 1200, true>(h, rp, lc, max_grid, s)
@@ -848,7 +849,7 @@ int decode_any(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_
     if (in.channel == LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "MSA/SPA cannot take BEC symbols");
     const bool res_ok = resident_eligible(h, algo, dtype, marg_out);
     if (path == LDPC_PATH_RESIDENT && !res_ok)
-        return fail(h, LDPC_EUNSUPPORTED, "resident path needs float32 MSA/SPA (or float64 MSA on a regular code of n <= 1280), no marg_out, degrees <= 8 and a code that fits in shared memory");
+        return fail(h, LDPC_EUNSUPPORTED, "resident path needs float32 MSA/SPA (or float64 MSA on a code of n <= 1280 with check degrees <= 6), no marg_out, degrees <= 8 and a code that fits in shared memory");
     if (path == LDPC_PATH_RESIDENT || (path == LDPC_PATH_AUTO && res_ok))
         return decode_bp_resident(h, algo, dtype, in, B, max_iter, iter_cap, x_hat, iters, reason, ws, ws_bytes, flags, s);
     if (dtype == LDPC_F32)

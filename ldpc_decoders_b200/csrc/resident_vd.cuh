@@ -13,7 +13,9 @@
 //   * variable node: marg = prior + ((c0 + c1) + c2) in ascending edge order (bpa.py:35);
 //   * refill: priors exactly as the reference computes them, (-2 y) / noise_var with the float64 division
 //     (biawgn.py:28), L (1 - 2 y) for BSC (bsc.py:25), or the caller's float64 priors; -0.0 folded to +0.0.
-// Exit rules, ring, frame dispenser and outputs are resident_vp's with 2-bit slot masks.
+// Exit rules, ring, frame dispenser and outputs are resident_vp's with 2-bit slot masks.  IRR = true is the irregular
+// instance (planes as prefixes of the degree-sorted positions, one index word per edge, checks padded with +inf reads and
+// scratch writes), exactly as in resident_vp.
 #pragma once
 #include "resident_vp.cuh"
 
@@ -70,17 +72,18 @@ __device__ __forceinline__ double vd_llr(const void *row, int v, int in_mode, in
     return __dadd_rn(val, 0.0);
 }
 
-// DC: degree of every check, DV <= 3: degree of every variable, TT / NPC as in resident_vp.
-template <int DC, int DV, int TT, int NPC>
+// DC, DV, TT, NPC, IRR as in resident_vp.
+template <int DC, int DV, int TT, int NPC, bool IRR = false>
 __global__ void __launch_bounds__(320, 2) resident_vd(const ResParams p)
 {
-    static_assert(DV >= 1 && DV <= 3 && DC >= 2 && DC <= 8, "see resident_vp");
-    constexpr int F = 2, CH = (DC + 1) / 2;
+    static_assert(DC >= 2 && DC <= 8 && DV >= 1 && (IRR ? (DV <= 8 && DC <= 6) : DV <= 3), "see resident_vp");
+    constexpr int F = 2, CH = IRR ? DC : (DC + 1) / 2;
     constexpr uint32_t ALL = 0x3u;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int np = NPC ? NPC : p.n, mp = NPC ? NPC * DV / DC : p.m;
+    constexpr int MPC = IRR ? NPC / 2 : NPC * DV / DC;
+    const int np = NPC ? NPC : p.n, mp = NPC ? MPC : p.m;
     const uint32_t S = (uint32_t)np * 16u;                            // bytes per plane
-    const VpSmem L = vp_smem_layout(np, DV, p.ring, p.stage_stride);
+    const VpSmem L = IRR ? vx_smem_layout(np, p.plane_cells, p.ring, p.stage_stride) : vp_smem_layout(np, DV, p.ring, p.stage_stride);
     double2 *marg = reinterpret_cast<double2 *>(smem + L.marg);
     double2 *planes = reinterpret_cast<double2 *>(smem + L.planes);
     double2 *prior = reinterpret_cast<double2 *>(smem + L.prior);
@@ -107,15 +110,21 @@ __global__ void __launch_bounds__(320, 2) resident_vd(const ResParams p)
 #pragma unroll
         for (int h = 0; h < CH; ++h) cw[ps][h] = 0u;
         if (c < mp) {
+            if (IRR) {
 #pragma unroll
-            for (int k = 0; k < DC; ++k) {
-                const uint32_t e = p.cw[(size_t)c * 8 + k];          // (position << 4) | (slot + 1)
-                if (k & 1) cw[ps][k >> 1] |= (e & 0xfff0u) << 16 | (e & 3u) << 2;
-                else cw[ps][k >> 1] |= e & 0xfff3u;
+                for (int k = 0; k < DC; ++k) cw[ps][k] = p.cwx[(size_t)c * 8 + k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < DC; ++k) {
+                    const uint32_t e = p.cw[(size_t)c * 8 + k];      // (position << 4) | (slot + 1)
+                    if (k & 1) cw[ps][k >> 1] |= (e & 0xfff0u) << 16 | (e & 3u) << 2;
+                    else cw[ps][k >> 1] |= e & 0xfff3u;
+                }
             }
         }
     }
     auto goff = [&](int ps, int k) -> uint32_t {
+        if (IRR) return vx_goff(cw[ps][k]);
         const uint32_t w = cw[ps][k >> 1];
         return (k & 1) ? vp_off1(w) : vp_off0(w);
     };
@@ -126,6 +135,14 @@ __global__ void __launch_bounds__(320, 2) resident_vd(const ResParams p)
         for (int k = 0; k < DC; ++k) old[ps][k] = make_double2(0.0, 0.0);
 
     for (int i = tid; i < np; i += T) imap[i] = p.vinvmap[i];
+    if (IRR) {
+        // cells nobody writes must read as +0.0 (short planes, holes), the padding cells behind marg as +inf
+        const double2 z2 = make_double2(0.0, 0.0);
+        for (int i = tid; i < (int)(L.stage / 16); i += T) reinterpret_cast<double2 *>(smem)[i] = z2;
+        for (int i = tid; i < np + 8; i += T) hb[i] = 0;
+        __syncthreads();
+        if (tid < 8) marg[np + tid] = make_double2((double)INFINITY, (double)INFINITY);
+    }
     if (tid == 0) {
         s_unsat[0] = s_unsat[1] = s_maxed[0] = s_maxed[1] = 0u;
         s_unsat0 = 0u;
@@ -162,7 +179,10 @@ __global__ void __launch_bounds__(320, 2) resident_vd(const ResParams p)
 #pragma unroll
             for (int ps = 0; ps < kResVnPasses; ++ps) {
                 const int item = tid + ps * T;
-                if (item < np) dst[imap[item]] = (uint8_t)(mj[(size_t)item * 4] >> 31);
+                if (item < np) {
+                    const uint32_t v = imap[item];
+                    if (!IRR || v != 0xffffu) dst[v] = (uint8_t)(mj[(size_t)item * 4] >> 31);
+                }
             }
         }
         if (tid < F && ((mask >> tid) & 1u)) {
@@ -271,7 +291,10 @@ __global__ void __launch_bounds__(320, 2) resident_vd(const ResParams p)
                     if (!((z >> s) & 1u)) continue;
                     const int g = s_frame[s];
                     uint8_t *dst = p.x_hat + (size_t)g * nref;
-                    for (int i = tid; i < np; i += T) dst[imap[i]] = (uint8_t)((hb[i] >> s) & 1u);
+                    for (int i = tid; i < np; i += T) {
+                        const uint32_t v = imap[i];
+                        if (!IRR || v != 0xffffu) dst[v] = (uint8_t)((hb[i] >> s) & 1u);
+                    }
                     if (tid == 0) {
                         p.iters[g] = 0;
                         if (p.reason != nullptr) p.reason[g] = (uint8_t)LDPC_REASON_DECODED;
@@ -317,8 +340,13 @@ __global__ void __launch_bounds__(320, 2) resident_vd(const ResParams p)
                 // scatter: plane (slot) of the variable's edge, same bank group as the gather of the same step
 #pragma unroll
                 for (int k = 0; k < DC; ++k) {
-                    const uint32_t w = cw[ps][k >> 1];
-                    const uint32_t coff = (k & 1) ? vp_sl1x4(w) * (S >> 2) + vp_off1(w) : vp_sl0(w) * S + vp_off0(w);
+                    uint32_t coff;
+                    if (IRR) {
+                        coff = vx_soff(cw[ps][k]);
+                    } else {
+                        const uint32_t w = cw[ps][k >> 1];
+                        coff = (k & 1) ? vp_sl1x4(w) * (S >> 2) + vp_off1(w) : vp_sl0(w) * S + vp_off0(w);
+                    }
                     *reinterpret_cast<double2 *>(smem + coff) = old[ps][k];
                 }
                 unsat |= syn;
@@ -344,7 +372,20 @@ __global__ void __launch_bounds__(320, 2) resident_vd(const ResParams p)
 #pragma unroll
         for (int ps = 0; ps < kResVnPasses; ++ps) {
             const int item = tid + ps * T;
-            if (item < np) {
+            if (IRR) {
+                if (item < np) {
+                    double2 sm = make_double2(0.0, 0.0);
+                    if (item < p.pcnt[0]) sm = *reinterpret_cast<const double2 *>(smem + p.pbase[0] + (size_t)item * 16);
+#pragma unroll
+                    for (int k = 1; k < DV; ++k) {
+                        if (item >= p.pcnt[k]) break;
+                        const double2 c = *reinterpret_cast<const double2 *>(smem + p.pbase[k] + (size_t)item * 16);
+                        sm.x = __dadd_rn(sm.x, c.x); sm.y = __dadd_rn(sm.y, c.y);
+                    }
+                    const double2 pr = prior[item];
+                    marg[item] = make_double2(__dadd_rn(pr.x, sm.x), __dadd_rn(pr.y, sm.y));
+                }
+            } else if (item < np) {
                 double2 c[DV];
 #pragma unroll
                 for (int k = 0; k < DV; ++k) c[k] = planes[(size_t)k * np + item];

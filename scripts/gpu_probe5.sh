@@ -9,6 +9,8 @@ python scripts/run_case.py --algo MSA --dtype f64 --steps 5 --streaming
 python scripts/run_case.py --algo MSA --dtype f64 --snr 3.0 --steps 10
 python scripts/run_case.py --algo MSA --dtype f64 --channel bsc --snr 0.05 --steps 10
 python scripts/run_case.py --code 512_3_6_rand_ldpc_1 --algo MSA --dtype f64 --cw 0
+python scripts/run_case.py --code 1200_rho_x5_rand_ldpc_1 --algo MSA --dtype f64 --cw 0
+python scripts/run_case.py --code 1200_rho_x5_rand_ldpc_1 --algo MSA --dtype f64 --cw 0 --streaming
 python scripts/run_case.py --algo MSA --steps 10
 } 2>&1 | tee gpurun_out/cases5.txt
-timeout 300 python scripts/e2e_probe.py 2>&1 | tail -4
+timeout 500 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; python -c "import json; d=json.load(open(\"gpurun_out/bench.json\")); print(d[\"value\"], d[\"e2e\"][\"value\"]); [print(e[\"workload\"][:80], e[\"value\"], e.get(\"path\")) for e in d[\"extra\"]]"

@@ -440,12 +440,13 @@ def test_resident_path_is_refused_where_it_cannot_run(mods):
     pri = torch.zeros((4, 1200), dtype=torch.float64, device="cuda")
     with pytest.raises(LdpcError):
         eng.decode_device(lib.SPA, pri, max_iter=3, flags=lib.PATH_RESIDENT)      # float64 sum-product has no resident kernel
-    irr = mods["engine"].engine_for(tables(mods, "1200_rho_x5_rand_ldpc_1"))
-    with pytest.raises(LdpcError):
-        irr.decode_device(lib.MSA, pri, max_iter=3, flags=lib.PATH_RESIDENT)      # float64 min-sum: regular codes only
+    mar = mods["engine"].engine_for(tables(mods, "margulis"))
+    with pytest.raises(LdpcError):                                               # float64 min-sum: not in the one-CTA-per-SM geometry
+        mar.decode_device(lib.MSA, torch.zeros((4, 2640), dtype=torch.float64, device="cuda"), max_iter=3, flags=lib.PATH_RESIDENT)
 
 
-@pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_2", "512_3_6_rand_ldpc_3", "1200_3_6_ldpc"])
+@pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_2", "512_3_6_rand_ldpc_3", "1200_3_6_ldpc", "1200_rho_x5_rand_ldpc_5",
+                                  "1200_rho_x5_rand_ldpc_7", "7_4_hamming", "12_3_4_ldpc"])
 def test_float64_on_chip_min_sum(mods, code):
     """resident_vd: float64 min-sum on chip (the reference's own arithmetic).  Same words, iteration counts and exit
     reasons as the float64 streaming sweeps for every front end, and as the float64 oracle."""
@@ -453,9 +454,10 @@ def test_float64_on_chip_min_sum(mods, code):
     tab, og = tables(mods, code), ograph(code)
     eng = mods["engine"].engine_for(tab)
     B = 777
-    Yg = G.channel_send("biawgn", 2.0, np.ones((B, tab.n), np.int64), 515)
-    Yb = G.channel_send("bsc", .05, np.ones((B, tab.n), np.int64), 516).astype(np.uint8)
-    Yb[5] = 1                                                                    # a clean word: iteration-0 exit
+    cw = 1 if "3_6" in code else 0                                               # all-ones is a codeword of the (3,6) codes only
+    Yg = G.channel_send("biawgn", 2.0, np.zeros((B, tab.n), np.int64) + cw, 515)
+    Yb = G.channel_send("bsc", .05, np.zeros((B, tab.n), np.int64) + cw, 516).astype(np.uint8)
+    Yb[5] = cw                                                                   # a clean word: iteration-0 exit
     nv = 10 ** (-2.0 / 10)
     for mi in (10, 3, 40):
         cases = [(lib.CH_BIAWGN, nv, torch.from_numpy(Yg).cuda()),
