@@ -715,7 +715,7 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
     const bool big = r.regular36 && !lay_check && np % 4 == 0 && np * 16 <= 0xfff0 &&
                      vp_smem_layout(np, 3, 0, 0).total > resident_budget(h) &&
                      vp_smem_layout(np, 3, 0, 0, false).total <= h->smem_optin - 1024 &&
-                     mp <= kResCnPasses * kVpBigThreads && np <= kResVnPasses * kVpBigThreads;
+                     mp <= (kResCnPasses + 1) * kVpBigThreads && np <= kVpBigVnPasses * kVpBigThreads;
     if (!big) {
         if ((long long)r.planes * mp * Q + 1 > 65535) return LDPC_OK;                // c2v float4 index must fit 16 bits
         if (((long long)np * Q + 1) * 16 > 65535) return LDPC_OK;                    // marg byte offset must fit 16 bits
@@ -726,6 +726,7 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
     int T = std::max((citems + kResCnPasses - 1) / kResCnPasses, (vitems + kResVnPasses - 1) / kResVnPasses);
     if (citems <= maxT && vitems <= 2 * maxT) T = std::max(citems, (vitems + 1) / 2);
     T = std::max(64, (T + 31) / 32 * 32);
+    if (big) T = kVpBigThreads;                                   // third check pass / fifth variable pass cover the rest
     if (T > maxT) return LDPC_OK;
     r.threads = T; r.Q = Q; r.np = np; r.mp = mp;
 

@@ -153,14 +153,19 @@ __device__ __forceinline__ void vp_load4(const unsigned char *row, int i4, int i
 // NPC: number of variable positions when known at compile time (0 = p.n); the shipped ensemble is n = 1200, and with
 // np, mp and T constant every shared-memory address of the variable phase is base + immediate and the pass bounds
 // fold away.
-// MAXT: 320 = two CTAs per SM (4 + 4 frames); 672 = ONE CTA per SM for codes whose 4 frames need the whole shared
-// memory (n up to 2688: the Margulis code, n = 2640), 96 registers per thread either way.
-constexpr int kVpBigThreads = 672;
+// MAXT: 320 = two CTAs per SM (4 + 4 frames); 640 = ONE CTA per SM for codes whose 4 frames need the whole shared
+// memory (n up to 2688: the Margulis code, n = 2640), 96 registers per thread either way.  20 warps is what 96
+// registers allow (warps are allocated in fours: 21 would get 80 registers and spill), so that geometry makes five
+// variable passes and, for the checks beyond 2 x 640, a third check pass whose c2v_old is read back from the planes
+// it was scattered to instead of being kept in registers.
+constexpr int kVpBigThreads = 640;
+constexpr int kVpBigVnPasses = 5;
 template <int ALGO, int DC, int DV, int TT, int NPC, bool IRR = false, int MAXT = 320>
 __global__ void __launch_bounds__(MAXT, MAXT > 320 ? 1 : 2) resident_vp(const ResParams p)
 {
     static_assert(MAXT == 320 || (MAXT == kVpBigThreads && !IRR && TT == 0 && NPC == 0), "two geometries");
     constexpr bool BIG = MAXT > 320;
+    constexpr int VNP = BIG ? kVpBigVnPasses : kResVnPasses;
     static_assert(DC >= 2 && DC <= 8 && DV >= 1 && (IRR ? (DV <= 8 && DC <= 6) : DV <= 3),
                   "regular: slot field is two bits, index words hold two edges; irregular: c2v of two checks in registers");
     constexpr int F = 4, CH = IRR ? DC : (DC + 1) / 2;
@@ -218,6 +223,16 @@ __global__ void __launch_bounds__(MAXT, MAXT > 320 ? 1 : 2) resident_vp(const Re
         const uint32_t w = cw[ps][k >> 1];
         return (k & 1) ? vp_off1(w) : vp_off0(w);
     };
+    // BIG: the check of the third pass (position tid + 2 T), its gather / scatter byte offsets straight from the table
+    const int ctail = tid + kResCnPasses * T;
+    auto tail_offsets = [&](uint32_t (&g)[DC], uint32_t (&sc)[DC]) {
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+            const uint32_t e = p.cw[(size_t)ctail * 8 + k];          // (position << 4) | (slot + 1)
+            g[k] = e & 0xfff0u;
+            sc[k] = (e & 3u) * S + g[k];
+        }
+    };
     float4 old[kResCnPasses][DC];                                    // c2v of the thread's own checks
 #pragma unroll
     for (int ps = 0; ps < kResCnPasses; ++ps)
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(MAXT, MAXT > 320 ? 1 : 2) resident_vp(const Re
             uint8_t *dst = p.x_hat + (size_t)s_frame[j] * nref;
             const uint32_t *mj = reinterpret_cast<const uint32_t *>(marg) + j;
 #pragma unroll
-            for (int ps = 0; ps < kResVnPasses; ++ps) {
+            for (int ps = 0; ps < VNP; ++ps) {
                 const int item = tid + ps * T;
                 if (item < np) {
                     const uint32_t v = imap[item];
@@ -395,6 +410,15 @@ __global__ void __launch_bounds__(MAXT, MAXT > 320 ? 1 : 2) resident_vp(const Re
                         if (nm & 8u) old[ps][k].w = 0.f;
                     }
             }
+            if (BIG && ctail < mp) {                       // third-pass checks keep their c2v in the planes only
+                uint32_t g[DC], sc[DC];
+                tail_offsets(g, sc);
+#pragma unroll
+                for (int k = 0; k < DC; ++k)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((nm >> j) & 1u) reinterpret_cast<float *>(smem + sc[k])[j] = 0.f;
+            }
             __syncthreads();                               // columns / hb visible; staged rows consumed
             if (tid == 0 && async) {
                 for (int s = 0; s < F; ++s)
@@ -412,6 +436,13 @@ __global__ void __launch_bounds__(MAXT, MAXT > 320 ? 1 : 2) resident_vp(const Re
                         for (int k = 0; k < DC; ++k) syn ^= hb[goff(ps, k) >> 4];
                         u0 |= syn & ALL;
                     }
+                }
+                if (BIG && ctail < mp) {
+                    uint32_t g[DC], sc[DC], syn = 0u;
+                    tail_offsets(g, sc);
+#pragma unroll
+                    for (int k = 0; k < DC; ++k) syn ^= hb[g[k] >> 4];
+                    u0 |= syn & ALL;
                 }
                 u0 = __reduce_or_sync(kFull, u0);
                 if (lane == 0 && u0 != 0u) atomicOr(&s_unsat0, u0);
@@ -486,6 +517,38 @@ __global__ void __launch_bounds__(MAXT, MAXT > 320 ? 1 : 2) resident_vp(const Re
                 unsat |= syn;
             }
         }
+        if (BIG && ctail < mp) {                             // third pass: c2v_old comes back from the planes
+            uint32_t g[DC], sc[DC];
+            tail_offsets(g, sc);
+            float4 mg[DC], ol[DC];
+#pragma unroll
+            for (int k = 0; k < DC; ++k) {
+                mg[k] = *reinterpret_cast<const float4 *>(smem + g[k]);
+                ol[k] = *reinterpret_cast<const float4 *>(smem + sc[k]);
+            }
+            uint32_t sx[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int k = 0; k < DC; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float mv = (&mg[k].x)[j];
+                    sx[j] ^= f32_bits(mv);
+                    (&mg[k].x)[j] = __fsub_rn(mv, (&ol[k].x)[j]);
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a[DC], o[DC];
+#pragma unroll
+                for (int k = 0; k < DC; ++k) a[k] = (&mg[k].x)[j];
+                if (ALGO == ALGO_MSA) cn_msa_lean<DC>(a, o);
+                else cn_spa_sc<DC>(a, DC, o, p.sat_llr);
+#pragma unroll
+                for (int k = 0; k < DC; ++k) (&ol[k].x)[j] = o[k];
+            }
+#pragma unroll
+            for (int k = 0; k < DC; ++k) *reinterpret_cast<float4 *>(smem + sc[k]) = ol[k];
+            unsat |= (sx[0] >> 31) | ((sx[1] >> 31) << 1) | ((sx[2] >> 31) << 2) | ((sx[3] >> 31) << 3);
+        }
         unsat = __reduce_or_sync(kFull, unsat);
         if (lane == 0 && unsat != 0u) atomicOr(&s_unsat[par], unsat);
         __syncthreads();
@@ -504,7 +567,7 @@ __global__ void __launch_bounds__(MAXT, MAXT > 320 ? 1 : 2) resident_vp(const Re
 
         // ======================================= variable-node phase =======================================
 #pragma unroll
-        for (int ps = 0; ps < kResVnPasses; ++ps) {
+        for (int ps = 0; ps < VNP; ++ps) {
             const int item = tid + ps * T;
             if (IRR) {
                 if (item < np) {
