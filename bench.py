@@ -370,7 +370,7 @@ def main():
         eng.profile(False)
         return dict(ms=ms, launches=launches, prof=prof, iters=res["o"]["iters"].cpu().numpy(), x_hat=res["o"]["x_hat"].clone())
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and os.environ.get("LDPC_BENCH_NO_SAMPLER") != "1" else None
     main = measure(args.flags)
     resident = main["prof"]["vn_launches"] == 0          # the on-chip path is ONE kernel per decode
     ms, launches, prof, iters, x_hat = main["ms"], main["launches"], main["prof"], main["iters"], main["x_hat"]
@@ -492,16 +492,19 @@ def main():
     torch.cuda.synchronize()
     e_el = time.perf_counter() - t0
     e_launches = eng.launch_count - e_launch0
+    e_rank_ms = [1e3 * e_el / args.steps]
     if dist is not None:
-        t = torch.tensor([e_el], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_el = float(t.item())
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = e_el
+        dist.all_reduce(t)
+        e_rank_ms = [1e3 * float(v) / args.steps for v in t.tolist()]
+        e_el = float(t.max().item())
     assert (ith == iters).all() and bool((torch.from_numpy(xh).cuda() == x_hat).all()), "e2e result differs from device path"
     e2e = {"value": total_frames / e_el, "unit": UNIT, "h2d_bytes_per_step": int(Yh.nbytes),
            "d2h_bytes_per_step": int(xh.nbytes + ith.nbytes + rsh.nbytes), "ms_per_step": 1e3 * e_el / args.steps,
            "api": "Engine.decode_host -> ldpc_decode_host (pinned float32 y in; x_hat, iters, reason out)",
            "timer": "host perf_counter around blocking calls, max over ranks",
-           "host_cpus_bound": (len(numa_cpus) if numa_cpus else None)}
+           "ms_per_step_by_rank": e_rank_ms, "host_cpus_bound": (len(numa_cpus) if numa_cpus else None)}
 
     clocks = sampler.stop() if sampler is not None else None
     for rf in (roofline, spa["roofline"]):
