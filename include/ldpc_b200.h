@@ -80,6 +80,7 @@ extern "C" {
 #define LDPC_CN_REGISTER    8u   /* streaming path: use the register-staged check-node sweep instead of the
                                     bulk-async (TMA) staged one (A/B measurements; it is also the fallback for
                                     check degrees > 8) */
+#define LDPC_HOST_ASYNC    16u   /* ldpc_decode_host: return once the work is enqueued; ldpc_host_sync() completes it */
 
 /* channel kinds for ldpc_decode_host / ldpc_channel_llr */
 #define LDPC_CH_PRIORS 0   /* input already is the prior LLR (bpa.*.decode(y, priors)) */
@@ -179,11 +180,17 @@ int ldpc_debug_step(ldpc_t *h, int algo, int dtype, int which, int B,
  *            ignored (uint8) for BSC and BEC.  Pinned memory makes the copies asynchronous.
  *   x_hat    host [B,n] uint8;  iters host [B] int32;  reason host [B] uint8 or NULL
  *   chunk    frames per pipeline stage (0 = default)
- * Device staging buffers are owned by the handle and reused across calls. */
+ * Device staging buffers are owned by the handle and reused across calls (in stream order). */
 int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
                      const void *y, int y_dtype, int B, int max_iter, int iter_cap,
                      uint8_t *x_hat, int32_t *iters, uint8_t *reason,
                      int chunk, unsigned flags);
+
+/* A stream of batches: with LDPC_HOST_ASYNC in `flags`, ldpc_decode_host returns as soon as every chunk is enqueued on
+ * the handle's internal streams, so the next call's copies overlap this call's tail (no pipeline ramp between batches).
+ * The host buffers of every such call (pinned) must stay valid and untouched until ldpc_host_sync returns, which waits
+ * for everything enqueued so far.  Results are the blocking call's. */
+int ldpc_host_sync(ldpc_t *h);
 
 /* Per-launch timing of the two sweeps, for bench.py's roofline.  While enabled, ldpc_decode records CUDA
  * events around every check-node and variable-node sweep launch on the stream it runs on;

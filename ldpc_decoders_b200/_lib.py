@@ -12,11 +12,12 @@ CH_PRIORS, CH_BSC, CH_BIAWGN, CH_BEC = 0, 1, 2, 3
 PATH_AUTO, PATH_STREAMING, PATH_RESIDENT = 0, 1, 2
 SPA_ROBUST = 4
 CN_REGISTER = 8
+HOST_ASYNC = 16
 REASONS = {0: "decoded", 1: "maximum", 2: "stopping", 4: "cap"}
 
 # every symbol include/ldpc_b200.h declares
 SYMBOLS = ("ldpc_abi_version", "ldpc_create", "ldpc_destroy", "ldpc_last_error", "ldpc_workspace_bytes",
-           "ldpc_decode", "ldpc_decode_channel", "ldpc_llr_bsc", "ldpc_llr_biawgn", "ldpc_debug_step", "ldpc_decode_host",
+           "ldpc_decode", "ldpc_decode_channel", "ldpc_llr_bsc", "ldpc_llr_biawgn", "ldpc_debug_step", "ldpc_decode_host", "ldpc_host_sync",
            "ldpc_launch_count", "ldpc_profile_enable", "ldpc_profile_read", "ldpc_resident_frames", "ldpc_resident_plan", "ldpc_resident_kernel", "ldpc_channel_generate", "ldpc_count_errors")
 
 
@@ -70,6 +71,8 @@ def load():
     L.ldpc_channel_generate.argtypes = [vp, i32, dbl, vp, ctypes.c_ulonglong, ctypes.c_ulonglong, i32, vp, vp]
     L.ldpc_count_errors.restype = i32
     L.ldpc_count_errors.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.ldpc_host_sync.restype = i32
+    L.ldpc_host_sync.argtypes = [vp]
     L.ldpc_resident_kernel.restype = ctypes.c_char_p
     L.ldpc_resident_kernel.argtypes = [vp]
     L.ldpc_resident_plan.restype = i32

@@ -330,6 +330,7 @@ struct HostSlot {
 struct HostStage {
     static constexpr int kSlots = 3;
     HostSlot slot[kSlots];
+    int next = 0;               // round-robin position, carried across calls so that back-to-back batches interleave
     int *h_flag = nullptr;      // pinned, used by the unlimited-iteration poll
 };
 
@@ -1237,7 +1238,7 @@ int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
     chunk = std::min(chunk, B);
 
     HostStage *st = h->stage;
-    int idx = 0;
+    int idx = st->next;
     for (int b0 = 0; b0 < B; b0 += chunk, ++idx) {
         const int nb = std::min(chunk, B - b0);
         HostSlot &sl = st->slot[idx % HostStage::kSlots];
@@ -1266,7 +1267,18 @@ int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
         CUDA_TRY(h, cudaMemcpyAsync(iters + b0, sl.d_it, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
         if (reason) CUDA_TRY(h, cudaMemcpyAsync(reason + b0, sl.d_rs, (size_t)nb, cudaMemcpyDeviceToHost, sl.stream));
     }
+    st->next = idx % HostStage::kSlots;
+    if (flags & LDPC_HOST_ASYNC) return LDPC_OK;
     for (auto &sl : st->slot) CUDA_TRY(h, cudaStreamSynchronize(sl.stream));
+    return LDPC_OK;
+}
+
+int ldpc_host_sync(ldpc_t *h)
+{
+    if (!h) return LDPC_EINVAL;
+    if (!h->stage) return LDPC_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (auto &sl : h->stage->slot) CUDA_TRY(h, cudaStreamSynchronize(sl.stream));
     return LDPC_OK;
 }
 

@@ -234,12 +234,18 @@ class Engine:
 
     # ------------------------------------------------------------------ host-buffer decode (e2e path)
     def decode_host(self, channel, algo, dtype, param, y, max_iter=10, iter_cap=0, chunk=0, flags=0,
-                    x_hat=None, iters=None, reason=None):
+                    x_hat=None, iters=None, reason=None, wait=True):
         """Decode a batch held in host memory (numpy); H2D / decode / D2H are pipelined in the library.
 
         y [B, n]: uint8 for BSC/BEC, float32/float64 for BIAWGN / PRIORS.  Pinned arrays
         (``pinned_empty``) make the copies asynchronous.  Returns numpy (x_hat, iters, reason).
+        wait=False (a stream of batches): returns once the work is enqueued, so the next call overlaps this one's
+        tail; y and the output arrays must be pinned, caller-provided and left alone until ``host_sync()``.
         """
+        if not wait:
+            if x_hat is None or iters is None or reason is None:
+                raise ValueError("wait=False needs caller-provided (pinned) output arrays")
+            flags |= _lib.HOST_ASYNC
         t = self.tables
         y = np.ascontiguousarray(y)
         if y.ndim != 2 or y.shape[1] != t.n:
@@ -264,6 +270,10 @@ class Engine:
                                        reason.ctypes.data, int(chunk), flags)
         _lib.check(self.handle, rc)
         return x_hat, iters, reason
+
+    def host_sync(self):
+        """Wait for every decode_host(..., wait=False) enqueued so far (ldpc_host_sync)."""
+        _lib.check(self.handle, self.lib.ldpc_host_sync(self.handle))
 
     # ------------------------------------------------------------------ front ends and the isolated sweep
     def llr_bsc(self, p_llr, y, dtype, stream=None):

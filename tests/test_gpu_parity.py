@@ -367,6 +367,29 @@ def test_device_and_host_entry_points_agree(mods):
     assert (pri.cpu().numpy() == ref).all()
 
 
+def test_host_entry_point_as_a_stream_of_batches(mods):
+    """LDPC_HOST_ASYNC: several batches submitted back to back and completed by one ldpc_host_sync give the blocking
+    call's results, each in its own output buffers (stream order keeps the handle's staging buffers consistent)."""
+    lib, E = mods["lib"], mods["engine"]
+    tab = tables(mods, "1200_3_6_rand_ldpc_1")
+    eng = E.engine_for(tab)
+    nv = 10 ** (-2.0 / 10)
+    sets = []
+    for k, B in enumerate((5000, 777, 9000)):
+        Y = E.pinned_empty((B, tab.n), np.float32)
+        Y[...] = G.channel_send("biawgn", 2.0, np.ones((B, tab.n), np.int64), 60 + k).astype(np.float32)
+        sets.append((Y, E.pinned_empty((B, tab.n), np.uint8), E.pinned_empty((B,), np.int32), E.pinned_empty((B,), np.uint8)))
+    ref = [tuple(a.copy() for a in eng.decode_host(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, Y, max_iter=10, chunk=1024)) for Y, _, _, _ in sets]
+    for Y, xh, it, rs in sets:
+        xh[...] = 7
+        eng.decode_host(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, Y, max_iter=10, chunk=1024, x_hat=xh, iters=it, reason=rs, wait=False)
+    eng.host_sync()
+    for (Y, xh, it, rs), (rx, ri, rr) in zip(sets, ref):
+        assert (xh == rx).all() and (it == ri).all() and (rs == rr).all()
+    with pytest.raises(ValueError):
+        eng.decode_host(lib.CH_BIAWGN, lib.MSA, lib.F32, nv, sets[0][0], max_iter=10, wait=False)
+
+
 @pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_10", "7_4_hamming",
                                   "512_3_6_rand_ldpc_1", "margulis", "12_3_4_ldpc"])
 def test_resident_and_streaming_paths_agree(mods, code):
