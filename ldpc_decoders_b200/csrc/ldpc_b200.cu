@@ -49,6 +49,10 @@ int fail(ldpc_t *h, int code, const std::string &msg)
         (h)->launches++;                                                                            \
     } while (0)
 
+// Word-wise tiles need 4-byte aligned symbol rows (io_kernels.cuh).
+inline bool rows_word_aligned(const void *base, int n) { return (n % 4) == 0 && (reinterpret_cast<uintptr_t>(base) & 3u) == 0; }
+inline dim3 tile_grid(int n, int wpr) { return dim3((unsigned)((n + kTileVars - 1) / kTileVars), (unsigned)((wpr + 7) / 8), 1); }
+
 int check_launch(ldpc_t *h, const char *what)
 {
     cudaError_t e = cudaPeekAtLastError();
@@ -437,7 +441,8 @@ int decode_bp_stream(ldpc_t *h, int algo, const InSpec &in, int B, int max_iter,
     }
 
     const dim3 egrid((t.n + 31) / 32, L.wpr), eblock(32, 8);
-    LAUNCH(h, emit_words, egrid, eblock, s, p.xbits, (const uint32_t *)nullptr, x_hat, B, t.n, L.wpr);
+    if (rows_word_aligned(x_hat, t.n)) LAUNCH(h, emit_words_tiled, tile_grid(t.n, L.wpr), 256, s, p.xbits, (const uint32_t *)nullptr, x_hat, B, t.n, L.wpr);
+    else LAUNCH(h, emit_words, egrid, eblock, s, p.xbits, (const uint32_t *)nullptr, x_hat, B, t.n, L.wpr);
     LAUNCH(h, emit_status, (B + 255) / 256, 256, s, p.iters, p.act, (const uint32_t *)nullptr, iters, reason, B,
            max_iter > 0 ? LDPC_REASON_MAXIMUM : LDPC_REASON_CAP);
     if (marg_out) {
@@ -481,7 +486,8 @@ int decode_bec_stream(ldpc_t *h, const uint8_t *y, int B, int max_iter, int iter
 
     CUDA_TRY(h, cudaMemsetAsync(p.changed, 0, (size_t)((char *)p.iters - (char *)p.changed), s));   // changed, haser, stopped
     const dim3 igrid((t.n + 31) / 32, L.wpr), iblock(32, 8);
-    LAUNCH(h, ingest_bec, igrid, iblock, s, y, pnz, ppos, p.xe, p.xv, p.haser, B, t.n, L.wpr);
+    if (rows_word_aligned(y, t.n)) LAUNCH(h, ingest_bec_tiled, tile_grid(t.n, L.wpr), 256, s, y, pnz, ppos, p.xe, p.xv, p.haser, B, t.n, L.wpr);
+    else LAUNCH(h, ingest_bec, igrid, iblock, s, y, pnz, ppos, p.xe, p.xv, p.haser, B, t.n, L.wpr);
     LAUNCH(h, init_flags, (L.Bp + 255) / 256, 256, s, p.act, (uint32_t *)nullptr, p.iters, B, L.Bp, L.wpr, 0);
 
     const int gx = (L.wpr + 127) / 128;
@@ -529,7 +535,8 @@ int decode_bec_stream(ldpc_t *h, const uint8_t *y, int B, int max_iter, int iter
     if (it == limit)    // account the last round; frames still active after it hit the bound
         LAUNCH(h, bec_book, book_blocks, 256, s, p.act, p.changed, p.haser, p.stopped, p.iters, L.wpr, 0, 1, any_active);
 
-    LAUNCH(h, emit_words, igrid, iblock, s, p.xv, p.xe, x_hat, B, t.n, L.wpr);
+    if (rows_word_aligned(x_hat, t.n)) LAUNCH(h, emit_words_tiled, tile_grid(t.n, L.wpr), 256, s, p.xv, p.xe, x_hat, B, t.n, L.wpr);
+    else LAUNCH(h, emit_words, igrid, iblock, s, p.xv, p.xe, x_hat, B, t.n, L.wpr);
     LAUNCH(h, emit_status, (B + 255) / 256, 256, s, p.iters, p.act, p.stopped, iters, reason, B,
            max_iter > 0 ? LDPC_REASON_MAXIMUM : LDPC_REASON_CAP);
     return check_launch(h, "decode_bec_stream");
