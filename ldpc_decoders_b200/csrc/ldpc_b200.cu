@@ -136,7 +136,7 @@ struct BecLayout {
 BecLayout bec_layout(const Tables &t, int B)
 {
     BecLayout L;
-    L.Bp = (B + 31) / 32 * 32;
+    L.Bp = (B + 127) / 128 * 128;                               // wpr % 4 == 0: the sweeps may take four words per thread
     L.wpr = L.Bp / 32;
     size_t b = 0;
     b += 2 * align_up((size_t)t.E * L.wpr * 4, 256);            // mnz, mpos
@@ -490,7 +490,11 @@ int decode_bec_stream(ldpc_t *h, const uint8_t *y, int B, int max_iter, int iter
     else LAUNCH(h, ingest_bec, igrid, iblock, s, y, pnz, ppos, p.xe, p.xv, p.haser, B, t.n, L.wpr);
     LAUNCH(h, init_flags, (L.Bp + 255) / 256, 256, s, p.act, (uint32_t *)nullptr, p.iters, B, L.Bp, L.wpr, 0);
 
-    const int gx = (L.wpr + 127) / 128;
+    // four words (128 frames) per thread once that still gives every SM two full loads of threads, else one word
+    // (LDPC(1200,3,6): 96 against 80 M frames/s at 131072 frames, but 43 against 72 M at 32768)
+    const bool wide = (long long)(L.wpr / 4) * std::min(t.m, t.n) >= (long long)h->sm_count * 4096;
+    const int wx = wide ? L.wpr / 4 : L.wpr;
+    const int gx = (wx + 127) / 128;
     const int target = h->sm_count * 32;
     auto grid_for = [&](int items, int *per) {
         int gy = std::max(1, std::min(items, target / gx));
@@ -524,12 +528,18 @@ int decode_bec_stream(ldpc_t *h, const uint8_t *y, int B, int max_iter, int iter
         p.first = (it == 0);
         p.per_cta = cpc;
         ProfEvent *pe = prof_begin(h, 0, s);
-        LAUNCH(h, bec_cn, cgrid, 128, s, p);
+        if (wide) LAUNCH(h, bec_cn<W4>, cgrid, 128, s, p);
+        else LAUNCH(h, bec_cn<uint32_t>, cgrid, 128, s, p);
         prof_end(pe, s);
         p.per_cta = vpc;
         pe = prof_begin(h, 1, s);
-        if (t.max_dv <= 14) LAUNCH(h, (bec_vn<5>), vgrid, 128, s, p);
-        else LAUNCH(h, (bec_vn<8>), vgrid, 128, s, p);
+        if (wide) {
+            if (t.max_dv <= 14) LAUNCH(h, (bec_vn<5, W4>), vgrid, 128, s, p);
+            else LAUNCH(h, (bec_vn<8, W4>), vgrid, 128, s, p);
+        } else {
+            if (t.max_dv <= 14) LAUNCH(h, (bec_vn<5, uint32_t>), vgrid, 128, s, p);
+            else LAUNCH(h, (bec_vn<8, uint32_t>), vgrid, 128, s, p);
+        }
         prof_end(pe, s);
     }
     if (it == limit)    // account the last round; frames still active after it hit the bound

@@ -423,48 +423,51 @@ LDPC_HD float llr_biawgn_f32(double y, double noise_var, double inv_noise_var)
 // BEC, 32 frames per word.  A message in {-1,0,+1} is two bit planes: nz (|msg|) and pos (msg > 0),
 // pos is a subset of nz.  Literal restatement of bec.py:100-119 in bit-sliced integer arithmetic.
 // ---------------------------------------------------------------------------------------------
-struct BecCnAcc {                 // per check: erasure count saturating at 2, parity of the +1 votes
-    uint32_t any, two, par;
-    LDPC_HD void init() { any = 0u; two = 0u; par = 0u; }
-    LDPC_HD void push(uint32_t nz, uint32_t pos) {
-        const uint32_t er = ~nz;                 // 1 - |v2c|  (bec.py:100)
-        two |= any & er;
-        any |= er;
-        par ^= pos;                              // (v2c > 0) summed mod 2 (bec.py:110,112)
+// U = the machine word(s) a thread owns: uint32_t (32 frames) or a pack of four (stream_bec.cuh, 128 frames); only
+// the bitwise operators are used, so any type providing them works.
+template <typename U> struct BecCnAccT {   // per check: erasure count saturating at 2, parity of the +1 votes
+    U any, two, par;
+    LDPC_HD void init() { any = U(); two = U(); par = U(); }
+    LDPC_HD void push(U nz, U pos) {
+        const U er = ~nz;                        // 1 - |v2c|  (bec.py:100)
+        two = two | (any & er);
+        any = any | er;
+        par = par ^ pos;                         // (v2c > 0) summed mod 2 (bec.py:110,112)
     }
     // sums == 0: echo v2c; sums > 1: 0; sums == 1: only the erased edge, value 2*(incoming%2)-1  (bec.py:105,112)
-    LDPC_HD void out(uint32_t nz, uint32_t pos, uint32_t &onz, uint32_t &opos) const {
-        const uint32_t zero = ~any, one = any & ~two, er = ~nz;
+    LDPC_HD void out(U nz, U pos, U &onz, U &opos) const {
+        const U zero = ~any, one = any & ~two, er = ~nz;
         onz = (zero & nz) | (one & er);
         opos = (zero & pos) | (one & er & par);
     }
 };
+using BecCnAcc = BecCnAccT<uint32_t>;
 
 // Bit-sliced two's-complement integer of NB bits per frame (range covers |prior + sum of dv votes|).
-template <int NB> struct BsInt {
-    uint32_t b[NB];
-    LDPC_HD void set_ternary(uint32_t nz, uint32_t pos) {   // +1 = 0..01, -1 = 1..11, 0 = 0
-        const uint32_t neg = nz & ~pos;
+template <int NB, typename U = uint32_t> struct BsInt {
+    U b[NB];
+    LDPC_HD void set_ternary(U nz, U pos) {      // +1 = 0..01, -1 = 1..11, 0 = 0
+        const U neg = nz & ~pos;
         b[0] = nz;
 #pragma unroll
         for (int i = 1; i < NB; ++i) b[i] = neg;
     }
-    LDPC_HD void add_ternary(uint32_t nz, uint32_t pos) {
-        const uint32_t neg = nz & ~pos;
-        uint32_t carry = b[0] & nz;
-        b[0] ^= nz;
+    LDPC_HD void add_ternary(U nz, U pos) {
+        const U neg = nz & ~pos;
+        U carry = b[0] & nz;
+        b[0] = b[0] ^ nz;
 #pragma unroll
         for (int i = 1; i < NB; ++i) {
-            const uint32_t x = b[i];
+            const U x = b[i];
             b[i] = x ^ neg ^ carry;
             carry = (x & neg) | (carry & (x ^ neg));
         }
     }
-    LDPC_HD void sub_ternary(uint32_t nz, uint32_t pos) { add_ternary(nz, nz & ~pos); }   // -(msg): swap +1/-1
-    LDPC_HD void sign(uint32_t &nz, uint32_t &pos) const {                                 // np.sign (bec.py:116,119)
-        uint32_t any = 0u;
+    LDPC_HD void sub_ternary(U nz, U pos) { add_ternary(nz, nz & ~pos); }   // -(msg): swap +1/-1
+    LDPC_HD void sign(U &nz, U &pos) const {                                // np.sign (bec.py:116,119)
+        U any = U();
 #pragma unroll
-        for (int i = 0; i < NB; ++i) any |= b[i];
+        for (int i = 0; i < NB; ++i) any = any | b[i];
         nz = any;
         pos = any & ~b[NB - 1];
     }

@@ -159,6 +159,31 @@ def test_bec_bit_exact_many_frames(mods, code, p, mi):
     assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all()
 
 
+def test_bec_wide_and_narrow_sweeps_agree(mods):
+    """Above ~129 k frames of an n = 1200 code the erasure sweeps take four flag words (128 frames) per thread
+    (stream_bec.cuh, W4); below, one.  The same frames decoded in one large batch and in four small ones must give
+    identical words, iteration counts and exit reasons (and the small batches are held to the oracle elsewhere)."""
+    torch, lib = mods["torch"], mods["lib"]
+    tab = tables(mods, "1200_3_6_rand_ldpc_1")
+    eng = mods["engine"].engine_for(tab)
+    B = 4 * 33000 + 17
+    g = torch.Generator(device="cuda").manual_seed(11)
+    r = torch.rand((B, tab.n), generator=g, device="cuda")
+    y = torch.where(r < 0.41, 2, 0).to(torch.uint8)
+    y[5] = 0
+    y[B - 1, ::2] = 2
+    big = eng.decode_device_channel(lib.CH_BEC, lib.BEC, lib.F32, 0.0, y, max_iter=100)
+    big = {k: v.clone() for k, v in big.items() if v is not None}
+    for lo in range(0, B, 33000):
+        part = eng.decode_device_channel(lib.CH_BEC, lib.BEC, lib.F32, 0.0, y[lo:lo + 33000].contiguous(), max_iter=100)
+        for k in ("x_hat", "iters", "reason"):
+            assert bool((part[k] == big[k][lo:lo + 33000]).all()), k
+    og = ograph("1200_3_6_rand_ldpc_1")
+    ref = O.bec_decode(og, y[:3000].cpu().numpy(), max_iter=100, nthreads=8)
+    assert (big["iters"][:3000].cpu().numpy() == ref["iters"]).all() and (big["x_hat"][:3000].cpu().numpy() == ref["x_hat"]).all()
+    assert (big["reason"][:3000].cpu().numpy() == ref["reason"]).all()
+
+
 def test_bec_arbitrary_symbols(mods):
     rng = np.random.RandomState(3)
     for code in ("7_4_hamming", "12_3_4_ldpc", "1200_rho_x5_rand_ldpc_10"):
