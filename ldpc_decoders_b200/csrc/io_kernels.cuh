@@ -23,34 +23,45 @@ template <typename Tin, typename T, int MODE> __device__ __forceinline__ T llr_m
 
 // src [B][n] (frame-major) -> prior [n][Bp]; frames >= B are zero-filled.
 // MODE == IN_BSC additionally packs the hard bits y into xbits [n][wpr].
-// grid (ceil(n/32), Bp/32), block (32, 8).
+// A CTA transposes kIngestTiles 32 x 32 tiles side by side along the variable axis: all their loads are issued before
+// the barrier (16 per thread in flight instead of 4), which is what this latency-bound copy needs.
+// grid (ceil(n / (32 * kIngestTiles)), Bp/32), block (32, 8).
+constexpr int kIngestTiles = 4;
 template <typename Tin, typename T, int MODE>
-__global__ void ingest_priors(const Tin *__restrict__ src, T *__restrict__ prior, uint32_t *__restrict__ xbits,
-                              int B, int n, int Bp, int wpr, double param)
+__global__ void __launch_bounds__(256) ingest_priors(const Tin *__restrict__ src, T *__restrict__ prior, uint32_t *__restrict__ xbits,
+                                                     int B, int n, int Bp, int wpr, double param)
 {
-    __shared__ T tile[32][33];
-    __shared__ uint8_t hard[32][33];
-    const int v0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const int f = f0 + r, v = v0 + threadIdx.x;
-        T val = (T)0;
-        uint8_t hb = 0;
-        if (f < B && v < n) {
-            const Tin y = src[(size_t)f * n + v];
-            val = llr_map<Tin, T, MODE>(y, param);
-            if (MODE == IN_BSC) hb = (uint8_t)(y != (Tin)0);
+    __shared__ T tile[kIngestTiles][32][33];
+    __shared__ uint8_t hard[MODE == IN_BSC ? kIngestTiles : 1][32][33];
+    const int vb = blockIdx.x * 32 * kIngestTiles, f0 = blockIdx.y * 32;
+#pragma unroll
+    for (int t = 0; t < kIngestTiles; ++t) {
+#pragma unroll
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const int f = f0 + r, v = vb + 32 * t + threadIdx.x;
+            T val = (T)0;
+            uint8_t hb = 0;
+            if (f < B && v < n) {
+                const Tin y = src[(size_t)f * n + v];
+                val = llr_map<Tin, T, MODE>(y, param);
+                if (MODE == IN_BSC) hb = (uint8_t)(y != (Tin)0);
+            }
+            tile[t][r][threadIdx.x] = val;
+            if (MODE == IN_BSC) hard[t][r][threadIdx.x] = hb;
         }
-        tile[r][threadIdx.x] = val;
-        if (MODE == IN_BSC) hard[r][threadIdx.x] = hb;
     }
     __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const int v = v0 + r, f = f0 + threadIdx.x;
-        if (v < n) {                                                 // warp-uniform
-            prior[(size_t)v * Bp + f] = tile[threadIdx.x][r];
-            if (MODE == IN_BSC) {
-                const uint32_t w = __ballot_sync(kFull, hard[threadIdx.x][r] != 0);
-                if (threadIdx.x == 0) xbits[(size_t)v * wpr + (f0 >> 5)] = w;
+#pragma unroll
+    for (int t = 0; t < kIngestTiles; ++t) {
+#pragma unroll
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const int v = vb + 32 * t + r, f = f0 + threadIdx.x;
+            if (v < n) {                                                 // warp-uniform
+                prior[(size_t)v * Bp + f] = tile[t][threadIdx.x][r];
+                if (MODE == IN_BSC) {
+                    const uint32_t w = __ballot_sync(kFull, hard[t][threadIdx.x][r] != 0);
+                    if (threadIdx.x == 0) xbits[(size_t)v * wpr + (f0 >> 5)] = w;
+                }
             }
         }
     }

@@ -275,7 +275,8 @@ int ingest_bp(ldpc_t *h, const InSpec &in, T *prior, uint32_t *xbits, int B, con
               bool *have_hard)
 {
     const Tables &t = h->t;
-    const dim3 grid((t.n + 31) / 32, L.Bp / 32), block(32, 8);
+    const dim3 pgrid((t.n + 31) / 32, L.Bp / 32), block(32, 8);                       // pack_hard: one 32 x 32 tile per CTA
+    const dim3 grid((t.n + 32 * kIngestTiles - 1) / (32 * kIngestTiles), L.Bp / 32);  // ingest_priors: kIngestTiles tiles per CTA
     *have_hard = false;
     switch (in.channel) {
     case LDPC_CH_PRIORS:
@@ -284,7 +285,7 @@ int ingest_bp(ldpc_t *h, const InSpec &in, T *prior, uint32_t *xbits, int B, con
         else
             LAUNCH(h, (ingest_priors<float, T, IN_COPY>), grid, block, s, (const float *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, 0.0);
         if (in.y_hard) {
-            LAUNCH(h, pack_hard, grid, block, s, in.y_hard, xbits, B, t.n, L.wpr);
+            LAUNCH(h, pack_hard, pgrid, block, s, in.y_hard, xbits, B, t.n, L.wpr);
             *have_hard = true;
         }
         break;
