@@ -200,7 +200,8 @@ int ldpc_profile_enable(ldpc_t *h, int on);
 int ldpc_profile_read(ldpc_t *h, double *cn_ms, unsigned long long *cn_launches,
                       double *vn_ms, unsigned long long *vn_launches);
 
-/* Frames a CTA of the on-chip path (LDPC_PATH_RESIDENT) keeps in shared memory for this code, or 0 when the code does
+/* Frames a CTA of the float32 on-chip path (LDPC_PATH_RESIDENT) keeps in shared memory for this code (the float64
+ * min-sum kernel keeps half as many), or 0 when the code does
  * not fit on chip (then LDPC_PATH_AUTO streams and LDPC_PATH_RESIDENT is refused with LDPC_EUNSUPPORTED). */
 int ldpc_resident_frames(const ldpc_t *h);
 
