@@ -259,7 +259,8 @@ def extra_workloads(torch, lib, eng_mod, Tables, peak):
         out.append({"workload": "irregular LDPC n=1200 (1200_rho_x5_rand_ldpc_1) BSC p=0.06 %s f32, max_iter 10, cw=0 (%s)"
                                 % (nm, eng.resident_kernel or "streaming"),
                     "value": frames * 3 / (ms / 1e3), "unit": UNIT, "mean_iters": float(iters.mean()),
-                    "edge_updates_per_s": 2 * irr.E * float(iters.sum()) * 3 / (ms / 1e3)})
+                    "edge_updates_per_s": 2 * irr.E * float(iters.sum()) * 3 / (ms / 1e3),
+                    "path": ("on-chip (%s)" % eng.resident_kernel) if eng.resident_kernel else "streaming"})
     # Monte-Carlo round entirely on the GPU (on-device Philox channel + decode + error count): what sim.py --noise device runs
     eng = eng_mod.engine_for(tab)
     frames = 32768
