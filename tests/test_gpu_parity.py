@@ -243,6 +243,59 @@ def test_max_iter_sweep_irregular_bsc(mods, mi):
     assert (iters[fin] == ref["iters"][fin]).all() and (x_hat[fin] == ref["x_hat"][fin]).all()
 
 
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_random_irregular_codes_fuzz(mods, seed):
+    """Randomly drawn irregular codes (codes.random_irregular: lengths that are not multiples of 4 or 8, variables of
+    degree 0..8, checks that lost edges to cancellation) through every kernel family: on-chip float32 / float64
+    min-sum and erasure decoding against the oracle, on-chip against streaming for sum-product."""
+    torch, lib = mods["torch"], mods["lib"]
+    from ldpc_decoders_b200 import codes
+    rng = np.random.RandomState(1000 + seed)
+    n = int(rng.randint(30, 900))
+    prof = {}
+    left = n
+    for d, frac in ((2, .55), (3, .2), (4, .08), (7, .06), (8, .04), (1, .02), (0, .01), (5, .02), (6, .02)):
+        c = min(left, int(round(frac * n * rng.uniform(.6, 1.4))))
+        prof[d] = c
+        left -= c
+    prof[2] += left
+    short = (-sum(d * c for d, c in prof.items())) % 6
+    if short:
+        prof[2] -= 1
+        prof[2 + short] = prof.get(2 + short, 0) + 1
+    tab = codes.random_irregular(prof, 6, seed=seed).tables
+    if tab.check_degrees.min() < 2:
+        pytest.skip("a check lost all but one of its edges: not a code the on-chip path takes")
+    og = O.Graph(tab.m, tab.n, tab.edge_chk.astype(np.int64), tab.edge_var.astype(np.int64))
+    eng = mods["engine"].engine_for(tab)
+    assert eng.resident_kernel == "resident_vp"
+    B = 300
+    zeros = np.zeros((B, tab.n), np.int64)
+    Y = G.channel_send("biawgn", 3.0, zeros, 4000 + seed)
+    nv = 10 ** (-3.0 / 10)
+    for dt, ldt in ((np.float32, lib.F32), (np.float64, lib.F64)):
+        ref = O.bp_decode(og, O.MSA, O.llr_biawgn(3.0, Y).astype(dt), max_iter=20, nthreads=4)
+        out = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, ldt, nv, torch.from_numpy(Y).cuda(), max_iter=20, flags=lib.PATH_RESIDENT)
+        assert (out["iters"].cpu().numpy() == ref["iters"]).all() and (out["x_hat"].cpu().numpy() == ref["x_hat"]).all()
+        assert (out["reason"].cpu().numpy() == ref["reason"]).all()
+    Yb = G.channel_send("bsc", .03, zeros, 5000 + seed).astype(np.uint8)
+    Yb[3] = 0
+    L = float(np.log(1 - .03) - np.log(.03))
+    ref = O.bp_decode(og, O.MSA, O.llr_bsc(.03, Yb).astype(np.float32), y_hard=Yb, max_iter=20, nthreads=4)
+    out = eng.decode_device_channel(lib.CH_BSC, lib.MSA, lib.F32, L, torch.from_numpy(Yb).cuda(), max_iter=20, flags=lib.PATH_RESIDENT)
+    assert (out["iters"].cpu().numpy() == ref["iters"]).all() and (out["x_hat"].cpu().numpy() == ref["x_hat"]).all()
+    for ch, prm, y in ((lib.CH_BIAWGN, nv, torch.from_numpy(Y.astype(np.float32)).cuda()), (lib.CH_BSC, L, torch.from_numpy(Yb).cuda())):
+        a = eng.decode_device_channel(ch, lib.SPA, lib.F32, prm, y, max_iter=20, flags=lib.PATH_STREAMING)
+        a = {k: (v.clone() if v is not None else None) for k, v in a.items()}
+        b = eng.decode_device_channel(ch, lib.SPA, lib.F32, prm, y, max_iter=20, flags=lib.PATH_RESIDENT)
+        assert bool((a["iters"] == b["iters"]).all()) and bool((a["x_hat"] == b["x_hat"]).all()) and bool((a["reason"] == b["reason"]).all())
+    Ye = G.channel_send("bec", .35, zeros, 6000 + seed).astype(np.uint8)
+    ref = O.bec_decode(og, Ye, max_iter=50, nthreads=4)
+    out = eng.decode_device_channel(lib.CH_BEC, lib.BEC, lib.F32, 0.0, torch.from_numpy(Ye).cuda(), max_iter=50)
+    assert (out["iters"].cpu().numpy() == ref["iters"]).all() and (out["x_hat"].cpu().numpy() == ref["x_hat"]).all()
+    assert (out["reason"].cpu().numpy() == ref["reason"]).all()
+
+
 # --------------------------------------------------------------------------------------------- SPA
 @pytest.mark.parametrize("case", G.spa_tf(), ids=lambda c: c[0]["slot"])
 def test_spa_teacher_forced(mods, case):
