@@ -735,11 +735,15 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
                      vp_smem_layout(np, 3, 0, 0).total > resident_budget(h) &&
                      vp_smem_layout(np, 3, 0, 0, false).total <= h->smem_optin - 1024 &&
                      mp <= (kResCnPasses + 1) * kVpBigThreads && np <= kVpBigVnPasses * kVpBigThreads;
-    if (!big) {
-        if ((long long)r.planes * mp * Q + 1 > 65535) return LDPC_OK;                // c2v float4 index must fit 16 bits
-        if (((long long)np * Q + 1) * 16 > 65535) return LDPC_OK;                    // marg byte offset must fit 16 bits
-        if (resident_smem_layout(Q, np, mp, r.planes, vtw, 0, 0).total > resident_budget(h)) return LDPC_OK;
-    }
+    // the check-major kernel (resident_bp) needs more shared memory than the variable-plane layouts (its edge table):
+    // it is only the fallback, so its limits must not keep a code off the variable-plane kernels (n = 1280 fits those only)
+    const bool bp_fits = (long long)r.planes * mp * Q + 1 <= 65535 &&                 // c2v float4 index must fit 16 bits
+                         ((long long)np * Q + 1) * 16 <= 65535 &&                     // marg byte offset must fit 16 bits
+                         resident_smem_layout(Q, np, mp, r.planes, vtw, 0, 0).total <= resident_budget(h);
+    const bool vp_cand = r.regular36 && !lay_check && np % 4 == 0 && np * 16 <= 0xfff0 &&
+                         (big || vp_smem_layout(np, 3, 0, 0).total <= resident_budget(h));
+    const bool vx_cand = !r.regular36 && !lay_check && t.max_dc <= 6 && t.max_dv <= 8;
+    if (!bp_fits && !vp_cand && !vx_cand) return LDPC_OK;
     // threads: check items (mp * Q) in at most 2 passes, variable items (np * Q) in at most 4
     const int citems = mp * Q, vitems = np * Q, maxT = big ? kVpBigThreads : res_max_threads(Q);
     int T = std::max((citems + kResCnPasses - 1) / kResCnPasses, (vitems + kResVnPasses - 1) / kResVnPasses);
@@ -760,8 +764,7 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
     cudaError_t e = cudaSuccess;
 
     // ---- variable-plane variant for regular (3,6) codes: its own placement per edge order (res_layout.h, vn_contiguous)
-    if (r.regular36 && np % 4 == 0 && np * 16 <= 0xfff0 && !lay_check &&
-        (big || vp_smem_layout(np, 3, 0, 0).total <= resident_budget(h))) {
+    if (vp_cand) {
         std::vector<int> slot((size_t)t.E, 0);
         for (int v = 0; v < t.n; ++v)
             for (int p0 = var_ptr[v], k = 0; p0 < var_ptr[v + 1]; ++p0, ++k) slot[var_edges[p0]] = k;
@@ -786,7 +789,7 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
     }
 
     // ---- the same layout for irregular codes (resident_vp IRR = true): check degrees 2..6, variable degrees 0..8
-    if (!r.regular36 && t.max_dc <= 6 && t.max_dv <= 8 && !lay_check) {
+    if (vx_cand) {
         bool fits = true;
         for (int tb = 0; tb < 2 && fits && e == cudaSuccess; ++tb) {
             ResPlanner pl2(t.n, t.m, t.E, chk_ptr, edge_var, var_ptr, var_edges, G);
@@ -815,6 +818,7 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
         }
     }
 
+    if (!bp_fits) return LDPC_OK;
     ResPlanner planner(t.n, t.m, t.E, chk_ptr, edge_var, var_ptr, var_edges, G);
     const ResLayout L = planner.plan(12345u, h->plan_effort);
     const long pl[7] = {L.cn_ideal, L.cn_file, L.cn_plan_natural, L.cn_plan, L.vn_ideal, L.vn_file, L.vn_plan};
