@@ -315,6 +315,21 @@ def test_random_irregular_codes_fuzz(mods, seed):
         a = {k: (v.clone() if v is not None else None) for k, v in a.items()}
         b = eng.decode_device_channel(ch, lib.SPA, lib.F32, prm, y, max_iter=20, flags=lib.PATH_RESIDENT)
         assert bool((a["iters"] == b["iters"]).all()) and bool((a["x_hat"] == b["x_hat"]).all()) and bool((a["reason"] == b["reason"]).all())
+    # tiny batches, one iteration, unlimited iterations with a cap, and the host entry point, on the same kernels
+    yd = torch.from_numpy(Y).cuda()
+    for ldt, dt in ((lib.F32, np.float32), (lib.F64, np.float64)):
+        full = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, ldt, nv, yd, max_iter=20, flags=lib.PATH_RESIDENT)
+        full = {k: v.clone() for k, v in full.items() if v is not None}
+        for b in (1, 5):
+            part = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, ldt, nv, yd[:b].contiguous(), max_iter=20, flags=lib.PATH_RESIDENT)
+            assert bool((part["iters"] == full["iters"][:b]).all()) and bool((part["x_hat"] == full["x_hat"][:b]).all())
+        for mi, cap in ((1, 0), (0, 30)):
+            ref = O.bp_decode(og, O.MSA, O.llr_biawgn(3.0, Y[:64]).astype(dt), max_iter=mi, iter_cap=cap, nthreads=4)
+            out = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, ldt, nv, yd[:64].contiguous(), max_iter=mi, iter_cap=cap, flags=lib.PATH_RESIDENT)
+            assert (out["iters"].cpu().numpy() == ref["iters"]).all() and (out["x_hat"].cpu().numpy() == ref["x_hat"]).all()
+            assert (out["reason"].cpu().numpy() == ref["reason"]).all()
+        xh, it, rs = eng.decode_host(lib.CH_BIAWGN, lib.MSA, ldt, nv, Y, max_iter=20, chunk=128)
+        assert (it == full["iters"].cpu().numpy()).all() and (xh == full["x_hat"].cpu().numpy()).all()
     Ye = G.channel_send("bec", .35, zeros, 6000 + seed).astype(np.uint8)
     ref = O.bec_decode(og, Ye, max_iter=50, nthreads=4)
     out = eng.decode_device_channel(lib.CH_BEC, lib.BEC, lib.F32, 0.0, torch.from_numpy(Ye).cuda(), max_iter=50)
