@@ -269,6 +269,36 @@ def test_random_regular_codes_fuzz(mods, n, dv, dc):
     assert bool((a["iters"] == b["iters"]).all()) and bool((a["x_hat"] == b["x_hat"]).all())
 
 
+def test_long_irregular_code_streams_bit_exact(mods):
+    """An irregular code too long for shared memory (n = 5000, variable degrees 1..8, a few short checks): the streaming
+    sweeps with non-uniform degree tables, min-sum float32 / float64 and erasure decoding against the oracle."""
+    torch, lib = mods["torch"], mods["lib"]
+    from ldpc_decoders_b200 import codes
+    prof = {2: 2760, 3: 1000, 4: 400, 7: 380, 8: 200, 1: 60, 5: 100, 6: 100}
+    short = (-sum(d * c for d, c in prof.items())) % 6
+    if short:
+        prof[2] -= 1
+        prof[2 + short] = prof.get(2 + short, 0) + 1
+    tab = codes.random_irregular(prof, 6, seed=21).tables
+    og = O.Graph(tab.m, tab.n, tab.edge_chk.astype(np.int64), tab.edge_var.astype(np.int64))
+    eng = mods["engine"].engine_for(tab)
+    assert eng.resident_kernel == "" and tab.n == 5000
+    B = 200
+    zeros = np.zeros((B, tab.n), np.int64)
+    Y = G.channel_send("biawgn", 2.5, zeros, 8101)
+    nv = 10 ** (-2.5 / 10)
+    for dt, ldt in ((np.float32, lib.F32), (np.float64, lib.F64)):
+        ref = O.bp_decode(og, O.MSA, O.llr_biawgn(2.5, Y).astype(dt), max_iter=12, nthreads=8)
+        out = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, ldt, nv, torch.from_numpy(Y).cuda(), max_iter=12)
+        assert (out["iters"].cpu().numpy() == ref["iters"]).all() and (out["x_hat"].cpu().numpy() == ref["x_hat"]).all()
+        assert (out["reason"].cpu().numpy() == ref["reason"]).all()
+    Ye = G.channel_send("bec", .33, zeros, 8102).astype(np.uint8)
+    ref = O.bec_decode(og, Ye, max_iter=60, nthreads=8)
+    out = eng.decode_device_channel(lib.CH_BEC, lib.BEC, lib.F32, 0.0, torch.from_numpy(Ye).cuda(), max_iter=60)
+    assert (out["iters"].cpu().numpy() == ref["iters"]).all() and (out["x_hat"].cpu().numpy() == ref["x_hat"]).all()
+    assert (out["reason"].cpu().numpy() == ref["reason"]).all()
+
+
 @pytest.mark.parametrize("seed", list(range(8)))
 def test_random_irregular_codes_fuzz(mods, seed):
     """Randomly drawn irregular codes (codes.random_irregular: lengths that are not multiples of 4 or 8, variables of
