@@ -42,7 +42,7 @@ struct ResidentInfo {                        // position-indexed tables of the o
     long plan[7] = {0, 0, 0, 0, 0, 0, 0};    // predicted wavefronts: cn ideal/file/plan-natural/plan, vn ideal/file/plan
     // variable-plane variant (resident_vp.cuh, regular codes): one placement per edge order, [0] min-sum, [1] natural
     bool vp = false;
-    bool vp_big = false;                     // ... in the one-CTA-per-SM geometry (resident_vp MAXT = 672; codes up to n = 2688)
+    bool vp_big = false;                     // ... in the one-CTA-per-SM geometry (resident_vp MAXT = 672; codes up to n ≈ 2850)
     uint16_t *vp_cw[2] = {nullptr, nullptr};                    // [mp][8]: (variable position << 4) | (edge rank at the variable + 1)
     uint16_t *vp_vposmap[2] = {nullptr, nullptr}, *vp_vinvmap[2] = {nullptr, nullptr};
     // ... for irregular codes (IRR = true): one word per edge, planes are prefixes of the positions (res_layout.h, VxTables)

@@ -732,7 +732,9 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
     const bool lay_check = lay && std::string(lay) == "check";
     // Regular (3,6) codes too long for half an SM (Margulis, n = 2640): ONE variable-plane CTA per SM, all of its shared memory
     const bool big = r.regular36 && !lay_check && np % 4 == 0 && np * 16 <= 0xfff0 &&
-                     vp_smem_layout(np, 3, 0, 0).total > resident_budget(h) &&
+                     (vp_smem_layout(np, 3, 0, 0).total > resident_budget(h) ||                      // too much state for half an SM,
+                      mp > kResCnPasses * res_max_threads(Q) || np > kResVnPasses * res_max_threads(Q)) &&   // or too many items for 320 threads
+
                      vp_smem_layout(np, 3, 0, 0, false).total <= h->smem_optin - 1024 &&
                      mp <= (kResCnPasses + 1) * kVpBigThreads && np <= kVpBigVnPasses * kVpBigThreads;
     // the check-major kernel (resident_bp) needs more shared memory than the variable-plane layouts (its edge table):

@@ -43,7 +43,7 @@ struct VpSmem {
     size_t marg, planes, prior, stage, bars, hb, imap, total;
 };
 // imap_in_smem = false: the position -> variable map of the output stays in global memory (the one-CTA-per-SM
-// geometry of codes up to n = 2688, where the 2 n bytes are what makes room for the row ring).
+// geometry of codes up to n ≈ 2850, where the 2 n bytes are what makes room for the row ring).
 __host__ __device__ inline VpSmem vp_smem_layout(int np, int dv, int ring, int stage_stride, bool imap_in_smem = true)
 {
     VpSmem L;
@@ -154,7 +154,7 @@ __device__ __forceinline__ void vp_load4(const unsigned char *row, int i4, int i
 // np, mp and T constant every shared-memory address of the variable phase is base + immediate and the pass bounds
 // fold away.
 // MAXT: 320 = two CTAs per SM (4 + 4 frames); 640 = ONE CTA per SM for codes whose 4 frames need the whole shared
-// memory (n up to 2688: the Margulis code, n = 2640), 96 registers per thread either way.  20 warps is what 96
+// memory (n up to ≈ 2850: the Margulis code, n = 2640), 96 registers per thread either way.  20 warps is what 96
 // registers allow (warps are allocated in fours: 21 would get 80 registers and spill), so that geometry makes five
 // variable passes and, for the checks beyond 2 x 640, a third check pass whose c2v_old is read back from the planes
 // it was scattered to instead of being kept in registers.

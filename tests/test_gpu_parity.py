@@ -243,29 +243,29 @@ def test_max_iter_sweep_irregular_bsc(mods, mi):
     assert (iters[fin] == ref["iters"][fin]).all() and (x_hat[fin] == ref["x_hat"][fin]).all()
 
 
-@pytest.mark.parametrize("n,dv,dc", [(600, 3, 6), (1000, 3, 6), (96, 2, 4), (300, 3, 4), (640, 4, 8), (250, 3, 5), (1280, 3, 6), (2000, 3, 6)])
+@pytest.mark.parametrize("n,dv,dc", [(600, 3, 6), (1000, 3, 6), (96, 2, 4), (300, 3, 4), (640, 4, 8), (250, 3, 5), (1280, 3, 6), (2000, 3, 6), (1296, 3, 6), (2688, 3, 6), (2848, 3, 6), (3008, 3, 6)])
 def test_random_regular_codes_fuzz(mods, n, dv, dc):
     """Seeded regular codes of several degree pairs and lengths: (3,6) runs on resident_vp (two CTAs per SM up to
-    n = 1280, one beyond), check degrees up to 6 on its irregular instance, (4,8) on resident_bp.  Min-sum against the
+    n = 1280, one up to n = 2848), check degrees up to 6 on its irregular instance, (4,8) on resident_bp.  Min-sum against the
     oracle at float32 (and float64 where the on-chip float64 kernel applies), sum-product on chip against streaming."""
     torch, lib = mods["torch"], mods["lib"]
     from ldpc_decoders_b200 import codes
     tab = codes.random_regular(n, dv, dc, seed=n + dc).tables
     og = O.Graph(tab.m, tab.n, tab.edge_chk.astype(np.int64), tab.edge_var.astype(np.int64))
     eng = mods["engine"].engine_for(tab)
-    assert eng.resident_kernel == ("resident_bp" if dc > 6 else "resident_vp")
+    assert eng.resident_kernel == ("" if n > 2848 else "resident_bp" if dc > 6 else "resident_vp")     # 3008: streaming only
     B = 260
     Y = G.channel_send("biawgn", 3.0, np.zeros((B, tab.n), np.int64), 7000 + n)
     nv = 10 ** (-3.0 / 10)
     dtypes = [(np.float32, lib.F32)] + ([(np.float64, lib.F64)] if dc <= 6 and n <= 1280 else [])
     for dt, ldt in dtypes:
         ref = O.bp_decode(og, O.MSA, O.llr_biawgn(3.0, Y).astype(dt), max_iter=15, nthreads=4)
-        out = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, ldt, nv, torch.from_numpy(Y).cuda(), max_iter=15, flags=lib.PATH_RESIDENT)
+        out = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, ldt, nv, torch.from_numpy(Y).cuda(), max_iter=15)      # AUTO: on chip where possible
         assert (out["iters"].cpu().numpy() == ref["iters"]).all() and (out["x_hat"].cpu().numpy() == ref["x_hat"]).all()
     y32 = torch.from_numpy(Y.astype(np.float32)).cuda()
     a = eng.decode_device_channel(lib.CH_BIAWGN, lib.SPA, lib.F32, nv, y32, max_iter=15, flags=lib.PATH_STREAMING)
     a = {k: (v.clone() if v is not None else None) for k, v in a.items()}
-    b = eng.decode_device_channel(lib.CH_BIAWGN, lib.SPA, lib.F32, nv, y32, max_iter=15, flags=lib.PATH_RESIDENT)
+    b = eng.decode_device_channel(lib.CH_BIAWGN, lib.SPA, lib.F32, nv, y32, max_iter=15)
     assert bool((a["iters"] == b["iters"]).all()) and bool((a["x_hat"] == b["x_hat"]).all())
 
 
