@@ -21,9 +21,14 @@
  *   - "device" pointers are CUDA device pointers on the handle's device and
  *     are CALLER-OWNED (e.g. torch.empty(...).data_ptr()); the handle owns
  *     only the graph tables (and, for ldpc_decode_host, its staging buffers).
- *   - ldpc_decode / ldpc_llr_* / ldpc_debug_step are asynchronous on the
- *     given stream and never synchronise; ldpc_create / ldpc_destroy /
- *     ldpc_decode_host synchronise.
+ *   - ldpc_decode / ldpc_decode_channel / ldpc_mc_round / ldpc_llr_* /
+ *     ldpc_debug_step are asynchronous on the given stream; ldpc_create /
+ *     ldpc_destroy / ldpc_decode_host synchronise.  ONE exception: a decode on
+ *     the streaming path whose iteration bound exceeds 32 (max_iter > 32, or
+ *     max_iter <= 0 = "unlimited") reads one word back every 8 iterations
+ *     (cudaStreamSynchronize on the given stream) to stop launching sweeps once
+ *     every frame has left; such a call cannot be captured into a CUDA graph.
+ *     The on-chip path (one launch per batch) never synchronises.
  *   - one handle per (process, device); a handle is not thread-safe.
  *   - there is NO CPU fallback: without a CUDA device ldpc_create fails.
  */
@@ -37,7 +42,7 @@
 extern "C" {
 #endif
 
-#define LDPC_ABI_VERSION 1
+#define LDPC_ABI_VERSION 2
 
 /* algo: which reference decoder is replaced */
 #define LDPC_MSA 0   /* bpa.MSA.decode_      src/bpa.py:86-102  */
@@ -52,6 +57,8 @@ extern "C" {
  *   BEC: dtype is ignored (bit-plane integer arithmetic). */
 #define LDPC_F32 0
 #define LDPC_F64 1
+#define LDPC_F16 2   /* y_dtype ONLY (received values / priors handed over as IEEE binary16): halves the bytes a host
+                        batch sends over PCIe.  Converted exactly; messages stay F32 / F64. */
 
 /* per-frame exit reason written by ldpc_decode (the reference's ret('...')
  * strings, src/bpa.py:28-29, src/bec.py:96-97,120) */
@@ -81,6 +88,11 @@ extern "C" {
                                     bulk-async (TMA) staged one (A/B measurements; it is also the fallback for
                                     check degrees > 8) */
 #define LDPC_HOST_ASYNC    16u   /* ldpc_decode_host: return once the work is enqueued; ldpc_host_sync() completes it */
+#define LDPC_OUT_PACKED    32u   /* ldpc_decode_host: x_hat is BIT-PACKED, one row of ldpc_packed_row_bytes(n) bytes per frame
+                                    (bit v of a word = bit (v & 7) of byte (v >> 3): numpy.packbits(bitorder="little"));
+                                    BEC: two such planes per frame, value plane (symbol == 1) then erasure plane (symbol == 2) */
+#define LDPC_IN_PACKED     64u   /* ldpc_decode_host, BSC / BEC: y is bit-packed the same way (1 bit per hard bit, 2 planes
+                                    per erasure symbol) instead of one byte per symbol */
 
 /* channel kinds for ldpc_decode_host / ldpc_channel_llr */
 #define LDPC_CH_PRIORS 0   /* input already is the prior LLR (bpa.*.decode(y, priors)) */
@@ -133,7 +145,7 @@ int ldpc_decode(ldpc_t *h, int algo, int dtype,
                 void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
 
 /* Same as ldpc_decode, with the channel front end fused into the load: `y` is the RECEIVED block on
- * the device ([B,n] row-major; uint8 for BSC / BEC, y_dtype F32 | F64 for BIAWGN / PRIORS) and the
+ * the device ([B,n] row-major; uint8 for BSC / BEC, y_dtype F32 | F64 | F16 for BIAWGN / PRIORS) and the
  * LLR map of the reference's adapters (src/bsc.py:25, src/biawgn.py:28, src/bec.py:85) is applied while
  * it is transposed into the kernels' layout.  channel = LDPC_CH_*, param = llr (BSC) / noise_var
  * (BIAWGN).  BSC uses y as the hard input of the iteration-0 syndrome test. */
@@ -162,6 +174,26 @@ int ldpc_channel_generate(ldpc_t *h, int channel, double param, const uint8_t *x
 /* bit_errs[b] = #{v : x_hat[b,v] != x[v]} (src/main.py:41; an undecoded BEC symbol counts); x NULL = all-zero word. */
 int ldpc_count_errors(ldpc_t *h, const uint8_t *x_hat, const uint8_t *x, int B, int32_t *bit_errs, void *stream);
 
+/* Monte-Carlo counters of a decoded batch, accumulated on the device (the loop body of src/main.py:37-45, B frames at
+ * once, no host round trip): counters is device int64 [4 + nhist]:
+ *   [0] += B (tot)   [1] += #{frames with a bit error} (wec)   [2] += bit errors (bec)   [3] += sum of iters
+ *   [4 + min(iters, nhist - 1)] += 1   (the iteration histogram of stats(), src/admm.py:38-40; nhist may be 0)
+ * bit_errs: device [B] int32 per-frame error counts, or NULL.  x NULL = the all-zero word. */
+int ldpc_count_accumulate(ldpc_t *h, const uint8_t *x_hat, const uint8_t *x, const int32_t *iters, int B,
+                          int32_t *bit_errs, long long *counters, int nhist, void *stream);
+
+/* One whole Monte-Carlo round on the device: ldpc_channel_generate (frames frame0 .. frame0 + B - 1 of the word x) ->
+ * ldpc_decode_channel -> ldpc_count_accumulate into `counters`; nothing is copied to the host.  A fixed-length
+ * simulation is a loop of these and ONE read (or one all-reduce over GPUs) of `counters` at the end.
+ *   ch_param   channel parameter of ldpc_channel_generate (p, or noise_var for BIAWGN)
+ *   dec_param  decoder parameter of ldpc_decode_channel (llr = log(1-p) - log(p) for BSC, noise_var for BIAWGN)
+ *   scratch    device, >= ldpc_mc_scratch_bytes(...) bytes, 256-byte aligned (received block, words, workspace) */
+size_t ldpc_mc_scratch_bytes(const ldpc_t *h, int channel, int algo, int dtype, int B);
+int ldpc_mc_round(ldpc_t *h, int channel, int algo, int dtype, double ch_param, double dec_param,
+                  const uint8_t *x, unsigned long long seed, unsigned long long frame0, int B,
+                  int max_iter, int iter_cap, long long *counters, int nhist,
+                  void *scratch, size_t scratch_bytes, unsigned flags, void *stream);
+
 /* One isolated sweep on caller-supplied messages in the reference's own layout
  * (teacher-forced parity): device [B,E] row-major, edge order of np.where(H).
  *   which = 0: check-node sweep   c2v = CN(v2c)            (src/bpa.py:71-75 / 86-102)
@@ -176,15 +208,20 @@ int ldpc_debug_step(ldpc_t *h, int algo, int dtype, int which, int B,
  * input): chunks the batch, overlaps H2D copy / LLR + decode / D2H copy on internal
  * streams, and returns when x_hat / iters are complete in host memory.
  *   channel  LDPC_CH_*; param = llr (BSC) or noise_var (BIAWGN), ignored otherwise
- *   y        host [B,n] row-major; y_dtype: LDPC_F32 / LDPC_F64 for PRIORS and BIAWGN,
- *            ignored (uint8) for BSC and BEC.  Pinned memory makes the copies asynchronous.
- *   x_hat    host [B,n] uint8;  iters host [B] int32;  reason host [B] uint8 or NULL
+ *   y        host [B,n] row-major; y_dtype: LDPC_F32 / LDPC_F64 / LDPC_F16 for PRIORS and BIAWGN,
+ *            ignored (uint8) for BSC and BEC — or, with LDPC_IN_PACKED, [B][planes * ldpc_packed_row_bytes(n)]
+ *            bit-packed symbols.  Pinned memory makes the copies asynchronous.
+ *   x_hat    host [B,n] uint8 (LDPC_OUT_PACKED: [B][planes * ldpc_packed_row_bytes(n)]);
+ *            iters host [B] int32;  reason host [B] uint8 or NULL
  *   chunk    frames per pipeline stage (0 = default)
  * Device staging buffers are owned by the handle and reused across calls (in stream order). */
 int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
                      const void *y, int y_dtype, int B, int max_iter, int iter_cap,
                      uint8_t *x_hat, int32_t *iters, uint8_t *reason,
                      int chunk, unsigned flags);
+
+/* Bytes of one bit-packed row (LDPC_IN_PACKED / LDPC_OUT_PACKED): ceil(n / 8) rounded up to a multiple of 16. */
+size_t ldpc_packed_row_bytes(int n);
 
 /* A stream of batches: with LDPC_HOST_ASYNC in `flags`, ldpc_decode_host returns as soon as every chunk is enqueued on
  * the handle's internal streams, so the next call's copies overlap this call's tail (no pipeline ramp between batches).

@@ -7,18 +7,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libldpc_b200.so")
 
 MSA, SPA, BEC = 0, 1, 2
-F32, F64 = 0, 1
+F32, F64, F16 = 0, 1, 2
 CH_PRIORS, CH_BSC, CH_BIAWGN, CH_BEC = 0, 1, 2, 3
 PATH_AUTO, PATH_STREAMING, PATH_RESIDENT = 0, 1, 2
 SPA_ROBUST = 4
 CN_REGISTER = 8
 HOST_ASYNC = 16
+OUT_PACKED = 32
+IN_PACKED = 64
 REASONS = {0: "decoded", 1: "maximum", 2: "stopping", 4: "cap"}
 
 # every symbol include/ldpc_b200.h declares
 SYMBOLS = ("ldpc_abi_version", "ldpc_create", "ldpc_destroy", "ldpc_last_error", "ldpc_workspace_bytes",
            "ldpc_decode", "ldpc_decode_channel", "ldpc_llr_bsc", "ldpc_llr_biawgn", "ldpc_debug_step", "ldpc_decode_host", "ldpc_host_sync",
-           "ldpc_launch_count", "ldpc_profile_enable", "ldpc_profile_read", "ldpc_resident_frames", "ldpc_resident_plan", "ldpc_resident_kernel", "ldpc_channel_generate", "ldpc_count_errors")
+           "ldpc_launch_count", "ldpc_profile_enable", "ldpc_profile_read", "ldpc_resident_frames", "ldpc_resident_plan", "ldpc_resident_kernel", "ldpc_channel_generate", "ldpc_count_errors",
+           "ldpc_packed_row_bytes", "ldpc_count_accumulate", "ldpc_mc_scratch_bytes", "ldpc_mc_round")
 
 
 class LdpcError(RuntimeError):
@@ -71,6 +74,15 @@ def load():
     L.ldpc_channel_generate.argtypes = [vp, i32, dbl, vp, ctypes.c_ulonglong, ctypes.c_ulonglong, i32, vp, vp]
     L.ldpc_count_errors.restype = i32
     L.ldpc_count_errors.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.ldpc_packed_row_bytes.restype = sz
+    L.ldpc_packed_row_bytes.argtypes = [i32]
+    L.ldpc_count_accumulate.restype = i32
+    L.ldpc_count_accumulate.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp]
+    L.ldpc_mc_scratch_bytes.restype = sz
+    L.ldpc_mc_scratch_bytes.argtypes = [vp, i32, i32, i32, i32]
+    L.ldpc_mc_round.restype = i32
+    L.ldpc_mc_round.argtypes = [vp, i32, i32, i32, dbl, dbl, vp, ctypes.c_ulonglong, ctypes.c_ulonglong, i32, i32, i32,
+                                vp, i32, vp, sz, u32, vp]
     L.ldpc_host_sync.restype = i32
     L.ldpc_host_sync.argtypes = [vp]
     L.ldpc_resident_kernel.restype = ctypes.c_char_p
@@ -79,7 +91,7 @@ def load():
     L.ldpc_resident_plan.argtypes = [vp, ctypes.POINTER(ctypes.c_long)]
     L.ldpc_launch_count.restype = ctypes.c_ulonglong
     L.ldpc_launch_count.argtypes = [vp]
-    if L.ldpc_abi_version() != 1:
+    if L.ldpc_abi_version() != 2:
         raise LdpcError("libldpc_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -54,19 +54,14 @@ class SPA:
         x_hat = x_hat.astype(np.int64)
         return (x_hat, iters, reason) if return_reason else (x_hat, iters)
 
-    def simulate_batch(self, x, B, seed, frame0=0):
+    def simulate_batch(self, x, B, seed, frame0=0, on_device=False):
         """On-device Monte-Carlo round: erase on the GPU, decode, count symbol errors (undecoded symbols count, main.py:41)."""
-        import torch
-        eng = self.engine
-        key = np.asarray(x, np.uint8).tobytes()
-        if getattr(self, "_xkey", None) != key:
-            self._xdev = torch.from_numpy(np.ascontiguousarray(x, np.uint8)).to(eng._dev())
-            self._xkey, self._bufs = key, {}
-        out = eng.simulate(_lib.CH_BEC, _lib.BEC, _lib.F32, self.p, B, seed, frame0, x=self._xdev,
-                           max_iter=self.max_iter, iter_cap=self.iter_cap, bufs=self._bufs)
-        errs, iters = out["bit_errs"].cpu().numpy(), out["iters"].cpu().numpy()
-        self._count(iters)
-        return errs, iters
+        from .biawgn import _simulate
+        return _simulate(self, _lib.CH_BEC, self.p, x, B, seed, frame0, on_device)
+
+    def simulate_round(self, x, B, seed, frame0, counters, nhist):
+        from .biawgn import _simulate_round
+        return _simulate_round(self, _lib.CH_BEC, self.p, x, B, seed, frame0, counters, nhist)
 
     def decode(self, y):
         y = np.asarray(y)

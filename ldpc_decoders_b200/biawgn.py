@@ -41,27 +41,48 @@ class LLR:
         return (x_hat, iters, reason) if return_reason else (x_hat, iters)
 
 
-    def simulate_batch(self, x, B, seed, frame0=0):
+    def simulate_batch(self, x, B, seed, frame0=0, on_device=False):
         """Draw B received frames of the word x on the GPU (global frame indices frame0 ..), decode, count bit errors.
-        Returns numpy (bit_errs [B], iters [B]); nothing but these two vectors crosses PCIe."""
-        return _simulate(self, _lib.CH_BIAWGN, self.noise_var, x, B, seed, frame0)
+        Returns numpy (bit_errs [B], iters [B]) — or, with on_device=True, the two CUDA int32 tensors themselves (no
+        synchronisation; the caller gathers them); nothing but these two vectors ever crosses PCIe."""
+        return _simulate(self, _lib.CH_BIAWGN, self.noise_var, x, B, seed, frame0, on_device)
+
+    def simulate_round(self, x, B, seed, frame0, counters, nhist):
+        """The same round with the counters kept on the GPU (Engine.mc_round): nothing crosses PCIe at all."""
+        return _simulate_round(self, _lib.CH_BIAWGN, self.noise_var, x, B, seed, frame0, counters, nhist)
 
 
-def _simulate(adapter, channel, param, x, B, seed, frame0):
+def _xdev(adapter, eng, x):
+    """The transmitted word as a cached device tensor (the cache key is the word itself)."""
     import torch
-    dec = adapter.dec
-    eng = dec.engine
-    dt = _lib.F32 if adapter.dtype == np.float32 else _lib.F64
     key = (np.asarray(x, np.uint8).tobytes(), eng.device)
     if getattr(adapter, "_xkey", None) != key:
         adapter._xdev = torch.from_numpy(np.ascontiguousarray(x, np.uint8)).to(eng._dev())
         adapter._xkey = key
         adapter._bufs = {}
-    out = eng.simulate(channel, dec._algo, dt, param, B, seed, frame0, x=adapter._xdev, max_iter=dec.max_iter,
+    return adapter._xdev
+
+
+def _simulate(adapter, channel, param, x, B, seed, frame0, on_device=False):
+    dec = getattr(adapter, "dec", adapter)                 # bec.SPA is its own decoder core
+    eng = dec.engine
+    dt = _lib.F32 if getattr(adapter, "dtype", np.dtype(np.float32)) == np.float32 else _lib.F64
+    xd = _xdev(adapter, eng, x)
+    out = eng.simulate(channel, getattr(dec, "_algo", _lib.BEC), dt, param, B, seed, frame0, x=xd, max_iter=dec.max_iter,
                        iter_cap=dec.iter_cap, bufs=adapter._bufs)
+    if on_device:
+        return out["bit_errs"], out["iters"]
     errs, iters = out["bit_errs"].cpu().numpy(), out["iters"].cpu().numpy()
     dec._count(iters)
     return errs, iters
+
+
+def _simulate_round(adapter, channel, param, x, B, seed, frame0, counters, nhist):
+    dec = getattr(adapter, "dec", adapter)
+    eng = dec.engine
+    dt = _lib.F32 if getattr(adapter, "dtype", np.dtype(np.float32)) == np.float32 else _lib.F64
+    eng.mc_round(channel, getattr(dec, "_algo", _lib.BEC), dt, param, B, seed, frame0, counters, nhist,
+                 x=_xdev(adapter, eng, x), max_iter=dec.max_iter, iter_cap=dec.iter_cap)
 
 
 class SPA(LLR):

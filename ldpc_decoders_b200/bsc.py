@@ -38,10 +38,14 @@ class LLR:
         return (x_hat, iters, reason) if return_reason else (x_hat, iters)
 
 
-    def simulate_batch(self, x, B, seed, frame0=0):
+    def simulate_batch(self, x, B, seed, frame0=0, on_device=False):
         """On-device Monte-Carlo round (see biawgn.LLR.simulate_batch)."""
         from .biawgn import _simulate
-        return _simulate(self, _lib.CH_BSC, self.p, x, B, seed, frame0)
+        return _simulate(self, _lib.CH_BSC, self.p, x, B, seed, frame0, on_device)
+
+    def simulate_round(self, x, B, seed, frame0, counters, nhist):
+        from .biawgn import _simulate_round
+        return _simulate_round(self, _lib.CH_BSC, self.p, x, B, seed, frame0, counters, nhist)
 
 
 class SPA(LLR):

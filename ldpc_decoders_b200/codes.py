@@ -105,10 +105,16 @@ def random_regular(n, dv, dc, seed=0):
         dup = order[1:][key[order][1:] == key[order][:-1]]
         if dup.size == 0:
             break
-        other = rng.integers(0, E, size=dup.size)
-        cols[dup], cols[other] = cols[other].copy(), cols[dup].copy()
+        # one socket pair at a time: a swap of two sockets keeps the multiset of variable sockets (and so every
+        # degree) whatever the indices are, which a vectorised fancy-index swap with repeated indices does not
+        for d in dup.tolist():
+            o = int(rng.integers(0, E - 1))
+            o += o >= d                                   # any socket but d itself
+            cols[d], cols[o] = cols[o], cols[d]
     else:
         raise RuntimeError("could not remove double edges")
+    if not ((np.bincount(cols, minlength=n) == dv).all() and (np.bincount(chk_sock, minlength=m) == dc).all()):
+        raise AssertionError("random_regular lost a socket: the code is not (%d,%d)-regular" % (dv, dc))
     return Code(Tables(m, n, chk_sock, cols), "%d_%d_%d_cfg_seed%d" % (n, dv, dc, seed))
 
 

@@ -120,6 +120,51 @@ __global__ void count_errors(const uint8_t *__restrict__ x_hat, const uint8_t *_
     if (lane == 0) bit_errs[f] = e;
 }
 
+// Monte-Carlo counters of one decoded batch, accumulated ON THE DEVICE (the inner loop of src/main.py:37-45 without a
+// host round trip): c[0] += frames (tot), c[1] += #{frames with a bit error} (wec), c[2] += bit errors (bec),
+// c[3] += sum of iteration counts, c[4 + min(iters, nhist - 1)] += 1 (the iteration histogram of stats(), admm.py:38-40).
+// One warp per frame counts the frame's errors against x (as count_errors); a CTA adds its 8 frames with one set of atomics.
+// bit_errs may be NULL.  Counters are unsigned 64-bit (read them as int64).
+__global__ void __launch_bounds__(256) count_accumulate(const uint8_t *__restrict__ x_hat, const uint8_t *__restrict__ x,
+                                                        const int *__restrict__ iters, int B, int n,
+                                                        int *__restrict__ bit_errs, unsigned long long *__restrict__ c, int nhist)
+{
+    __shared__ int s_e[8], s_it[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x * 8 + warp;
+    int e = 0, it = -1;
+    if (f < B) {
+        const uint8_t *row = x_hat + (size_t)f * n;
+        for (int v = lane; v < n; v += 32) e += (row[v] != ((x != nullptr) ? x[v] : (uint8_t)0)) ? 1 : 0;
+        e = __reduce_add_sync(kFull, e);
+        it = iters[f];
+        if (lane == 0 && bit_errs != nullptr) bit_errs[f] = e;
+    }
+    if (lane == 0) { s_e[warp] = e; s_it[warp] = it; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0, wec = 0, bec = 0, its = 0;
+        for (int w = 0; w < 8; ++w) {
+            if (s_it[w] < 0) continue;
+            tot += 1; wec += s_e[w] > 0; bec += (unsigned long long)s_e[w]; its += (unsigned long long)s_it[w];
+            if (nhist > 0) {                                     // one atomic per distinct iteration count of the CTA
+                bool seen = false;
+                unsigned long long same = 0;
+                for (int u = 0; u < 8; ++u) {
+                    if (s_it[u] != s_it[w]) continue;
+                    if (u < w) { seen = true; break; }
+                    same += 1;
+                }
+                if (!seen) atomicAdd(c + 4 + min(s_it[w], nhist - 1), same);
+            }
+        }
+        atomicAdd(c + 0, tot);
+        if (wec) atomicAdd(c + 1, wec);
+        if (bec) atomicAdd(c + 2, bec);
+        atomicAdd(c + 3, its);
+    }
+}
+
 #endif  // __CUDACC__
 
 }  // namespace ldpc

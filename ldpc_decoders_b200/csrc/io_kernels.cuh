@@ -8,17 +8,27 @@
 //   BEC     messages[y] = [-1, +1, 0][y]       /root/reference/src/bec.py:76,85
 // evaluated in float64 and rounded once to the message type (== reference priors.astype(dtype)).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ldpc {
 
 enum { IN_COPY = 0, IN_BSC = 1, IN_BIAWGN = 2 };
 
+// A received value as the float64 the reference computes with.  binary16 rows (y_dtype LDPC_F16) halve the bytes a
+// host batch sends over PCIe; the conversion is exact, so the parity definition is unchanged: priors = (-2 y) / var on
+// the values the caller handed over.
+template <typename Tin> __device__ __forceinline__ double in_f64(Tin y) { return (double)y; }
+template <> __device__ __forceinline__ double in_f64<__half>(__half y) { return (double)__half2float(y); }
+template <typename Tin> __device__ __forceinline__ bool in_nonzero(Tin y) { return y != (Tin)0; }
+template <> __device__ __forceinline__ bool in_nonzero<__half>(__half y) { return __half2float(y) != 0.0f; }
+
 template <typename Tin, typename T, int MODE> __device__ __forceinline__ T llr_map(Tin y, double param)
 {
-    if (MODE == IN_BSC) return (T)(param * (double)(1 - 2 * (int)y));
-    if (MODE == IN_BIAWGN) return (T)((-2.0 * (double)y) / param);
-    return (T)y;
+    if (MODE == IN_BSC) return (T)(param * (double)(1 - 2 * (int)in_nonzero(y)));
+    if (MODE == IN_BIAWGN) return (T)((-2.0 * in_f64(y)) / param);
+    return (T)in_f64(y);
 }
 
 // src [B][n] (frame-major) -> prior [n][Bp]; frames >= B are zero-filled.
@@ -44,7 +54,7 @@ __global__ void __launch_bounds__(256) ingest_priors(const Tin *__restrict__ src
             if (f < B && v < n) {
                 const Tin y = src[(size_t)f * n + v];
                 val = llr_map<Tin, T, MODE>(y, param);
-                if (MODE == IN_BSC) hb = (uint8_t)(y != (Tin)0);
+                if (MODE == IN_BSC) hb = (uint8_t)in_nonzero(y);
             }
             tile[t][r][threadIdx.x] = val;
             if (MODE == IN_BSC) hard[t][r][threadIdx.x] = hb;
@@ -212,6 +222,59 @@ __global__ void __launch_bounds__(256) emit_words_tiled(const uint32_t *__restri
         const int idx = tid + i * 256, r = idx >> 3, q = idx & 7;
         const int f = f0 + r, v = v0 + 4 * q;
         if (f < B && v < n) *reinterpret_cast<uint32_t *>(x_hat + (size_t)f * n + v) = sym[r][q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bit-packed rows at the HOST boundary (ldpc_decode_host with LDPC_IN_PACKED / LDPC_OUT_PACKED): a hard bit costs one
+// bit on PCIe instead of one byte, an erasure symbol two.  Layout of a packed row (stride = ldpc_packed_row_bytes(n),
+// a multiple of 16): bit v of the row = bit (v & 7) of byte (v >> 3), i.e. numpy.packbits(..., bitorder="little");
+// BEC rows are two such planes back to back: the value plane (symbol == 1), then the erasure plane (symbol == 2).
+// Both kernels are a few tens of microseconds per 32768 frames: the decoders keep their byte interface.
+// ---------------------------------------------------------------------------------------------------------------
+// src [B][planes * stride] -> dst [B][n] bytes.  Thread = (frame, 8 consecutive variables = one packed byte).
+__global__ void unpack_rows(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int B, int n, int stride, int planes)
+{
+    const int bpr = (n + 7) >> 3;                                    // packed bytes that carry symbols
+    const long long total = (long long)B * bpr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i / bpr), q = (int)(i % bpr);
+        const uint8_t *row = src + (size_t)f * planes * stride;
+        const uint32_t val = row[q], er = (planes == 2) ? row[stride + q] : 0u;
+        uint8_t *out = dst + (size_t)f * n + (size_t)q * 8;
+        const int cnt = min(8, n - q * 8);
+        if (cnt == 8 && (n & 7) == 0) {                              // 8-byte aligned: one 64-bit store
+            uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                lo |= (((er >> b) & 1u) ? 2u : ((val >> b) & 1u)) << (8 * b);
+                hi |= (((er >> (b + 4)) & 1u) ? 2u : ((val >> (b + 4)) & 1u)) << (8 * b);
+            }
+            *reinterpret_cast<uint2 *>(out) = make_uint2(lo, hi);
+        } else {
+            for (int b = 0; b < cnt; ++b) out[b] = (uint8_t)(((er >> b) & 1u) ? 2u : ((val >> b) & 1u));
+        }
+    }
+}
+
+// src [B][n] bytes -> dst [B][planes * stride] (padding bits and bytes zero).  Warp = one frame, lane = variable.
+__global__ void pack_rows(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int B, int n, int stride, int planes)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int words = stride >> 2;
+    for (int f = blockIdx.x * wpb + (threadIdx.x >> 5); f < B; f += gridDim.x * wpb) {
+        const uint8_t *row = src + (size_t)f * n;
+        uint32_t *out = reinterpret_cast<uint32_t *>(dst + (size_t)f * planes * stride);
+        for (int w = 0; w < words; ++w) {
+            const int v = w * 32 + lane;
+            const uint8_t sy = (v < n) ? row[v] : (uint8_t)0;
+            const uint32_t one = __ballot_sync(kFull, sy == 1), er = __ballot_sync(kFull, sy >= 2);
+            if (lane == 0) {
+                out[w] = one;
+                if (planes == 2) out[words + w] = er;
+            }
+        }
     }
 }
 

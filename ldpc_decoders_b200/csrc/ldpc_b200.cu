@@ -43,22 +43,34 @@ int fail(ldpc_t *h, int code, const std::string &msg)
             return fail((h), LDPC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
     } while (0)
 
+// A failed launch stops the call at once: nothing that depends on it is enqueued behind it.
 #define LAUNCH(h, kern, grid, block, stream, ...)                                                   \
     do {                                                                                            \
         kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                        \
         (h)->launches++;                                                                            \
+        if (cudaPeekAtLastError() != cudaSuccess) return check_launch((h), #kern);                  \
     } while (0)
 
 // Word-wise tiles need 4-byte aligned symbol rows (io_kernels.cuh).
 inline bool rows_word_aligned(const void *base, int n) { return (n % 4) == 0 && (reinterpret_cast<uintptr_t>(base) & 3u) == 0; }
 inline dim3 tile_grid(int n, int wpr) { return dim3((unsigned)((n + kTileVars - 1) / kTileVars), (unsigned)((wpr + 7) / 8), 1); }
 
+// cudaGetLastError, not Peek: the error is reported ONCE, by the call that caused it, and does not stick to the
+// thread (a stale launch error would otherwise be blamed on every later ldpc_* call and on the caller's own CUDA work).
 int check_launch(ldpc_t *h, const char *what)
 {
-    cudaError_t e = cudaPeekAtLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, LDPC_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
     return LDPC_OK;
 }
+
+// Entry of every ABI call that launches: select the device and drop whatever error an EARLIER call (ours or the
+// caller's) left on this thread, so that check_launch reports this call's launches only.
+#define ENTER(h)                                                                                    \
+    do {                                                                                            \
+        CUDA_TRY((h), cudaSetDevice((h)->device));                                                  \
+        (void)cudaGetLastError();                                                                   \
+    } while (0)
 
 // Optional per-launch timing of the two sweeps (bench.py's roofline): events on the launching stream.
 ProfEvent *prof_begin(ldpc_t *h, int kind, cudaStream_t s)
@@ -79,6 +91,8 @@ void prof_end(ProfEvent *ev, cudaStream_t s)
     if (ev) cudaEventRecord(ev->t1, s);
 }
 
+constexpr int kMaxFramesPerCall = 65535 * 32 - 480;      // Bp / 32 (grid.y of the layout kernels) must stay <= 65535 after padding to 512
+
 template <typename T> struct Fpt;
 template <> struct Fpt<float> { static constexpr int value = 4; };
 template <> struct Fpt<double> { static constexpr int value = 2; };
@@ -86,6 +100,8 @@ template <> struct Fpt<double> { static constexpr int value = 2; };
 inline int frames_per_group(int dtype) { return dtype == LDPC_F64 ? 64 : 128; }     // one warp of the register sweeps
 inline int frames_per_tile(int dtype) { return dtype == LDPC_F64 ? 256 : 512; }     // one CTA tile of cn_sweep_tma (2 KB rows)
 inline size_t elem_size(int dtype) { return dtype == LDPC_F64 ? 8 : 4; }
+inline size_t in_elem_size(int y_dtype) { return y_dtype == LDPC_F64 ? 8 : (y_dtype == LDPC_F16 ? 2 : 4); }   // received rows may be binary16
+inline bool in_dtype_ok(int y_dtype) { return y_dtype == LDPC_F32 || y_dtype == LDPC_F64 || y_dtype == LDPC_F16; }
 
 // Grid for a sweep: x = frame tiles of 8 groups, y = chunks of checks / variables, >= ~16 CTAs per SM.
 dim3 sweep_grid(const ldpc_t *h, int ngroups, int items, int *per_cta)
@@ -282,6 +298,8 @@ int ingest_bp(ldpc_t *h, const InSpec &in, T *prior, uint32_t *xbits, int B, con
     case LDPC_CH_PRIORS:
         if (in.in_dtype == LDPC_F64)
             LAUNCH(h, (ingest_priors<double, T, IN_COPY>), grid, block, s, (const double *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, 0.0);
+        else if (in.in_dtype == LDPC_F16)
+            LAUNCH(h, (ingest_priors<__half, T, IN_COPY>), grid, block, s, (const __half *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, 0.0);
         else
             LAUNCH(h, (ingest_priors<float, T, IN_COPY>), grid, block, s, (const float *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, 0.0);
         if (in.y_hard) {
@@ -296,6 +314,8 @@ int ingest_bp(ldpc_t *h, const InSpec &in, T *prior, uint32_t *xbits, int B, con
     case LDPC_CH_BIAWGN:
         if (in.in_dtype == LDPC_F64)
             LAUNCH(h, (ingest_priors<double, T, IN_BIAWGN>), grid, block, s, (const double *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, in.param);
+        else if (in.in_dtype == LDPC_F16)
+            LAUNCH(h, (ingest_priors<__half, T, IN_BIAWGN>), grid, block, s, (const __half *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, in.param);
         else
             LAUNCH(h, (ingest_priors<float, T, IN_BIAWGN>), grid, block, s, (const float *)in.src, prior, xbits, B, t.n, L.Bp, L.wpr, in.param);
         break;
@@ -328,6 +348,8 @@ struct HostSlot {
     cudaStream_t stream = nullptr;
     void *d_y = nullptr; size_t y_bytes = 0;
     uint8_t *d_x = nullptr; size_t x_bytes = 0;
+    uint8_t *d_yp = nullptr; size_t yp_bytes = 0;       // bit-packed input rows as they arrive (LDPC_IN_PACKED)
+    uint8_t *d_xp = nullptr; size_t xp_bytes = 0;       // bit-packed words before they leave (LDPC_OUT_PACKED)
     int32_t *d_it = nullptr; uint8_t *d_rs = nullptr; size_t f_cap = 0;
     void *ws = nullptr; size_t ws_bytes = 0;
 };
@@ -646,9 +668,9 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
     rp.param = in.param;
     rp.inv_param = (in.param != 0.0) ? 1.0 / in.param : 0.0;
     switch (in.channel) {
-    case LDPC_CH_PRIORS: rp.in_mode = IN_COPY; rp.in_es = (in.in_dtype == LDPC_F64) ? 8 : 4; break;
+    case LDPC_CH_PRIORS: rp.in_mode = IN_COPY; rp.in_es = (int)in_elem_size(in.in_dtype); break;
     case LDPC_CH_BSC: rp.in_mode = IN_BSC; rp.in_es = 1; break;
-    case LDPC_CH_BIAWGN: rp.in_mode = IN_BIAWGN; rp.in_es = (in.in_dtype == LDPC_F64) ? 8 : 4; break;
+    case LDPC_CH_BIAWGN: rp.in_mode = IN_BIAWGN; rp.in_es = (int)in_elem_size(in.in_dtype); break;
     default: return fail(h, LDPC_EINVAL, "bad channel for MSA/SPA");
     }
     rp.B = B; rp.limit = limit;
@@ -862,9 +884,10 @@ int decode_any(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_
 {
     if (!h) return LDPC_EINVAL;
     if (B <= 0) return fail(h, LDPC_EINVAL, "B must be positive");
+    if (B > kMaxFramesPerCall) return fail(h, LDPC_EINVAL, "B too large: at most 2096640 frames per call (grid limits of the layout kernels); split the batch");
     if (!in.src || !x_hat || !iters || !ws) return fail(h, LDPC_EINVAL, "null buffer");
     const unsigned path = flags & LDPC_PATH_MASK;
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER(h);
     if (algo == LDPC_BEC) {
         if (in.channel != LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "BEC decoder needs symbol input");
         if (marg_out) return fail(h, LDPC_EINVAL, "marg_out is MSA/SPA only");
@@ -1088,6 +1111,8 @@ void ldpc_destroy(ldpc_t *h)
         for (auto &sl : h->stage->slot) {
             if (sl.d_y) cudaFree(sl.d_y);
             if (sl.d_x) cudaFree(sl.d_x);
+            if (sl.d_yp) cudaFree(sl.d_yp);
+            if (sl.d_xp) cudaFree(sl.d_xp);
             if (sl.d_it) cudaFree(sl.d_it);
             if (sl.d_rs) cudaFree(sl.d_rs);
             if (sl.ws) cudaFree(sl.ws);
@@ -1145,7 +1170,7 @@ int ldpc_decode_channel(ldpc_t *h, int channel, int algo, int dtype, double para
     if (!h) return LDPC_EINVAL;
     if (algo == LDPC_BEC) channel = LDPC_CH_BEC;
     if (channel < LDPC_CH_PRIORS || channel > LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "bad channel");
-    if ((channel == LDPC_CH_PRIORS || channel == LDPC_CH_BIAWGN) && y_dtype != LDPC_F32 && y_dtype != LDPC_F64)
+    if ((channel == LDPC_CH_PRIORS || channel == LDPC_CH_BIAWGN) && !in_dtype_ok(y_dtype))
         return fail(h, LDPC_EINVAL, "bad y_dtype");
     InSpec in;
     in.channel = channel;
@@ -1161,7 +1186,7 @@ int ldpc_llr_bsc(ldpc_t *h, int dtype, double llr, const uint8_t *y, void *prior
 {
     if (!h || !y || !priors) return fail(h, LDPC_EINVAL, "null buffer");
     if (count == 0) return LDPC_OK;
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER(h);
     const int blocks = (int)std::min<size_t>((count + 255) / 256, (size_t)h->sm_count * 32);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == LDPC_F32) LAUNCH(h, (llr_flat<uint8_t, float, IN_BSC>), blocks, 256, s, y, (float *)priors, count, llr);
@@ -1174,7 +1199,7 @@ int ldpc_llr_biawgn(ldpc_t *h, int y_dtype, int dtype, double noise_var, const v
 {
     if (!h || !y || !priors) return fail(h, LDPC_EINVAL, "null buffer");
     if (count == 0) return LDPC_OK;
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER(h);
     const int blocks = (int)std::min<size_t>((count + 255) / 256, (size_t)h->sm_count * 32);
     cudaStream_t s = (cudaStream_t)stream;
     if (y_dtype == LDPC_F64 && dtype == LDPC_F64) LAUNCH(h, (llr_flat<double, double, IN_BIAWGN>), blocks, 256, s, (const double *)y, (double *)priors, count, noise_var);
@@ -1191,7 +1216,7 @@ int ldpc_channel_generate(ldpc_t *h, int channel, double param, const uint8_t *x
     if (!h) return LDPC_EINVAL;
     if (B <= 0 || !y) return fail(h, LDPC_EINVAL, "bad arguments");
     if (!(param >= 0.0)) return fail(h, LDPC_EINVAL, "channel parameter must be >= 0");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER(h);
     const Tables &t = h->t;
     const long long total = (long long)B * ((t.n + 3) / 4);
     const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
@@ -1209,7 +1234,7 @@ int ldpc_count_errors(ldpc_t *h, const uint8_t *x_hat, const uint8_t *x, int B, 
 {
     if (!h) return LDPC_EINVAL;
     if (B <= 0 || !x_hat || !bit_errs) return fail(h, LDPC_EINVAL, "bad arguments");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER(h);
     LAUNCH(h, count_errors, (B + 7) / 8, 256, (cudaStream_t)stream, x_hat, x, B, h->t.n, bit_errs);
     return check_launch(h, "count_errors");
 }
@@ -1221,13 +1246,15 @@ int ldpc_debug_step(ldpc_t *h, int algo, int dtype, int which, int B, const void
     if (B <= 0 || !msg_in || !msg_out || !workspace) return fail(h, LDPC_EINVAL, "bad arguments");
     if (algo != LDPC_MSA && algo != LDPC_SPA) return fail(h, LDPC_EINVAL, "debug step is MSA/SPA only");
     if (which != 0 && which != 1) return fail(h, LDPC_EINVAL, "which must be 0 (CN) or 1 (VN)");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER(h);
     if (dtype == LDPC_F32)
         return debug_step_t<float>(h, algo, which, B, prior, msg_in, msg_out, marg, workspace, workspace_bytes, (cudaStream_t)stream);
     if (dtype == LDPC_F64)
         return debug_step_t<double>(h, algo, which, B, prior, msg_in, msg_out, marg, workspace, workspace_bytes, (cudaStream_t)stream);
     return fail(h, LDPC_EINVAL, "bad dtype");
 }
+
+size_t ldpc_packed_row_bytes(int n) { return n > 0 ? align_up(((size_t)n + 7) / 8, 16) : 0; }
 
 int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
                      const void *y, int y_dtype, int B, int max_iter, int iter_cap,
@@ -1236,17 +1263,23 @@ int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
     if (!h) return LDPC_EINVAL;
     if (B <= 0 || !y || !x_hat || !iters) return fail(h, LDPC_EINVAL, "bad arguments");
     if (algo == LDPC_BEC) channel = LDPC_CH_BEC;
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER(h);
     int rc = ensure_stage(h);
     if (rc) return rc;
     const Tables &t = h->t;
+    const bool in_packed = (flags & LDPC_IN_PACKED) != 0, out_packed = (flags & LDPC_OUT_PACKED) != 0;
+    const int planes = (channel == LDPC_CH_BEC) ? 2 : 1;                  // erasure symbols: value plane + erasure plane
+    const size_t pstride = ldpc_packed_row_bytes(t.n);
     size_t in_es;
     switch (channel) {
-    case LDPC_CH_PRIORS: in_es = elem_size(y_dtype); if (y_dtype != dtype) return fail(h, LDPC_EINVAL, "priors must have the message dtype"); break;
-    case LDPC_CH_BIAWGN: in_es = elem_size(y_dtype); break;
+    case LDPC_CH_PRIORS: in_es = in_elem_size(y_dtype); if (!in_dtype_ok(y_dtype)) return fail(h, LDPC_EINVAL, "bad y_dtype"); break;
+    case LDPC_CH_BIAWGN: in_es = in_elem_size(y_dtype); if (!in_dtype_ok(y_dtype)) return fail(h, LDPC_EINVAL, "bad y_dtype"); break;
     case LDPC_CH_BSC: case LDPC_CH_BEC: in_es = 1; break;
     default: return fail(h, LDPC_EINVAL, "bad channel");
     }
+    if (in_packed && channel != LDPC_CH_BSC && channel != LDPC_CH_BEC)
+        return fail(h, LDPC_EINVAL, "LDPC_IN_PACKED is for BSC / BEC symbol input");
+    const unsigned dflags = flags & ~(LDPC_IN_PACKED | LDPC_OUT_PACKED | LDPC_HOST_ASYNC);
     if (chunk <= 0) {
         // Enough chunks to overlap H2D / decode / D2H on the 3 slot streams and keep the pipeline's ramp and tail short
         // (B / 16; scripts/e2e_probe.py: 2048-frame chunks of the n = 1200 code reach 0.90 of a plain pinned H2D copy,
@@ -1260,6 +1293,8 @@ int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
         chunk = (int)std::max<size_t>(128, c / 128 * 128);
     }
     chunk = std::min(chunk, B);
+    const size_t in_row = in_packed ? planes * pstride : (size_t)t.n * in_es;      // bytes of one frame on the host side
+    const size_t out_row = out_packed ? planes * pstride : (size_t)t.n;
 
     HostStage *st = h->stage;
     int idx = st->next;
@@ -1270,6 +1305,8 @@ int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
         if (wsb == 0) return fail(h, LDPC_EINVAL, "bad algo/dtype");
         if ((rc = grow(h, &sl.d_y, &sl.y_bytes, (size_t)nb * t.n * in_es)) != 0) return rc;
         if ((rc = grow(h, &sl.d_x, &sl.x_bytes, (size_t)nb * t.n)) != 0) return rc;
+        if (in_packed && (rc = grow(h, &sl.d_yp, &sl.yp_bytes, (size_t)nb * in_row)) != 0) return rc;
+        if (out_packed && (rc = grow(h, &sl.d_xp, &sl.xp_bytes, (size_t)nb * out_row)) != 0) return rc;
         if (sl.f_cap < (size_t)nb) {
             if (sl.d_it) cudaFree(sl.d_it);
             if (sl.d_rs) cudaFree(sl.d_rs);
@@ -1280,28 +1317,89 @@ int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
         }
         if ((rc = grow(h, &sl.ws, &sl.ws_bytes, wsb)) != 0) return rc;
 
-        const char *src = (const char *)y + (size_t)b0 * t.n * in_es;
-        CUDA_TRY(h, cudaMemcpyAsync(sl.d_y, src, (size_t)nb * t.n * in_es, cudaMemcpyHostToDevice, sl.stream));
+        const char *src = (const char *)y + (size_t)b0 * in_row;
+        const int pblocks = (int)std::min<long long>(((long long)nb * ((t.n + 7) / 8) + 255) / 256, (long long)h->sm_count * 16);
+        if (in_packed) {
+            CUDA_TRY(h, cudaMemcpyAsync(sl.d_yp, src, (size_t)nb * in_row, cudaMemcpyHostToDevice, sl.stream));
+            LAUNCH(h, unpack_rows, pblocks, 256, sl.stream, sl.d_yp, (uint8_t *)sl.d_y, nb, t.n, (int)pstride, planes);
+        } else {
+            CUDA_TRY(h, cudaMemcpyAsync(sl.d_y, src, (size_t)nb * in_row, cudaMemcpyHostToDevice, sl.stream));
+        }
         InSpec in;
         in.channel = channel; in.in_dtype = y_dtype; in.src = sl.d_y; in.y_hard = nullptr; in.param = param;
         rc = decode_any(h, algo, dtype, in, nb, max_iter, iter_cap, sl.d_x, sl.d_it, sl.d_rs, nullptr,
-                        sl.ws, sl.ws_bytes, flags, sl.stream);
+                        sl.ws, sl.ws_bytes, dflags, sl.stream);
         if (rc) return rc;
-        CUDA_TRY(h, cudaMemcpyAsync(x_hat + (size_t)b0 * t.n, sl.d_x, (size_t)nb * t.n, cudaMemcpyDeviceToHost, sl.stream));
+        if (out_packed) {
+            LAUNCH(h, pack_rows, std::min((nb + 7) / 8, h->sm_count * 16), 256, sl.stream, sl.d_x, sl.d_xp, nb, t.n, (int)pstride, planes);
+            CUDA_TRY(h, cudaMemcpyAsync(x_hat + (size_t)b0 * out_row, sl.d_xp, (size_t)nb * out_row, cudaMemcpyDeviceToHost, sl.stream));
+        } else {
+            CUDA_TRY(h, cudaMemcpyAsync(x_hat + (size_t)b0 * out_row, sl.d_x, (size_t)nb * out_row, cudaMemcpyDeviceToHost, sl.stream));
+        }
         CUDA_TRY(h, cudaMemcpyAsync(iters + b0, sl.d_it, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
         if (reason) CUDA_TRY(h, cudaMemcpyAsync(reason + b0, sl.d_rs, (size_t)nb, cudaMemcpyDeviceToHost, sl.stream));
     }
     st->next = idx % HostStage::kSlots;
     if (flags & LDPC_HOST_ASYNC) return LDPC_OK;
     for (auto &sl : st->slot) CUDA_TRY(h, cudaStreamSynchronize(sl.stream));
-    return LDPC_OK;
+    return check_launch(h, "decode_host");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Monte-Carlo round on the device (the loop body of src/main.py:37-45 for B frames at once)
+// ------------------------------------------------------------------------------------------------
+static size_t mc_y_bytes(const ldpc_t *h, int channel, int B) { return align_up((size_t)B * h->t.n * (channel == LDPC_CH_BIAWGN ? 4 : 1), 256); }
+
+size_t ldpc_mc_scratch_bytes(const ldpc_t *h, int channel, int algo, int dtype, int B)
+{
+    if (!h || B <= 0) return 0;
+    if (channel == LDPC_CH_BEC) algo = LDPC_BEC;
+    const size_t ws = workspace_bytes_impl(h, algo, dtype, B, false);
+    if (ws == 0) return 0;
+    return mc_y_bytes(h, channel, B) + align_up((size_t)B * h->t.n, 256) + align_up((size_t)B * 4, 256) + align_up(ws, 256) + 256;
+}
+
+int ldpc_count_accumulate(ldpc_t *h, const uint8_t *x_hat, const uint8_t *x, const int32_t *iters, int B,
+                          int32_t *bit_errs, long long *counters, int nhist, void *stream)
+{
+    if (!h) return LDPC_EINVAL;
+    if (B <= 0 || !x_hat || !iters || !counters || nhist < 0) return fail(h, LDPC_EINVAL, "bad arguments");
+    ENTER(h);
+    LAUNCH(h, count_accumulate, (B + 7) / 8, 256, (cudaStream_t)stream, x_hat, x, iters, B, h->t.n, bit_errs,
+           reinterpret_cast<unsigned long long *>(counters), nhist);
+    return check_launch(h, "count_accumulate");
+}
+
+int ldpc_mc_round(ldpc_t *h, int channel, int algo, int dtype, double ch_param, double dec_param,
+                  const uint8_t *x, unsigned long long seed, unsigned long long frame0, int B,
+                  int max_iter, int iter_cap, long long *counters, int nhist,
+                  void *scratch, size_t scratch_bytes, unsigned flags, void *stream)
+{
+    if (!h) return LDPC_EINVAL;
+    if (B <= 0 || !counters || !scratch || nhist < 0) return fail(h, LDPC_EINVAL, "bad arguments");
+    if (channel == LDPC_CH_BEC) algo = LDPC_BEC;
+    if (scratch_bytes < ldpc_mc_scratch_bytes(h, channel, algo, dtype, B) || (reinterpret_cast<uintptr_t>(scratch) & 255u) != 0)
+        return fail(h, LDPC_EWORKSPACE, "scratch too small (ldpc_mc_scratch_bytes) or not 256-byte aligned");
+    const Tables &t = h->t;
+    Carver cv(scratch);
+    void *y = cv.take<char>(mc_y_bytes(h, channel, B));
+    uint8_t *x_hat = cv.take<uint8_t>((size_t)B * t.n);
+    int32_t *iters = cv.take<int32_t>((size_t)B);
+    const size_t ws_bytes = workspace_bytes_impl(h, algo, dtype, B, false);
+    void *ws = cv.take<char>(ws_bytes);
+    int rc = ldpc_channel_generate(h, channel, ch_param, x, seed, frame0, B, y, stream);
+    if (rc) return rc;
+    rc = ldpc_decode_channel(h, channel, algo, dtype, dec_param, y, LDPC_F32, B, max_iter, iter_cap, x_hat, iters, nullptr, nullptr,
+                             ws, ws_bytes, flags, stream);
+    if (rc) return rc;
+    return ldpc_count_accumulate(h, x_hat, x, iters, B, nullptr, counters, nhist, stream);
 }
 
 int ldpc_host_sync(ldpc_t *h)
 {
     if (!h) return LDPC_EINVAL;
     if (!h->stage) return LDPC_OK;
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER(h);
     for (auto &sl : h->stage->slot) CUDA_TRY(h, cudaStreamSynchronize(sl.stream));
     return LDPC_OK;
 }

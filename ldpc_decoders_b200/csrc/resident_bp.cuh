@@ -63,7 +63,7 @@ struct ResParams {
     int cn_items, vn_items;            // m * Q, n * Q
     const void *src;                   // [B][n] received block (or priors)
     int in_mode;                       // IN_COPY / IN_BSC / IN_BIAWGN
-    int in_es;                         // element size of src: 1 (BSC), 4, 8
+    int in_es;                         // element size of src: 1 (BSC), 2 (binary16), 4, 8
     const uint8_t *y_hard;             // optional hard input for IN_COPY
     double param, inv_param;           // inv_param = 1 / param (BIAWGN fast path)
     int B, limit, bound_reason;
@@ -101,6 +101,14 @@ __host__ __device__ inline ResSmem resident_smem_layout(int Q, int n, int m, int
 // (io_kernels.cuh llr_map; BIAWGN without a float64 division in the common case, ldpc_math.cuh llr_biawgn_f32).
 __device__ __noinline__ float res_llr_biawgn_exact(double t, double param) { return (float)(t / param); }
 
+// Element v of a received row as float64: in_es = 8 (float64), 4 (float32) or 2 (binary16, LDPC_F16); all exact.
+__device__ __forceinline__ double res_in_f64(const void *row, int v, int in_es)
+{
+    if (in_es == 8) return ((const double *)row)[v];
+    if (in_es == 4) return (double)((const float *)row)[v];
+    return (double)__half2float(((const __half *)row)[v]);
+}
+
 __device__ __forceinline__ float res_llr(const void *row, int v, int in_mode, int in_es, double param, double inv_param, uint32_t *hard)
 {
     *hard = 0u;
@@ -111,13 +119,13 @@ __device__ __forceinline__ float res_llr(const void *row, int v, int in_mode, in
         const float lf = (float)param;                                   // (float)(L * (+-1)) == +-(float)L
         val = y ? -lf : lf;
     } else if (in_mode == IN_BIAWGN) {
-        const double y = (in_es == 8) ? ((const double *)row)[v] : (double)((const float *)row)[v];
+        const double y = res_in_f64(row, v, in_es);
         const double t = -2.0 * y;                                       // exact
         const double pr = t * inv_param;
         val = (float)pr;
         if (!llr_biawgn_fast_ok(pr)) val = res_llr_biawgn_exact(t, param);   // rare: keep the division out of line
     } else {
-        val = (in_es == 8) ? (float)((const double *)row)[v] : ((const float *)row)[v];
+        val = (float)res_in_f64(row, v, in_es);
     }
     return __fadd_rn(val, 0.0f);          // -0.0 -> +0.0 (value-neutral, see cn_msa_lean), NaN -> canonical
 }

@@ -66,7 +66,7 @@ __device__ __forceinline__ double vd_llr(const void *row, int v, int in_mode, in
         *hard = (uint32_t)(y != 0);
         val = param * (double)(1 - 2 * (int)y);
     } else {
-        const double y = (in_es == 8) ? ((const double *)row)[v] : (double)((const float *)row)[v];
+        const double y = res_in_f64(row, v, in_es);
         val = (in_mode == IN_BIAWGN) ? __ddiv_rn(-2.0 * y, param) : y;
     }
     return __dadd_rn(val, 0.0);

@@ -119,6 +119,17 @@ __device__ __forceinline__ void vp_load4(const unsigned char *row, int i4, int i
 #pragma unroll
                 for (int j = 0; j < 4; ++j) y[j] = reinterpret_cast<const double *>(row)[i4 * 4 + j];
             }
+        } else if (in_es == 2) {                                         // binary16 rows (LDPC_F16)
+            __half hv[4];
+            if (vec) {
+                const uint2 a = *reinterpret_cast<const uint2 *>(row + (size_t)i4 * 8);
+                *reinterpret_cast<uint2 *>(hv) = a;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hv[j] = reinterpret_cast<const __half *>(row)[i4 * 4 + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) y[j] = (double)__half2float(hv[j]);
         } else {
             float f[4];
             if (vec) {

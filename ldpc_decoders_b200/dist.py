@@ -96,6 +96,31 @@ class Comm:
         self.dist.all_gather(out, t)
         return np.stack([o.cpu().numpy() for o in out])
 
+    # ---- the same collectives on torch tensors that already live where the backend wants them (NCCL: on the GPU):
+    # no host round trip on the way in, the caller decides when (and whether) the result is read back
+    def _native(self, t):
+        return t if (self.device == "cuda") == t.is_cuda else t.to(self.device)
+
+    def allreduce_tensor(self, t):
+        """Element-wise SUM over ranks of an int64 tensor, returned on the tensor's own device (in place when possible)."""
+        if self.dist is None:
+            return t
+        w = self._native(t)
+        self.dist.all_reduce(w, op=self.dist.ReduceOp.SUM)
+        if w is not t:
+            t.copy_(w)
+        return t
+
+    def allgather_tensor(self, t):
+        """Equal-length 1-D tensor per rank -> [world, len] in rank order, on the tensor's own device."""
+        import torch
+        if self.dist is None:
+            return t[None, :]
+        w = self._native(t.contiguous())
+        out = torch.empty((self.world,) + tuple(w.shape), dtype=w.dtype, device=w.device)
+        self.dist.all_gather_into_tensor(out, w)
+        return out if out.device == t.device else out.to(t.device)
+
     def barrier(self):
         if self.dist is not None:
             self.dist.barrier()

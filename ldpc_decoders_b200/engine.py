@@ -14,7 +14,46 @@ from . import _lib
 from ._lib import LdpcError
 from .graph import Tables
 
-_NP2DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64}
+_NP2DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64, np.dtype(np.float16): _lib.F16}
+
+
+def packed_row_bytes(n):
+    """Bytes of one bit-packed row of n symbols (ldpc_packed_row_bytes): ceil(n / 8) rounded up to 16."""
+    return (((int(n) + 7) // 8) + 15) // 16 * 16
+
+
+def pack_bits(Y, out=None):
+    """Hard bits [B, n] (0/1) -> bit-packed rows uint8 [B, packed_row_bytes(n)] for decode_host(..., packed_in=True).
+    Bit v of a row is bit (v & 7) of byte (v >> 3) (numpy.packbits, bitorder="little")."""
+    Y = np.asarray(Y)
+    B, n = Y.shape
+    out = np.zeros((B, packed_row_bytes(n)), np.uint8) if out is None else out
+    out[:, :(n + 7) // 8] = np.packbits(Y != 0, axis=1, bitorder="little")
+    out[:, (n + 7) // 8:] = 0
+    return out
+
+
+def pack_symbols(Y, out=None):
+    """BEC symbols [B, n] in {0, 1, 2} -> two packed planes per row: value plane (== 1), then erasure plane (== 2)."""
+    Y = np.asarray(Y)
+    B, n = Y.shape
+    s = packed_row_bytes(n)
+    out = np.zeros((B, 2 * s), np.uint8) if out is None else out
+    pack_bits(Y == 1, out[:, :s])
+    pack_bits(Y == 2, out[:, s:])
+    return out
+
+
+def unpack_bits(P, n):
+    """Inverse of pack_bits: packed rows -> uint8 [B, n]."""
+    return np.unpackbits(np.asarray(P)[:, :(n + 7) // 8], axis=1, count=n, bitorder="little")
+
+
+def unpack_symbols(P, n):
+    """Inverse of pack_symbols: two packed planes -> uint8 [B, n] symbols {0, 1, 2}."""
+    s = packed_row_bytes(n)
+    val, er = unpack_bits(np.asarray(P)[:, :s], n), unpack_bits(np.asarray(P)[:, s:], n)
+    return np.where(er != 0, 2, val).astype(np.uint8)
 
 
 def _torch():
@@ -140,6 +179,9 @@ class Engine:
         dev = self._dev()
         if out is None:
             out = {}
+        for key, shape in (("x_hat", (B, t.n)), ("iters", (B,))):        # buffers of another batch size are not reused
+            if out.get(key) is not None and tuple(out[key].shape) != shape:
+                out[key] = None
         x_hat = out.get("x_hat")
         if x_hat is None:
             x_hat = torch.empty((B, t.n), dtype=torch.uint8, device=dev)
@@ -172,9 +214,12 @@ class Engine:
                 raise TypeError("BSC/BEC input must be uint8")
             y_dtype = _lib.F32
         else:
-            y_dtype = {torch.float32: _lib.F32, torch.float64: _lib.F64}[y.dtype]
+            y_dtype = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.float16: _lib.F16}[y.dtype]
         dev = self._dev()
         out = {} if out is None else out
+        for key, shape in (("x_hat", (B, t.n)), ("iters", (B,)), ("reason", (B,))):     # buffers of another batch size
+            if out.get(key) is not None and tuple(out[key].shape) != shape:
+                out[key] = None
         x_hat = out.get("x_hat")
         if x_hat is None:
             x_hat = torch.empty((B, t.n), dtype=torch.uint8, device=dev)
@@ -199,6 +244,8 @@ class Engine:
         torch = _torch()
         t = self.tables
         dt = torch.float32 if channel == _lib.CH_BIAWGN else torch.uint8
+        if out is not None and (tuple(out.shape) != (int(B), t.n) or out.dtype != dt or not out.is_contiguous()):
+            out = None                         # a cached block of another batch size / channel: never write past it
         y = out if out is not None else torch.empty((int(B), t.n), dtype=dt, device=self._dev())
         rc = self.lib.ldpc_channel_generate(self.handle, channel, float(param), None if x is None else x.data_ptr(),
                                             int(seed) & (2 ** 64 - 1), int(frame0), int(B), y.data_ptr(),
@@ -232,13 +279,42 @@ class Engine:
         out["bit_errs"] = self.count_errors(out["x_hat"], x, stream)
         return out
 
+    def new_counters(self, nhist):
+        """Zeroed device int64 [4 + nhist] Monte-Carlo counters for mc_round: tot, wec, bec, sum of iters, histogram."""
+        torch = _torch()
+        return torch.zeros(4 + int(nhist), dtype=torch.int64, device=self._dev())
+
+    def mc_round(self, channel, algo, dtype, param, B, seed, frame0, counters, nhist, x=None, max_iter=10, iter_cap=0,
+                 flags=0, stream=None):
+        """One Monte-Carlo round that never leaves the GPU (ldpc_mc_round): draw frames frame0 .. frame0 + B - 1 of the
+        word x, decode, add (tot, wec, bec, sum iters, iteration histogram) to the device tensor `counters`
+        (new_counters(nhist)); asynchronous on the current stream.  `param` as in simulate()."""
+        torch = _torch()
+        if counters.dtype != torch.int64 or counters.numel() < 4 + int(nhist) or not counters.is_cuda:
+            raise ValueError("counters must be a CUDA int64 tensor of 4 + nhist elements")
+        dec_algo = _lib.BEC if channel == _lib.CH_BEC else algo
+        need = int(self.lib.ldpc_mc_scratch_bytes(self.handle, channel, dec_algo, dtype, int(B)))
+        if need == 0:
+            raise LdpcError("ldpc_mc_scratch_bytes: bad arguments")
+        if getattr(self, "_mc_scratch", None) is None or self._mc_scratch.numel() < need:
+            self._mc_scratch = None
+            self._mc_scratch = torch.empty(need, dtype=torch.uint8, device=self._dev())
+        dec_param = float(np.log(1 - param) - np.log(param)) if channel == _lib.CH_BSC else float(param)
+        rc = self.lib.ldpc_mc_round(self.handle, channel, dec_algo, dtype, float(param), dec_param,
+                                    None if x is None else x.data_ptr(), int(seed) & (2 ** 64 - 1), int(frame0), int(B),
+                                    int(max_iter), int(iter_cap), counters.data_ptr(), int(nhist),
+                                    self._mc_scratch.data_ptr(), self._mc_scratch.numel(), flags, self._stream_ptr(stream))
+        _lib.check(self.handle, rc)
+
     # ------------------------------------------------------------------ host-buffer decode (e2e path)
     def decode_host(self, channel, algo, dtype, param, y, max_iter=10, iter_cap=0, chunk=0, flags=0,
-                    x_hat=None, iters=None, reason=None, wait=True):
+                    x_hat=None, iters=None, reason=None, wait=True, packed_in=False, packed_out=False):
         """Decode a batch held in host memory (numpy); H2D / decode / D2H are pipelined in the library.
 
-        y [B, n]: uint8 for BSC/BEC, float32/float64 for BIAWGN / PRIORS.  Pinned arrays
+        y [B, n]: uint8 for BSC/BEC, float32 / float64 / float16 for BIAWGN / PRIORS.  Pinned arrays
         (``pinned_empty``) make the copies asynchronous.  Returns numpy (x_hat, iters, reason).
+        packed_in (BSC / BEC): y is bit-packed rows (pack_bits / pack_symbols) — 1 bit per hard bit on PCIe instead of
+        a byte; packed_out: x_hat comes back bit-packed the same way (unpack_bits / unpack_symbols).
         wait=False (a stream of batches): returns once the work is enqueued, so the next call overlaps this one's
         tail; y and the output arrays must be pinned, caller-provided and left alone until ``host_sync()``.
         """
@@ -248,7 +324,15 @@ class Engine:
             flags |= _lib.HOST_ASYNC
         t = self.tables
         y = np.ascontiguousarray(y)
-        if y.ndim != 2 or y.shape[1] != t.n:
+        planes = 2 if (channel == _lib.CH_BEC or algo == _lib.BEC) else 1
+        prow = planes * packed_row_bytes(t.n)
+        if packed_in:
+            if channel not in (_lib.CH_BSC, _lib.CH_BEC):
+                raise ValueError("packed_in is for BSC / BEC symbol input")
+            if y.ndim != 2 or y.shape[1] != prow or y.dtype != np.uint8:
+                raise ValueError("packed y must be uint8 [B, %d]" % prow)
+            flags |= _lib.IN_PACKED
+        elif y.ndim != 2 or y.shape[1] != t.n:
             raise ValueError("y must be [B, n]")
         B = y.shape[0]
         if channel in (_lib.CH_BSC, _lib.CH_BEC):
@@ -257,14 +341,21 @@ class Engine:
             y_dtype = _lib.F32
         else:
             if y.dtype not in _NP2DT:
-                raise TypeError("input must be float32 or float64")
+                raise TypeError("input must be float16, float32 or float64")
             y_dtype = _NP2DT[y.dtype]
+        if packed_out:
+            flags |= _lib.OUT_PACKED
+        xshape = (B, prow) if packed_out else (B, t.n)
         if x_hat is None:
-            x_hat = np.empty((B, t.n), np.uint8)
+            x_hat = np.empty(xshape, np.uint8)
+        elif tuple(x_hat.shape) != xshape or x_hat.dtype != np.uint8 or not x_hat.flags.c_contiguous:
+            raise ValueError("x_hat must be a contiguous uint8 array of shape %r" % (xshape,))
         if iters is None:
             iters = np.empty(B, np.int32)
         if reason is None:
             reason = np.empty(B, np.uint8)
+        if iters.shape != (B,) or reason.shape != (B,):
+            raise ValueError("iters / reason must have one element per frame")
         rc = self.lib.ldpc_decode_host(self.handle, channel, algo, dtype, float(param), y.ctypes.data, y_dtype,
                                        B, int(max_iter), int(iter_cap), x_hat.ctypes.data, iters.ctypes.data,
                                        reason.ctypes.data, int(chunk), flags)
@@ -314,7 +405,8 @@ def pinned_empty(shape, dtype):
     """A numpy array backed by pinned (page-locked) host memory, for asynchronous copies."""
     torch = _torch()
     tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32,
-           np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+           np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+           np.dtype(np.float16): torch.float16, np.dtype(np.int64): torch.int64}[np.dtype(dtype)]
     t = torch.empty(tuple(shape) if not np.isscalar(shape) else (shape,), dtype=tdt, pin_memory=True)
     return t.numpy()          # the array keeps the tensor (and its pinned allocation) alive
 

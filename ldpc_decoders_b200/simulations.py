@@ -71,13 +71,23 @@ def main(argv=None):
     p = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     p.add_argument('case', nargs='+', choices=sorted(all_cases))
     p.add_argument('--print', action='store_true', help='only print the case lines (what the reference does)')
+    p.add_argument('--limit', type=int, default=0, help='run only the first LIMIT case lines of each named case')
     args, extra = p.parse_known_args(argv)
+    comm = None
+    out = []
     for name in args.case:
-        for case in all_cases[name]():
+        cases = all_cases[name]()
+        for case in (cases[:args.limit] if args.limit > 0 else cases):
             if args.print:
                 print(' '.join(case + extra), flush=True)
-            else:
-                sim.main(case + extra)
+                continue
+            if comm is None:                       # ONE process group for every case (not an init / destroy per case)
+                from .dist import Comm
+                comm = Comm()
+            out.append((case[:3], sim.main(case + extra, comm=comm)))
+    if comm is not None:
+        comm.close()
+    return out
 
 
 if __name__ == '__main__':

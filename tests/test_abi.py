@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(_lib.SYMBOLS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.ldpc_abi_version() == 1
+    assert lib.ldpc_abi_version() == 2
 
 
 def test_library_is_sm100a_only():

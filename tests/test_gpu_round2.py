@@ -1,0 +1,358 @@
+"""GPU tier, round 2: the parity holes VERDICT r1 listed, the device-side Monte-Carlo counters, bit-packed / binary16
+host I/O, the published curves, and the N-GPU Monte-Carlo run under NCCL (needs >= 2 GPUs, skipped otherwise)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import _golden as G
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    from ldpc_decoders_b200 import Tables, _lib, bec, biawgn, bsc, engine, models
+    torch.cuda.set_device(0)
+    return dict(torch=torch, Tables=Tables, lib=_lib, bec=bec, biawgn=biawgn, bsc=bsc, engine=engine, models=models)
+
+
+_tabs = {}
+
+
+def tables(mods, name):
+    if name not in _tabs:
+        _tabs[name] = mods["Tables"](*G.code_tables(name))
+    return _tabs[name]
+
+
+def write_code_txt(directory, name):
+    m, n, rows, cols = G.code_tables(name)
+    with open(os.path.join(directory, name + ".txt"), "w") as fp:
+        for c in range(m):
+            fp.write(" ".join(str(v + 1) for v in cols[rows == c]) + "\n")
+
+
+# ------------------------------------------------------------------------------------------ parity holes
+@pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_3"])
+def test_spa_degenerate_priors_against_the_f64_oracle(mods, code):
+    """Saturated, exactly-zero, NaN and -0.0 priors: the float64 formula mirror on the GPU against the float64 oracle
+    (which the CPU tier pins to the reference) — not only CUDA against CUDA.  Words and iteration counts must be
+    identical on every frame whose oracle marginals stay finite; flooded frames (inf / NaN everywhere) must still agree
+    on 90 %; the float32 kernels (on-chip and streaming) must decode the well-conditioned frames to the same words."""
+    torch, lib = mods["torch"], mods["lib"]
+    tab = tables(mods, code)
+    og = O.Graph(*G.code_tables(code))
+    eng = mods["engine"].engine_for(tab)
+    B = 600
+    Y = G.channel_send("biawgn", 1.0, np.zeros((B, tab.n), np.int64), 4242)
+    pri = O.llr_biawgn(1.0, Y)
+    pri[100:300] *= 12.0                                   # confidently wrong bits: saturates within a few iterations
+    pri[300:400, ::7] = 0.0                                # exact zeros -> 0/0 = NaN messages (bpa.py:74)
+    pri[400:420, 3] = np.nan
+    pri[420:440, 5] = -0.0
+    for mi in (10, 40):
+        with np.errstate(all="ignore"):
+            ref = O.bp_decode(og, O.SPA, pri, max_iter=mi, want_marg=True, nthreads=8)
+        finite = np.isfinite(ref["marg"]).all(axis=1)
+        out = eng.decode_device(lib.SPA, torch.from_numpy(pri).cuda(), max_iter=mi)       # float64: formula mirror
+        xh, it = out["x_hat"].cpu().numpy(), out["iters"].cpu().numpy()
+        same = (it == ref["iters"]) & (xh == ref["x_hat"]).all(axis=1)
+        assert finite[:100].all() and finite[440:].all()
+        assert same[finite].all(), np.flatnonzero(~same & finite)[:8]
+        assert same[~finite].mean() >= 0.9 if (~finite).any() else True
+        # float32 kernels: frames that are well conditioned in the reference (plain noise, and the -0.0 rows)
+        good = np.r_[0:100, 420:600]
+        margin = np.abs(ref["marg"][good]).min(axis=1) > 1e-3
+        for flags in (lib.PATH_RESIDENT, lib.PATH_STREAMING):
+            o32 = eng.decode_device(lib.SPA, torch.from_numpy(pri.astype(np.float32)).cuda(), max_iter=mi, flags=flags)
+            x32 = o32["x_hat"].cpu().numpy()[good]
+            agree = (x32 == ref["x_hat"][good]).all(axis=1)
+            assert agree[margin].mean() >= 0.99
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_msa_with_infinite_priors_matches_the_oracle(mods, dt):
+    """+-inf priors ("known" bits) are defined in the reference's min-sum as long as no inf - inf arises (probe, round 2:
+    the unmodified reference and the oracle agree on every frame); NaN priors make the reference itself RAISE
+    (math_utils.csr_csc_argmax mis-indexes a row that contains NaN), so they are outside the contract.  Both paths
+    must reproduce the oracle bit for bit on every frame whose oracle marginals stay NaN-free."""
+    torch, lib = mods["torch"], mods["lib"]
+    code = "1200_3_6_rand_ldpc_1"
+    tab = tables(mods, code)
+    og = O.Graph(*G.code_tables(code))
+    eng = mods["engine"].engine_for(tab)
+    B = 512
+    rng = np.random.RandomState(8)
+    Y = G.channel_send("biawgn", 2.0, np.ones((B, tab.n), np.int64), 31)
+    pri = O.llr_biawgn(2.0, Y)
+    known = rng.rand(B, tab.n) < .02
+    pri[:170][known[:170]] = np.inf                                    # "certainly 0" on a word of ones: wrong and infinite
+    pri[170:340][known[170:340]] = -np.inf                             # certainly 1: right
+    mix = known[340:]
+    pri[340:][mix] = np.where(rng.rand(int(mix.sum())) < .5, np.inf, -np.inf)
+    pri = pri.astype(dt)
+    with np.errstate(all="ignore"):
+        ref = O.bp_decode(og, O.MSA, pri, max_iter=10, want_marg=True, nthreads=8)
+    ok = ~np.isnan(ref["marg"]).any(axis=1)
+    assert ok.mean() > 0.9
+    d = torch.from_numpy(pri).cuda()
+    for flags in (lib.PATH_AUTO, lib.PATH_STREAMING):
+        out = eng.decode_device(lib.MSA, d, max_iter=10, flags=flags)
+        xh, it = out["x_hat"].cpu().numpy(), out["iters"].cpu().numpy()
+        assert (it[ok] == ref["iters"][ok]).all(), flags
+        assert (xh[ok] == ref["x_hat"][ok]).all(), flags
+
+
+@pytest.mark.parametrize("cw,mi", [(0, 10), (1, 10), (0, 100), (1, 100)])
+def test_bec_config2_1e5_frames_bit_exact(mods, cw, mi):
+    """BASELINE config 2: `1200_3_6_rand_ldpc_1` on the BEC, >= 1e5 frames per case with codeword 0 AND 1, max_iter 10
+    AND 100, erasure rates across the sweep of README.md:42 — words, iteration counts and exit reasons bit-exact."""
+    code = "1200_3_6_rand_ldpc_1"
+    tab = tables(mods, code)
+    og = O.Graph(*G.code_tables(code))
+    dec = mods["bec"].SPA(.4, tab, max_iter=mi)
+    total = 0
+    for k, p in enumerate((.5, .45, .425, .4, .375, .35, .3)):
+        frames = 15000
+        Y = G.channel_send("bec", p, np.zeros((frames, tab.n), np.int64) + cw, 1000 + 10 * cw + k).astype(np.uint8)
+        ref = O.bec_decode(og, Y, max_iter=mi, nthreads=8)
+        x_hat, iters, reason = dec.decode_batch(Y, return_reason=True)
+        assert (iters == ref["iters"]).all() and (reason == ref["reason"]).all() and (x_hat == ref["x_hat"]).all(), p
+        total += frames
+    assert total >= 100000
+
+
+def test_frames_per_call_limit_is_reported(mods):
+    lib = mods["lib"]
+    tab = tables(mods, "7_4_hamming")
+    eng = mods["engine"].engine_for(tab)
+    torch = mods["torch"]
+    y = torch.zeros((4, tab.n), dtype=torch.float32, device="cuda")
+    ws = eng.workspace(lib.MSA, lib.F32, 4)
+    xh = torch.empty((4, tab.n), dtype=torch.uint8, device="cuda")
+    it = torch.empty(4, dtype=torch.int32, device="cuda")
+    rc = eng.lib.ldpc_decode_channel(eng.handle, lib.CH_BIAWGN, lib.MSA, lib.F32, 1.0, y.data_ptr(), lib.F32, 3000000, 10, 0,
+                                     xh.data_ptr(), it.data_ptr(), None, None, ws.data_ptr(), ws.numel(), 0, None)
+    assert rc == -1 and b"too large" in eng.lib.ldpc_last_error(eng.handle)
+    out = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, lib.F32, 1.0, y, max_iter=10)     # the handle still works, no stale error
+    assert int(out["iters"].sum().item()) >= 0
+
+
+# ------------------------------------------------------------------------------------------ device-side counters
+@pytest.mark.parametrize("channel,algo,param,code", [("biawgn", "MSA", 2.0, "1200_3_6_rand_ldpc_1"),
+                                                      ("bsc", "SPA", .05, "1200_rho_x5_rand_ldpc_1"),
+                                                      ("bec", "SPA", .4, "1200_3_6_rand_ldpc_1"),
+                                                      ("biawgn", "SPA", 3.0, "7_4_hamming")])
+def test_mc_round_counters_equal_the_per_frame_results(mods, channel, algo, param, code):
+    """ldpc_mc_round (generate -> decode -> count, counters on the device) == Engine.simulate + host sums, for ragged
+    round sizes and several rounds into the same counters."""
+    torch, lib = mods["torch"], mods["lib"]
+    tab = tables(mods, code)
+    eng = mods["engine"].engine_for(tab)
+    ch = dict(biawgn=lib.CH_BIAWGN, bsc=lib.CH_BSC, bec=lib.CH_BEC)[channel]
+    al = lib.MSA if algo == "MSA" else lib.SPA
+    prm = 10 ** (-param / 10) if channel == "biawgn" else param
+    x = torch.ones(tab.n, dtype=torch.uint8, device="cuda") if channel == "biawgn" else None
+    nh = 12
+    c = eng.new_counters(nh)
+    exp = np.zeros(4 + nh, np.int64)
+    f0 = 12345
+    for B in (1, 7, 1000, 4097):
+        eng.mc_round(ch, al, lib.F32, prm, B, 99, f0, c, nh, x=x, max_iter=10)
+        r = eng.simulate(ch, al, lib.F32, prm, B, 99, f0, x=x, max_iter=10)
+        e, it = r["bit_errs"].cpu().numpy().astype(np.int64), r["iters"].cpu().numpy().astype(np.int64)
+        exp[0] += B; exp[1] += (e > 0).sum(); exp[2] += e.sum(); exp[3] += it.sum()
+        np.add.at(exp, 4 + np.minimum(it, nh - 1), 1)
+        f0 += B
+    assert (c.cpu().numpy() == exp).all()
+    assert exp[4:].sum() == exp[0] and 0 < exp[1] < exp[0]
+
+
+def test_simulate_buffers_follow_the_batch_size(mods):
+    """cached y / x_hat buffers of another batch size must not be reused (out-of-bounds write before)."""
+    from ldpc_decoders_b200 import biawgn
+    tab = tables(mods, "512_3_6_rand_ldpc_1")
+    dec = biawgn.MSA(2.0, tab, max_iter=10, dtype=np.float32)
+    x = np.ones(tab.n, np.int64)
+    small = dec.simulate_batch(x, 64, seed=3, frame0=0)
+    large = dec.simulate_batch(x, 4096, seed=3, frame0=0)
+    again = dec.simulate_batch(x, 64, seed=3, frame0=0)
+    assert small[0].shape == (64,) and large[0].shape == (4096,) and again[0].shape == (64,)
+    assert (large[0][:64] == small[0]).all() and (again[0] == small[0]).all() and (again[1] == small[1]).all()
+
+
+# ------------------------------------------------------------------------------------------ host I/O formats
+def test_bit_packed_host_io_bsc_and_bec(mods):
+    """LDPC_IN_PACKED / LDPC_OUT_PACKED: one bit per hard bit (two planes per erasure symbol) across PCIe, same results."""
+    lib, E = mods["lib"], mods["engine"]
+    for code in ("1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_10", "7_4_hamming", "12_3_4_ldpc"):
+        tab = tables(mods, code)
+        eng = E.engine_for(tab)
+        B = 3001
+        Yb = G.channel_send("bsc", .05, np.zeros((B, tab.n), np.int64), 5).astype(np.uint8)
+        llr = float(np.log(1 - .05) - np.log(.05))
+        xh, it, rs = eng.decode_host(lib.CH_BSC, lib.MSA, lib.F32, llr, Yb, max_iter=10, chunk=1024)
+        P = E.pack_bits(Yb)
+        assert P.shape == (B, E.packed_row_bytes(tab.n)) and (E.unpack_bits(P, tab.n) == Yb).all()
+        xp, it2, rs2 = eng.decode_host(lib.CH_BSC, lib.MSA, lib.F32, llr, P, max_iter=10, chunk=1024, packed_in=True, packed_out=True)
+        assert (it2 == it).all() and (rs2 == rs).all() and (E.unpack_bits(xp, tab.n) == xh).all()
+        assert (xp[:, (tab.n + 7) // 8:] == 0).all()
+        x3, it3, _ = eng.decode_host(lib.CH_BSC, lib.MSA, lib.F32, llr, Yb, max_iter=10, packed_out=True)
+        assert (it3 == it).all() and (E.unpack_bits(x3, tab.n) == xh).all()
+        Ye = G.channel_send("bec", .4, np.ones((B, tab.n), np.int64), 6).astype(np.uint8)
+        xh, it, rs = eng.decode_host(lib.CH_BEC, lib.BEC, lib.F32, 0.0, Ye, max_iter=100)
+        Pe = E.pack_symbols(Ye)
+        assert (E.unpack_symbols(Pe, tab.n) == Ye).all()
+        xp, it2, rs2 = eng.decode_host(lib.CH_BEC, lib.BEC, lib.F32, 0.0, Pe, max_iter=100, packed_in=True, packed_out=True)
+        assert (it2 == it).all() and (rs2 == rs).all() and (E.unpack_symbols(xp, tab.n) == xh).all()
+
+
+@pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_1", "margulis", "7_4_hamming"])
+def test_binary16_rows_decode_like_the_same_values_in_float32(mods, code):
+    """y_dtype LDPC_F16: the received values cross PCIe as binary16; priors = (-2 * float64(y)) / var on THOSE values,
+    so the result is the oracle's on the same (float16-representable) inputs, on every path and arithmetic."""
+    torch, lib, E = mods["torch"], mods["lib"], mods["engine"]
+    tab = tables(mods, code)
+    og = O.Graph(*G.code_tables(code))
+    eng = E.engine_for(tab)
+    B = 1500
+    Y16 = G.channel_send("biawgn", 2.0, np.ones((B, tab.n), np.int64), 17).astype(np.float16)
+    nv = 10 ** (-2.0 / 10)
+    for dt, ldt in ((np.float32, lib.F32), (np.float64, lib.F64)):
+        ref = O.bp_decode(og, O.MSA, O.llr_biawgn(2.0, Y16.astype(np.float64)).astype(dt), max_iter=10, nthreads=8)
+        xh, it, _ = eng.decode_host(lib.CH_BIAWGN, lib.MSA, ldt, nv, Y16, max_iter=10)
+        assert (it == ref["iters"]).all() and (xh == ref["x_hat"]).all()
+        for flags in (lib.PATH_STREAMING, lib.PATH_AUTO):
+            o = eng.decode_device_channel(lib.CH_BIAWGN, lib.MSA, ldt, nv, torch.from_numpy(Y16).cuda(), max_iter=10, flags=flags)
+            assert (o["iters"].cpu().numpy() == ref["iters"]).all() and (o["x_hat"].cpu().numpy() == ref["x_hat"]).all()
+
+
+# ------------------------------------------------------------------------------------------ the named sweeps on a GPU
+def test_simulations_main_runs_named_cases_in_process(mods, tmp_path):
+    """simulations.main executes the reference's named cases in-process (one process group, one engine cache): the
+    first case lines of REG_ENS (BEC sweep of `1200_3_6_rand_ldpc_1`) and HMG, results in the reference's schema."""
+    from ldpc_decoders_b200 import simulations
+    d = str(tmp_path)
+    write_code_txt(d, "1200_3_6_rand_ldpc_1")
+    out = simulations.main(["REG_ENS", "--limit", "1", "--noise", "device", "--dtype", "f32", "--frames", "20000",
+                            "--batch", "4096", "--seed", "1", "--console", "--data_dir", d, "--codes-dir", d])
+    assert len(out) == 1 and out[0][0] == ["bec", "1200_3_6_rand_ldpc_1", "SPA"]
+    res = json.load(open(os.path.join(d, "bec-1200_3_6_rand_ldpc_1-SPA-0-100-10.json")))
+    assert list(res)[:6] == ["channel", "code", "decoder", "codeword", "min_wec", "max_iter"]
+    wer = [res["wer"][str(float(p))] for p in simulations.P_BEC.split()]
+    assert all(res["tot"][k] == 20000 for k in res["tot"]) and wer[0] == 1.0 and wer[-1] < 1e-3
+    assert all(a >= b - 0.01 for a, b in zip(wer, wer[1:]))                      # WER falls with the erasure rate
+    out = simulations.main(["HMG", "--limit", "3", "--noise", "device", "--dtype", "f32", "--batch", "2048",
+                            "--seed", "1", "--console", "--data_dir", d])
+    assert [c[0][:3] for c in out] == [["bec", "7_4_hamming", "SPA"], ["bsc", "7_4_hamming", "SPA"], ["bsc", "7_4_hamming", "MSA"]]
+    res = json.load(open(os.path.join(d, "bsc-7_4_hamming-MSA-1-300-10.json")))
+    assert all(v >= 300 for v in res["wec"].values())                           # min_wec rule reached on every parameter
+
+
+# ------------------------------------------------------------------------------------------ published curves
+def _published():
+    with open(os.path.join(G.GOLD, "published.json")) as fp:
+        return json.load(fp)
+
+
+def consistent_with_published(errs, n, pt, z=4.0):
+    """Is the reference's published point (tot frames, wec word errors, bec bit errors; data/output/*.json) a
+    plausible draw given OUR per-frame bit-error counts `errs`?  Word errors: binomial(tot, wer_ours); bit errors:
+    sum of tot i.i.d. per-frame counts with our mean and variance.  Our own sampling error is added in quadrature.
+    The reference stops at min_wec word errors (negative-binomial sampling): its WER estimate is biased up by ~1/wec,
+    which the z = 4 band absorbs."""
+    errs = np.asarray(errs, np.float64)
+    N, tot = errs.size, pt["tot"]
+    w = (errs > 0).mean()
+    ref_w = pt["wec"] / tot
+    sd_w = np.sqrt(w * (1 - w) / tot + w * (1 - w) / N) + 1.0 / tot
+    ok_w = abs(ref_w - w) <= z * sd_w + 1e-12
+    mu, var = errs.mean(), errs.var()
+    ref_b = pt["bec"] / tot
+    sd_b = np.sqrt(var / tot + var / N) + 1.0 / tot
+    ok_b = abs(ref_b - mu) <= z * sd_b + 1e-12
+    return ok_w, ok_b, (ref_w, w, sd_w, ref_b / n, mu / n, sd_b / n)
+
+
+@pytest.mark.parametrize("rec", _published(), ids=lambda r: r["file"][:-5])
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_wer_ber_lie_within_confidence_intervals_of_the_published_curves(mods, rec, dtype):
+    """north_star: "BER/WER curves must lie within Monte-Carlo confidence intervals" of the reference's published
+    results (data/output/*.json, frozen in tests/golden/published.json with their frame counts).  On-device noise,
+    >= 2e5 frames per point (more where the published WER is small), float32 (production) and float64 messages."""
+    torch, lib = mods["torch"], mods["lib"]
+    if rec["channel"] == "bec" and dtype == "f64":
+        pytest.skip("BEC decoding is integer arithmetic")
+    tab = tables(mods, rec["code"])
+    eng = mods["engine"].engine_for(tab)
+    ch = dict(biawgn=lib.CH_BIAWGN, bsc=lib.CH_BSC, bec=lib.CH_BEC)[rec["channel"]]
+    al = lib.MSA if rec["decoder"] == "MSA" else lib.SPA
+    ldt = lib.F32 if dtype == "f32" else lib.F64
+    x = (torch.ones(tab.n, dtype=torch.uint8, device="cuda") if rec["codeword"] else None)
+    bad = []
+    checked = 0
+    for pt in rec["points"]:
+        ref_w = pt["wec"] / pt["tot"]
+        if pt["wec"] < 50 or ref_w < 2e-5:
+            continue                                       # unfinished points of the published run / out of reach here
+        frames = int(min(4e6, max(2e5, 400 / ref_w)))
+        prm = 10 ** (-pt["param"] / 10) if rec["channel"] == "biawgn" else pt["param"]
+        errs = []
+        for f0 in range(0, frames, 65536):
+            nb = min(65536, frames - f0)
+            r = eng.simulate(ch, al, ldt, prm, nb, seed=2024, frame0=f0, x=x, max_iter=rec["max_iter"], iter_cap=1000)
+            errs.append(r["bit_errs"].cpu().numpy())
+        ok_w, ok_b, info = consistent_with_published(np.concatenate(errs), rec["n"], pt)
+        checked += 1
+        if not (ok_w and ok_b):
+            bad.append((pt["param"], ok_w, ok_b) + tuple(float("%.4g" % v) for v in info))
+    assert checked >= 3
+    assert not bad, "outside the confidence band: (param, wer ok, ber ok, ref wer, wer, sd, ref ber, ber, sd) %r" % (bad,)
+
+
+# ------------------------------------------------------------------------------------------ N GPUs under NCCL
+def _run_sim(tmp, sub, nproc, extra, port):
+    d = os.path.join(tmp, sub)
+    os.makedirs(d, exist_ok=True)
+    args = ["biawgn", "512_3_6_rand_ldpc_1", "MSA", "--codeword", "1", "--params", "1.5", "2.5", "--max-iter", "10",
+            "--dtype", "f32", "--seed", "5", "--console", "--data_dir", d, "--codes-dir", tmp] + extra
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    if nproc == 1:
+        cmd = [sys.executable, "-m", "ldpc_decoders_b200.sim"] + args
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc,
+               "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", "ldpc_decoders_b200.sim"] + args
+    out = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    files = [f for f in os.listdir(d) if f.endswith(".json")]
+    assert len(files) == 1
+    return json.load(open(os.path.join(d, files[0])))
+
+
+def test_monte_carlo_on_two_gpus_under_nccl_equals_one_gpu(mods, tmp_path):
+    """torchrun --nproc-per-node 2 -m ldpc_decoders_b200.sim (NCCL): frames sharded over the GPUs, counters
+    all-reduced.  Frame-index-keyed noise makes the counters IDENTICAL to the 1-GPU run: fixed --frames (one
+    all-reduce per parameter), the reference's `while wec < min_wec` rule (per-round all-gather, global frame order),
+    and numpy host noise (the reference's RNG stream, which the 1-GPU run holds to the oracle in test_gpu_sim.py)."""
+    torch = mods["torch"]
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    tmp = str(tmp_path)
+    write_code_txt(tmp, "512_3_6_rand_ldpc_1")
+    keys = ("tot", "wec", "bec", "dec")
+    for k, extra in enumerate((["--noise", "device", "--frames", "100000", "--batch", "4096"],
+                               ["--noise", "device", "--min-wec", "60", "--batch", "512"],
+                               ["--noise", "host", "--min-wec", "12", "--batch", "64"])):
+        one = _run_sim(tmp, "one%d" % k, 1, extra, 0)
+        two = _run_sim(tmp, "two%d" % k, 2, extra, 29541 + k)
+        for key in keys:
+            assert one[key] == two[key], (extra, key)
+        if "--frames" in extra:
+            assert all(v == 100000 for v in two["tot"].values())

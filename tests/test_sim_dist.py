@@ -129,6 +129,114 @@ def test_two_process_gloo_run_matches_single_process(tmp_path):
     assert r["sum_tot"] == 2 * ref["tot"] and r["ranks"] == 1      # all_reduce(SUM) over 2 ranks
 
 
+# ---- fixed-length runs with the counters kept "on the device" (run_fixed_on_device): one all-reduce per parameter.
+# The stand-in round below draws frame-index-keyed noise (like the Philox generator) and decodes with the oracle; its
+# counters live in a CPU torch tensor, which is where a gloo group wants them.
+FIXED_HELPER = r"""
+import numpy as np, torch
+def make_round(O, g, snr, calls):
+    std = np.sqrt(10 ** (-snr / 10))
+    def simulate_round(x, nb, seed, frame0, c, nh):
+        Y = np.stack([(2 * x - 1) + np.random.RandomState((seed + frame0 + i) % (2 ** 31)).normal(0, std, x.size) for i in range(nb)])
+        r = O.bp_decode(g, O.MSA, O.llr_biawgn(snr, Y), max_iter=10)
+        e = (r["x_hat"] != x[None, :]).sum(1)
+        c[0] += nb; c[1] += int((e > 0).sum()); c[2] += int(e.sum()); c[3] += int(r["iters"].sum())
+        for it in r["iters"]:
+            c[4 + min(int(it), nh - 1)] += 1
+        calls.append((frame0, nb))
+    return simulate_round
+new_counters = lambda k: torch.zeros(4 + k, dtype=torch.int64)
+"""
+
+
+def _fixed_ref(frames):
+    ns = {}
+    exec(FIXED_HELPER, ns)
+    g = O.Graph(*G.code_tables("512_3_6_rand_ldpc_1"))
+    x = np.ones(g.n, np.int64)
+    calls = []
+    r = sim.run_fixed_on_device(ns["make_round"](O, g, 1.5, calls), ns["new_counters"], x, dist.Comm(), 8, frames, seed=11)
+    return r, calls
+
+
+def test_fixed_length_device_counters_single_process():
+    r, calls = _fixed_ref(37)
+    assert r["tot"] == 37 and sum(r["dec"]["iter"]) == 37 and r["wec"] <= 37
+    assert calls == [(0, 8), (8, 8), (16, 8), (24, 8), (32, 5)]          # the last round is short, nothing past `frames`
+    r2, calls2 = _fixed_ref(37)
+    assert r2 == r
+    # status callbacks (partial results) do not change the outcome
+    ns = {}
+    exec(FIXED_HELPER, ns)
+    g = O.Graph(*G.code_tables("512_3_6_rand_ldpc_1"))
+    seen = []
+    r3 = sim.run_fixed_on_device(ns["make_round"](O, g, 1.5, []), ns["new_counters"], np.ones(g.n, np.int64), dist.Comm(),
+                                 8, 37, on_status=lambda *a: seen.append(a[0]), log_freq=0., seed=11)
+    assert r3 == r and seen and seen == sorted(seen) and seen[-1] < 37
+
+
+FIXED_WORKER = r"""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import _golden as G
+from ldpc_decoders_b200 import dist, sim
+from oracle import oracle as O
+{helper}
+comm = dist.Comm("gloo")
+g = O.Graph(*G.code_tables("512_3_6_rand_ldpc_1"))
+x = np.ones(g.n, np.int64)
+calls, seen = [], []
+r = sim.run_fixed_on_device(make_round(O, g, 1.5, calls), new_counters, x, comm, 4, 37,
+                            on_status=lambda *a: seen.append(a[0]), log_freq=0., seed=11)
+if comm.rank == 0:
+    print("RESULT " + json.dumps(dict(r=r, calls=calls, seen=seen)))
+comm.close()
+"""
+
+
+def test_fixed_length_device_counters_two_process_gloo(tmp_path):
+    ref, _ = _fixed_ref(37)
+    script = tmp_path / "worker_fixed.py"
+    script.write_text(FIXED_WORKER.format(root=ROOT, helper=FIXED_HELPER))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         env=dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533"),
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    assert got["r"] == json.loads(json.dumps(ref))                       # same frames, same counters, any GPU count
+    assert [tuple(c) for c in got["calls"]] == [(0, 4), (8, 4), (16, 4), (24, 4), (32, 4)]      # rank 0's slices
+    assert got["seen"] == sorted(got["seen"]) and all(0 < t < 37 for t in got["seen"])
+
+
+def test_run_param_fixed_frames_host_noise_sums_locally():
+    """--frames with numpy noise: local sums + ONE all-reduce; equals the min_wec-free sequential loop."""
+    name, snr = "512_3_6_rand_ldpc_1", 1.5
+    g, decode_batch = oracle_decoder(name, snr)
+    x = np.ones(g.n, np.int64)
+    std = np.sqrt(10 ** (-snr / 10))
+    send = lambda X: (2 * X - 1) + np.random.normal(0, std, X.shape)
+    np.random.seed(5)
+    Y = send(np.tile(x, (21, 1)))
+    xh, it = decode_batch(Y)
+    e = (xh != x[None, :]).sum(1)
+    np.random.seed(5)
+    r = sim.run_param(decode_batch, send, x, dist.Comm(), 7, 100, frames=21)
+    assert (r["tot"], r["wec"], r["bec"]) == (21, int((e > 0).sum()), int(e.sum()))
+    assert r["dec"]["average"] == it.sum() / 21
+
+
+def test_status_persists_partial_results(tmp_path):
+    """sim.main saves the counters at every status report (main.py:30-35 log_status -> saver.add)."""
+    ids = [("channel", "biawgn"), ("code", "c"), ("decoder", "MSA"), ("codeword", 1), ("min_wec", 100), ("max_iter", 10)]
+    s = sim.Saver(str(tmp_path), ids)
+    r = sim._result(10, 2, 5, 93, np.array([0, 0, 1, 9]), 1200)
+    s.add(2.0, {k: r[k] for k in ("tot", "wec", "wer", "bec", "ber", "dec")})
+    d = json.load(open(s.file_path))
+    assert d["tot"]["2.0"] == 10 and d["dec"]["2.0"]["iter"] == [0, 0, 1, 9] and abs(d["dec"]["2.0"]["average"] - 9.3) < 1e-12
+
+
 def test_named_simulation_cases_match_the_reference():
     """ldpc_decoders_b200.simulations expands REG_ENS / IREG_ENS / REG_BAD / MAR / HMG to the same main.py command
     lines as the reference's simulations.py (tests/golden/simulations_cases.txt = its own output, SPA / MSA lines)."""
