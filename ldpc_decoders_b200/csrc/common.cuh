@@ -49,6 +49,7 @@ struct ResidentInfo {                        // position-indexed tables of the o
     bool vx = false;
     uint32_t *vx_cwx[2] = {nullptr, nullptr};
     int vx_pcnt[2][8] = {}, vx_pbase[2][8] = {}, vx_cells[2] = {0, 0};
+    uint8_t *vx_vdeg = nullptr;              // [np] degree of the variable at a position of placement [0], 0xff = hole (resident_bec.cuh)
 };
 
 struct ProfEvent {                           // one timed launch (ldpc_profile_*)

@@ -20,6 +20,7 @@
 #include "resident_bp.cuh"
 #include "resident_vp.cuh"
 #include "resident_vd.cuh"
+#include "resident_bec.cuh"
 #include "stream_bec.cuh"
 #include "stream_bp.cuh"
 #include "stream_bp_tma.cuh"
@@ -737,6 +738,59 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
     return check_launch(h, "decode_bp_resident");
 }
 
+// ------------------------------------------------------------------------------------------------
+// resident (on-chip) BEC decode for short codes (resident_bec.cuh)
+// ------------------------------------------------------------------------------------------------
+// The erasure kernel shares the variable-plane tables of resident_vp (two-CTA geometry): regular (3,6) codes and the
+// irregular instance; the code length must be a multiple of 4 (32-bit symbol reads of the transposes) and 32 rows of
+// symbols must fit in the message region they are staged in.
+bool bec_resident_eligible(const ldpc_t *h)
+{
+    const ResidentInfo &r = h->res;
+    if (!r.ok || !((r.vp && !r.vp_big) || r.vx) || (h->t.n % 4) != 0) return false;
+    const BecSmem L = bec_smem_layout(r.np, r.vx ? r.vx_cells[0] : 0, r.vx, h->t.n);
+    return (size_t)32 * h->t.n <= L.planes_bytes && L.total <= resident_budget(h) && (!r.vx || r.vx_vdeg != nullptr);
+}
+
+int decode_bec_resident(ldpc_t *h, const uint8_t *y, int B, int max_iter, int iter_cap,
+                        uint8_t *x_hat, int32_t *iters, uint8_t *reason, void *ws, size_t ws_bytes, cudaStream_t s)
+{
+    const Tables &t = h->t;
+    const ResidentInfo &r = h->res;
+    if (ws_bytes < 256) return fail(h, LDPC_EWORKSPACE, "workspace too small");
+    BecResParams bp;
+    bp.np = r.np; bp.mp = r.mp; bp.nref = t.n;
+    bp.cw = r.vp ? r.vp_cw[0] : nullptr;
+    bp.cwx = r.vx ? r.vx_cwx[0] : nullptr;
+    bp.vposmap = r.vp_vposmap[0];
+    bp.vdeg = r.vx_vdeg;
+    bp.plane_cells = r.vx ? r.vx_cells[0] : 0;
+    for (int k = 0; k < 8; ++k) { bp.pcnt[k] = r.vx ? r.vx_pcnt[0][k] : 0; bp.pbase[k] = r.vx ? r.vx_pbase[0][k] : 0; }
+    bp.y = y; bp.B = B;
+    // peeling ends by itself ('decoded' or 'stopping') after at most n rounds; that bounds "unlimited"
+    bp.limit = max_iter > 0 ? max_iter : (iter_cap > 0 ? iter_cap : t.n + 1);
+    bp.bound_reason = max_iter > 0 ? LDPC_REASON_MAXIMUM : LDPC_REASON_CAP;
+    bp.x_hat = x_hat; bp.iters = iters; bp.reason = reason;
+    bp.counter = static_cast<int *>(ws);
+    const BecSmem L = bec_smem_layout(r.np, bp.plane_cells, r.vx, t.n);
+    const int tiles = (B + 63) / 64;
+    CUDA_TRY(h, cudaMemsetAsync(bp.counter, 0, sizeof(int), s));
+    ProfEvent *pe = prof_begin(h, 0, s);
+    int per_sm = 1, rc;
+    if (r.vx) {
+        auto kern = resident_bec<true>;
+        if ((rc = resident_occupancy(h, kern, r.threads, L.total, &per_sm)) != 0) return rc;
+        kern<<<std::max(1, std::min(tiles, h->sm_count * per_sm)), r.threads, L.total, s>>>(bp);
+    } else {
+        auto kern = resident_bec<false>;
+        if ((rc = resident_occupancy(h, kern, r.threads, L.total, &per_sm)) != 0) return rc;
+        kern<<<std::max(1, std::min(tiles, h->sm_count * per_sm)), r.threads, L.total, s>>>(bp);
+    }
+    h->launches++;
+    prof_end(pe, s);
+    return check_launch(h, "decode_bec_resident");
+}
+
 // Places the graph in shared memory (res_layout.h), builds the position-indexed uint16 tables and the geometry of
 // the resident kernel; leaves res.ok = false when the code does not fit.
 int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, const int32_t *var_ptr, const int32_t *var_edges)
@@ -826,6 +880,11 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
             if ((e = up((void **)&r.vp_vinvmap[tb], X.vinvmap.data(), X.vinvmap.size() * 2)) != cudaSuccess) break;
             r.vx_cells[tb] = X.plane_cells;
             for (int k = 0; k < 8; ++k) { r.vx_pcnt[tb][k] = X.pcnt[k]; r.vx_pbase[tb][k] = X.pbase[k]; }
+            if (tb == 0) {                                            // degree by position, for the on-chip erasure kernel
+                std::vector<uint8_t> vd((size_t)np, 0xffu);
+                for (int v = 0; v < t.n; ++v) vd[X.vposmap[v]] = (uint8_t)(var_ptr[v + 1] - var_ptr[v]);
+                if ((e = up((void **)&r.vx_vdeg, vd.data(), vd.size())) != cudaSuccess) break;
+            }
             if (tb == 0) { r.plan[0] = V.cn_ideal; r.plan[1] = V.cn_file; r.plan[3] = V.cn_plan; r.plan[4] = V.vn_ideal; r.plan[5] = V.vn_file; r.plan[6] = V.vn_plan; }
             else r.plan[2] = V.cn_plan;
         }
@@ -840,6 +899,7 @@ int build_resident(ldpc_t *h, const int32_t *chk_ptr, const int32_t *edge_var, c
             if (r.vp_vposmap[tb]) { cudaFree(r.vp_vposmap[tb]); r.vp_vposmap[tb] = nullptr; }
             if (r.vp_vinvmap[tb]) { cudaFree(r.vp_vinvmap[tb]); r.vp_vinvmap[tb] = nullptr; }
         }
+        if (r.vx_vdeg) { cudaFree(r.vx_vdeg); r.vx_vdeg = nullptr; }
     }
 
     if (!bp_fits) return LDPC_OK;
@@ -891,7 +951,11 @@ int decode_any(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_
     if (algo == LDPC_BEC) {
         if (in.channel != LDPC_CH_BEC) return fail(h, LDPC_EINVAL, "BEC decoder needs symbol input");
         if (marg_out) return fail(h, LDPC_EINVAL, "marg_out is MSA/SPA only");
-        if (path == LDPC_PATH_RESIDENT) return fail(h, LDPC_EUNSUPPORTED, "BEC has no resident path");
+        const bool bec_res = bec_resident_eligible(h);
+        if (path == LDPC_PATH_RESIDENT && !bec_res)
+            return fail(h, LDPC_EUNSUPPORTED, "the on-chip erasure kernel needs a code on the variable-plane tables (two-CTA geometry) with n % 4 == 0");
+        if (path == LDPC_PATH_RESIDENT || (path == LDPC_PATH_AUTO && bec_res))
+            return decode_bec_resident(h, (const uint8_t *)in.src, B, max_iter, iter_cap, x_hat, iters, reason, ws, ws_bytes, s);
         return decode_bec_stream(h, (const uint8_t *)in.src, B, max_iter, iter_cap, x_hat, iters, reason, ws, ws_bytes, s);
     }
     if (algo != LDPC_MSA && algo != LDPC_SPA) return fail(h, LDPC_EINVAL, "bad algo");
@@ -1131,6 +1195,7 @@ void ldpc_destroy(ldpc_t *h)
         if (h->res.vp_vposmap[tb]) cudaFree(h->res.vp_vposmap[tb]);
         if (h->res.vp_vinvmap[tb]) cudaFree(h->res.vp_vinvmap[tb]);
     }
+    if (h->res.vx_vdeg) cudaFree(h->res.vx_vdeg);
     if (h->res.vposmap) cudaFree(h->res.vposmap);
     if (h->res.vinvmap) cudaFree(h->res.vinvmap);
     if (h->res.cdeg) cudaFree(h->res.cdeg);

@@ -473,4 +473,38 @@ template <int NB, typename U = uint32_t> struct BsInt {
     }
 };
 
+// Degree-3 variable node on bit planes WITHOUT integer arithmetic (the on-chip erasure kernel, resident_bec.cuh).
+// Inputs: index 0 = prior, 1..3 = the three c2v messages, each a ternary value (nz, pos subset of nz).
+// bec.py:115-119:  marginal = prior + sum c2v;  v2c_e = sign(marginal - c2v_e);  x_new = symbols[sign(marginal)].
+// marginal - c2v_e is the sum of the OTHER three inputs, and the sign of a sum of three ternary values a, b, c is
+//   > 0  <=>  #(+1) > #(-1)  <=>  maj(p_a, p_b, p_c) | (any p & no n)        (p = "is +1", n = "is -1")
+// so every output is a handful of 3-input boolean functions (one LOP3 each) instead of ripple adders: ~40 logic
+// instructions per variable and word against ~70 with BsInt<4>.  The marginal's sign is recovered from the
+// leave-one-out sum of edge 1 (S1 in [-3, 3], known up to {<= -2, -1, 0, 1, >= 2}) plus the left-out message.
+// Exhaustively checked against BsInt on all 3^4 inputs (tests/test_host_emu.py).
+template <typename U>
+LDPC_HD void bec_vn3(const U (&nz)[4], const U (&pos)[4], U (&onz)[3], U (&opos)[3], U &mnz, U &mpos)
+{
+    U n[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) n[i] = nz[i] & ~pos[i];
+    U ge2 = U(), le2 = U();
+#pragma unroll
+    for (int e = 1; e <= 3; ++e) {
+        const int a = 0, b = (e == 1) ? 2 : 1, c = (e == 3) ? 2 : 3;      // the other three inputs
+        const U mp = (pos[a] & pos[b]) | (pos[c] & (pos[a] | pos[b]));
+        const U mn = (n[a] & n[b]) | (n[c] & (n[a] | n[b]));
+        const U op = pos[a] | pos[b] | pos[c], on = n[a] | n[b] | n[c];
+        const U gt = mp | (op & ~on), lt = mn | (on & ~op);
+        onz[e - 1] = gt | lt;
+        opos[e - 1] = gt;
+        if (e == 1) { ge2 = mp & ~on; le2 = mn & ~op; }
+    }
+    const U z1 = ~onz[0];
+    const U ps = ge2 | (opos[0] & ~n[1]) | (z1 & pos[1]);
+    const U ng = le2 | ((onz[0] & ~opos[0]) & ~pos[1]) | (z1 & n[1]);
+    mnz = ps | ng;
+    mpos = ps;
+}
+
 }  // namespace ldpc

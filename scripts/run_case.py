@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--code", default="1200_3_6_rand_ldpc_1")
     ap.add_argument("--algo", default="MSA", choices=["MSA", "SPA"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--channel", default="biawgn", choices=["biawgn", "bsc"])
+    ap.add_argument("--channel", default="biawgn", choices=["biawgn", "bsc", "bec"])
     ap.add_argument("--snr", type=float, default=2.0, help="SNR in dB (biawgn) or crossover probability (bsc)")
     ap.add_argument("--frames", type=int, default=32768)
     ap.add_argument("--cw", type=int, default=1)
@@ -48,6 +48,10 @@ def main():
         nv = 10 ** (-args.snr / 10)
         y = (2 * args.cw - 1) + nv ** .5 * torch.randn((args.frames, tab.n), generator=g, device="cuda", dtype=torch.float32)
         ch, par = lib.CH_BIAWGN, nv
+    elif args.channel == "bec":
+        er = torch.rand((args.frames, tab.n), generator=g, device="cuda") < args.snr
+        y = torch.where(er, 2, args.cw).to(torch.uint8)
+        ch, par, algo = lib.CH_BEC, 0.0, lib.BEC
     else:
         flip = torch.rand((args.frames, tab.n), generator=g, device="cuda") < args.snr
         import math

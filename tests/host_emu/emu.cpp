@@ -116,6 +116,27 @@ void decode_bp(const G &g, int algo, const T *prior, const uint8_t *y_hard, int 
 
 extern "C" {
 
+// bec_vn3 (degree-3 variable node as boolean functions) against the bit-sliced integer form, on caller-supplied planes:
+// nz/pos [4] words in, out[8] = {onz0, opos0, onz1, opos1, onz2, opos2, mnz, mpos} for both formulations.
+void emu_bec_vn3(const uint32_t *nz, const uint32_t *pos, uint32_t *fast, uint32_t *ref)
+{
+    uint32_t a[4] = {nz[0], nz[1], nz[2], nz[3]}, b[4] = {pos[0], pos[1], pos[2], pos[3]};
+    uint32_t onz[3], opos[3], mnz, mpos;
+    ldpc::bec_vn3<uint32_t>(a, b, onz, opos, mnz, mpos);
+    for (int k = 0; k < 3; ++k) { fast[2 * k] = onz[k]; fast[2 * k + 1] = opos[k]; }
+    fast[6] = mnz; fast[7] = mpos;
+    ldpc::BsInt<5, uint32_t> acc;
+    acc.set_ternary(a[0], b[0]);
+    for (int k = 1; k < 4; ++k) acc.add_ternary(a[k], b[k]);
+    for (int k = 1; k < 4; ++k) {
+        ldpc::BsInt<5, uint32_t> t = acc;
+        t.sub_ternary(a[k], b[k]);
+        t.sign(ref[2 * (k - 1)], ref[2 * (k - 1) + 1]);
+    }
+    acc.sign(ref[6], ref[7]);
+}
+
+
 int emu_bp_f64(int algo, int n, int m, int E, const int32_t *cp, const int32_t *ev, const int32_t *vp, const int32_t *ve,
                int B, const double *priors, const uint8_t *y_hard, int max_iter, uint8_t *x_hat, int32_t *iters, double *marg)
 {

@@ -359,3 +359,33 @@ def test_box_muller_normals(emu):
     z2 = np.zeros((10, n), np.float32)
     emu.emu_normals(ctypes.c_ulonglong(7), ctypes.c_ulonglong(10 ** 12 + 5), 10, n, ptr(z2))
     assert (z2 == z[5:15]).all()                      # keyed by the global frame index only
+
+
+def test_bec_degree3_variable_rule_is_exhaustively_the_integer_form(emu):
+    """ldpc::bec_vn3 (boolean leave-one-out form of bec.py:115-119 for degree-3 variables) == the bit-sliced integer
+    form on all 3^4 ternary inputs, 32 random assignments of them to bit lanes at a time."""
+    import itertools
+    combos = list(itertools.product((-1, 0, 1), repeat=4))
+    rng = np.random.RandomState(0)
+    for rep in range(8):
+        pick = [combos[i] for i in rng.permutation(len(combos))[:32]] if rep else combos[:32]
+        if rep == 1:
+            pick = combos[32:64]
+        if rep == 2:
+            pick = combos[49:81]
+        nz = np.zeros(4, np.uint32); pos = np.zeros(4, np.uint32)
+        for lane, c in enumerate(pick):
+            for i, t in enumerate(c):
+                if t != 0:
+                    nz[i] |= np.uint32(1 << lane)
+                if t > 0:
+                    pos[i] |= np.uint32(1 << lane)
+        fast = np.zeros(8, np.uint32); ref = np.zeros(8, np.uint32)
+        emu.emu_bec_vn3(ptr(nz), ptr(pos), ptr(fast), ptr(ref))
+        assert (fast == ref).all(), (rep, fast, ref)
+        for lane, c in enumerate(pick):                    # and against plain integers
+            S = sum(c)
+            assert ((int(fast[6]) >> lane) & 1, (int(fast[7]) >> lane) & 1) == (int(S != 0), int(S > 0))
+            for e in range(3):
+                Se = S - c[e + 1]
+                assert ((int(fast[2 * e]) >> lane) & 1, (int(fast[2 * e + 1]) >> lane) & 1) == (int(Se != 0), int(Se > 0))
