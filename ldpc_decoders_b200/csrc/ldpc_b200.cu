@@ -742,14 +742,13 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
 // resident (on-chip) BEC decode for short codes (resident_bec.cuh)
 // ------------------------------------------------------------------------------------------------
 // The erasure kernel shares the variable-plane tables of resident_vp (two-CTA geometry): regular (3,6) codes and the
-// irregular instance; the code length must be a multiple of 4 (32-bit symbol reads of the transposes) and 32 rows of
-// symbols must fit in the message region they are staged in.
+// irregular instance (check degrees 2..6, variable degrees 0..8).
 bool bec_resident_eligible(const ldpc_t *h)
 {
     const ResidentInfo &r = h->res;
-    if (!r.ok || !((r.vp && !r.vp_big) || r.vx) || (h->t.n % 4) != 0) return false;
+    if (!r.ok || !((r.vp && !r.vp_big) || r.vx)) return false;
     const BecSmem L = bec_smem_layout(r.np, r.vx ? r.vx_cells[0] : 0, r.vx, h->t.n);
-    return (size_t)32 * h->t.n <= L.planes_bytes && L.total <= resident_budget(h) && (!r.vx || r.vx_vdeg != nullptr);
+    return L.total <= resident_budget(h) && (!r.vx || r.vx_vdeg != nullptr);
 }
 
 int decode_bec_resident(ldpc_t *h, const uint8_t *y, int B, int max_iter, int iter_cap,
@@ -777,15 +776,22 @@ int decode_bec_resident(ldpc_t *h, const uint8_t *y, int B, int max_iter, int it
     CUDA_TRY(h, cudaMemsetAsync(bp.counter, 0, sizeof(int), s));
     ProfEvent *pe = prof_begin(h, 0, s);
     int per_sm = 1, rc;
-    if (r.vx) {
-        auto kern = resident_bec<true>;
-        if ((rc = resident_occupancy(h, kern, r.threads, L.total, &per_sm)) != 0) return rc;
-        kern<<<std::max(1, std::min(tiles, h->sm_count * per_sm)), r.threads, L.total, s>>>(bp);
-    } else {
-        auto kern = resident_bec<false>;
-        if ((rc = resident_occupancy(h, kern, r.threads, L.total, &per_sm)) != 0) return rc;
-        kern<<<std::max(1, std::min(tiles, h->sm_count * per_sm)), r.threads, L.total, s>>>(bp);
-    }
+    // wide geometry: one check and two variables per thread when the code allows it (n = 1200: 608 threads)
+    const int wide_t = (std::max(r.mp, (r.np + 1) / 2) + 31) / 32 * 32;
+    // measured (r2): 318 M frames/s wide against 356 M for resident_vp's own geometry on config 2 — 48 registers starve the
+    // transposes and add instructions; kept behind LDPC_BEC_WIDE=1 for A/B runs (regular codes only: the irregular instance spills)
+    const bool wide = !r.vx && wide_t <= 608 && wide_t > r.threads && getenv("LDPC_BEC_WIDE") != nullptr;
+    const int threads = wide ? wide_t : r.threads;
+#define BEC_LAUNCH(...)                                                                             \
+    do {                                                                                            \
+        auto kern = resident_bec<__VA_ARGS__>;                                                      \
+        if ((rc = resident_occupancy(h, kern, threads, L.total, &per_sm)) != 0) return rc;          \
+        kern<<<std::max(1, std::min(tiles, h->sm_count * per_sm)), threads, L.total, s>>>(bp);      \
+    } while (0)
+    if (r.vx) BEC_LAUNCH(true);
+    else if (wide) BEC_LAUNCH(false, 1, 2, 608);
+    else BEC_LAUNCH(false);
+#undef BEC_LAUNCH
     h->launches++;
     prof_end(pe, s);
     return check_launch(h, "decode_bec_resident");
@@ -953,7 +959,7 @@ int decode_any(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, int max_
         if (marg_out) return fail(h, LDPC_EINVAL, "marg_out is MSA/SPA only");
         const bool bec_res = bec_resident_eligible(h);
         if (path == LDPC_PATH_RESIDENT && !bec_res)
-            return fail(h, LDPC_EUNSUPPORTED, "the on-chip erasure kernel needs a code on the variable-plane tables (two-CTA geometry) with n % 4 == 0");
+            return fail(h, LDPC_EUNSUPPORTED, "the on-chip erasure kernel needs a code on the variable-plane tables (two-CTA geometry: regular (3,6) or check degrees 2..6 / variable degrees <= 8, n up to ~1280)");
         if (path == LDPC_PATH_RESIDENT || (path == LDPC_PATH_AUTO && bec_res))
             return decode_bec_resident(h, (const uint8_t *)in.src, B, max_iter, iter_cap, x_hat, iters, reason, ws, ws_bytes, s);
         return decode_bec_stream(h, (const uint8_t *)in.src, B, max_iter, iter_cap, x_hat, iters, reason, ws, ws_bytes, s);

@@ -483,11 +483,8 @@ template <int NB, typename U = uint32_t> struct BsInt {
 // leave-one-out sum of edge 1 (S1 in [-3, 3], known up to {<= -2, -1, 0, 1, >= 2}) plus the left-out message.
 // Exhaustively checked against BsInt on all 3^4 inputs (tests/test_host_emu.py).
 template <typename U>
-LDPC_HD void bec_vn3(const U (&nz)[4], const U (&pos)[4], U (&onz)[3], U (&opos)[3], U &mnz, U &mpos)
+LDPC_HD void bec_vn3_pn(const U (&pos)[4], const U (&n)[4], U (&onz)[3], U (&opos)[3], U &mnz, U &mpos)
 {
-    U n[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) n[i] = nz[i] & ~pos[i];
     U ge2 = U(), le2 = U();
 #pragma unroll
     for (int e = 1; e <= 3; ++e) {
@@ -506,5 +503,33 @@ LDPC_HD void bec_vn3(const U (&nz)[4], const U (&pos)[4], U (&onz)[3], U (&opos)
     mnz = ps | ng;
     mpos = ps;
 }
+template <typename U>
+LDPC_HD void bec_vn3(const U (&nz)[4], const U (&pos)[4], U (&onz)[3], U (&opos)[3], U &mnz, U &mpos)
+{
+    U n[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) n[i] = nz[i] & ~pos[i];
+    bec_vn3_pn<U>(pos, n, onz, opos, mnz, mpos);
+}
+
+// Check node of degree 6 on bit planes, erasure count and parity as reduction TREES (three-input functions, one LOP3
+// each) instead of the sequential accumulator BecCnAccT::push: 9 logic instructions per word instead of 18.
+// Same outputs as BecCnAccT (bec.py:100-112).
+template <typename U> struct BecCn6 {
+    U zero, one, onepar;
+    LDPC_HD void reduce(const U (&nz)[6], const U (&pos)[6]) {
+        const U a1 = ~(nz[0] & nz[1] & nz[2]), a2 = ~(nz[3] & nz[4] & nz[5]);                      // some erasure in the triple
+        const U t1 = (~nz[0] & ~nz[1]) | (~nz[2] & (~nz[0] | ~nz[1])), t2 = (~nz[3] & ~nz[4]) | (~nz[5] & (~nz[3] | ~nz[4]));   // two or more
+        const U any = a1 | a2, two = t1 | t2 | (a1 & a2);
+        const U par = (pos[0] ^ pos[1] ^ pos[2]) ^ (pos[3] ^ pos[4] ^ pos[5]);
+        zero = ~any;
+        one = any & ~two;
+        onepar = one & par;
+    }
+    LDPC_HD void out(U nz, U pos, U &onz, U &opos) const {
+        onz = (zero & nz) | (one & ~nz);
+        opos = (zero & pos) | (onepar & ~nz);
+    }
+};
 
 }  // namespace ldpc

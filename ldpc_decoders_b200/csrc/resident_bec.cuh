@@ -25,8 +25,9 @@
 //
 // No per-frame hand-over: a tile runs until its last frame stops (or the iteration bound) — at the reference's
 // operating points (max_iter 10) nearly every frame runs every iteration.  Symbols are transposed into bit planes
-// inside the kernel: 32 rows land in the (not yet used) message region with a flat coalesced copy, then warp ballots
-// build the planes; the words leave the same way in reverse.
+// inside the kernel: a warp takes 32 variables x 32 frames, every lane reads the 32 bytes of its own row straight from
+// global memory (whole 32-byte sectors: no staging, no barrier), packs them into a value and an erasure word, and five
+// shuffle stages transpose the 32 x 32 bit tile (bit_transpose32); the words leave the same way in reverse.
 #pragma once
 #include "resident_vp.cuh"
 
@@ -64,38 +65,96 @@ __host__ __device__ inline BecSmem bec_smem_layout(int np, int plane_cells, bool
     return L;
 }
 
-// nbytes from src to dst by the whole CTA; 128-bit accesses when everything is 16-byte aligned.
-__device__ __forceinline__ void bec_copy(void *dst, const void *src, size_t nbytes, int tid, int T)
+// 32 x 32 bit transpose across a warp: lane i holds row i in, column i out (bit j of the result = bit i of lane j's
+// input).  Five butterfly stages of one shuffle and two logic operations each — against 64 ballots plus 64 compares for
+// the same tile, which made the symbol transposes 46 % of the kernel's instructions (profiles/, r2a).
+__device__ __forceinline__ uint32_t bit_transpose32(uint32_t x, int lane)
 {
-    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | nbytes) & 15u) == 0) {
-        const uint4 *s = reinterpret_cast<const uint4 *>(src);
-        uint4 *d = reinterpret_cast<uint4 *>(dst);
-        for (size_t i = tid; i < nbytes / 16; i += T) d[i] = s[i];
-    } else if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | nbytes) & 3u) == 0) {
-        const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
-        uint32_t *d = reinterpret_cast<uint32_t *>(dst);
-        for (size_t i = tid; i < nbytes / 4; i += T) d[i] = s[i];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int w = 16 >> s;
+        const uint32_t m = (s == 0) ? 0x0000ffffu : (s == 1) ? 0x00ff00ffu : (s == 2) ? 0x0f0f0f0fu : (s == 3) ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(kFull, x, w);
+        x = (lane & w) ? ((x & ~m) | ((y >> w) & m)) : ((x & m) | ((y << w) & ~m));
+    }
+    return x;
+}
+
+// Four symbol bytes {0, 1, >= 2 = erased} -> 4-bit (value, erased) nibbles.  0x00204081 = 1 | 1<<7 | 1<<14 | 1<<21
+// gathers the low bits of the four bytes into bits 21..24 of the product (all partial products land on distinct bits).
+__device__ __forceinline__ void sym4_to_nibbles(uint32_t w, uint32_t &val, uint32_t &er)
+{
+    const uint32_t e = ((((w & 0x7f7f7f7fu) + 0x7e7e7e7eu) | w) >> 7) & 0x01010101u;     // byte >= 2
+    const uint32_t v = w & 0x01010101u & ~e;
+    val = ((v * 0x00204081u) >> 21) & 0xfu;
+    er = ((e * 0x00204081u) >> 21) & 0xfu;
+}
+// ... and back: nibbles -> four symbol bytes (value and erased are disjoint).
+__device__ __forceinline__ uint32_t nibbles_to_sym4(uint32_t val, uint32_t er)
+{
+    return ((val * 0x00204081u) & 0x01010101u) | (((er * 0x00204081u) & 0x01010101u) << 1);
+}
+
+// 32 consecutive symbols (variables 32 g ..) of one frame's row, straight from / to global memory.  A lane touches whole
+// 32-byte sectors, so the warp's 32 rows cost exactly the bytes they hold; no staging, no barrier.  Rows are 16-byte
+// aligned when n % 16 == 0 and the block itself is (vec16), 4-byte aligned when n % 4 == 0 (vec4), else bytes.
+__device__ __forceinline__ void bec_load32(const uint8_t *row, int g, int n, bool vec16, bool vec4, uint32_t (&sy)[8])
+{
+    const uint8_t *q = row + (size_t)g * 32;
+    if (vec16 && g * 32 + 32 <= n) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(q)), b = __ldcs(reinterpret_cast<const uint4 *>(q) + 1);
+        sy[0] = a.x; sy[1] = a.y; sy[2] = a.z; sy[3] = a.w; sy[4] = b.x; sy[5] = b.y; sy[6] = b.z; sy[7] = b.w;
+    } else if (vec4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sy[i] = (g * 32 + 4 * i < n) ? __ldcs(reinterpret_cast<const uint32_t *>(q) + i) : 0u;
     } else {
-        const uint8_t *s = reinterpret_cast<const uint8_t *>(src);
-        uint8_t *d = reinterpret_cast<uint8_t *>(dst);
-        for (size_t i = tid; i < nbytes; i += T) d[i] = s[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t w = 0u;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (g * 32 + 4 * i + b < n) w |= (uint32_t)q[4 * i + b] << (8 * b);
+            sy[i] = w;
+        }
+    }
+}
+__device__ __forceinline__ void bec_store32(uint8_t *row, int g, int n, bool vec16, bool vec4, const uint32_t (&sy)[8])
+{
+    uint8_t *q = row + (size_t)g * 32;
+    if (vec16 && g * 32 + 32 <= n) {
+        __stcs(reinterpret_cast<uint4 *>(q), make_uint4(sy[0], sy[1], sy[2], sy[3]));
+        __stcs(reinterpret_cast<uint4 *>(q) + 1, make_uint4(sy[4], sy[5], sy[6], sy[7]));
+    } else if (vec4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (g * 32 + 4 * i < n) __stcs(reinterpret_cast<uint32_t *>(q) + i, sy[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (g * 32 + 4 * i + b < n) q[4 * i + b] = (uint8_t)(sy[i] >> (8 * b));
     }
 }
 
 // IRR = false: regular code, every check 6 edges, every variable 3 (resident_vp's `cw` tables).
 // IRR = true : check degrees 2..6, variable degrees 0..8, holes (resident_vp's irregular `cwx` tables).
-// nref % 4 == 0 and 32 * nref <= planes_bytes (the staging area of the transposes) are checked by the host.
-template <bool IRR>
-__global__ void __launch_bounds__(320, 2) resident_bec(const BecResParams p)
+// CNP / VNP: check / variable items per thread (mp <= CNP * T, np <= VNP * T); MAXT: threads per CTA, two CTAs per SM.
+// (2, 4, 320) is resident_vp's geometry; (1, 2, 608) gives every thread ONE check and TWO variables of an n = 1200 code:
+// 19 + 19 warps per SM instead of 10 + 10 behind the same two barriers per iteration, at 48 registers per thread.
+template <bool IRR, int CNP = kResCnPasses, int VNP = kResVnPasses, int MAXT = 320>
+__global__ void __launch_bounds__(MAXT, 2) resident_bec(const BecResParams p)
 {
     constexpr int DC = 6, DV = IRR ? 8 : 3, CH = IRR ? DC : 3;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int np = p.np, mp = p.mp, n = p.nref, n4 = n >> 2;
+    const int np = p.np, mp = p.mp, n = p.nref;
+    // alignment of the symbol rows in global memory (both blocks): 128-bit, 32-bit or byte accesses
+    const uintptr_t addr_or = reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.x_hat);
+    const bool vec16 = ((n | addr_or) & 15) == 0, vec4 = ((n | addr_or) & 3) == 0;
     const uint32_t S = (uint32_t)np * 16u;
     const BecSmem L = bec_smem_layout(np, p.plane_cells, IRR, n);
     uint4 *xc = reinterpret_cast<uint4 *>(smem + L.x);
     uint4 *prior = reinterpret_cast<uint4 *>(smem + L.prior);
-    unsigned char *stage = smem + L.planes;                              // 32 rows of symbols, before / after the decode
     uint16_t *s_vpos = reinterpret_cast<uint16_t *>(smem + L.vpos);
 
     __shared__ uint32_t s_act[2], s_chg[2], s_has[2], s_stop[2];
@@ -105,9 +164,9 @@ __global__ void __launch_bounds__(320, 2) resident_bec(const BecResParams p)
     const int tid = threadIdx.x, T = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
 
     // ---- per-thread graph indices -> registers (once per CTA), packed exactly as in resident_vp
-    uint32_t cw[kResCnPasses][CH];
+    uint32_t cw[CNP][CH];
 #pragma unroll
-    for (int ps = 0; ps < kResCnPasses; ++ps) {
+    for (int ps = 0; ps < CNP; ++ps) {
         const int c = tid + ps * T;
 #pragma unroll
         for (int h = 0; h < CH; ++h) cw[ps][h] = 0u;
@@ -150,45 +209,53 @@ __global__ void __launch_bounds__(320, 2) resident_bec(const BecResParams p)
             okw[w] = nvalid[w] == 32 ? 0xffffffffu : ((1u << nvalid[w]) - 1u);
         }
 
-        // ================================ symbols in: rows -> bit planes (x cells), one word at a time ================
-#pragma unroll 1
-        for (int w = 0; w < 2; ++w) {
-            if (w) __syncthreads();                                      // the ballots of word 0 have read the staging area
-            bec_copy(stage, p.y + (size_t)(f0 + 32 * w) * n, (size_t)nvalid[w] * n, tid, T);
-            __syncthreads();
-            const bool valid = lane < nvalid[w];
-            uint32_t er_any = 0u;
-            for (int q = warp; q < n4; q += nwarps) {
-                const uint32_t wv = valid ? reinterpret_cast<const uint32_t *>(stage)[(size_t)lane * n4 + q] : 0u;
-                uint32_t e[4], o[4];
+        // ================================ symbols in: rows -> bit planes (x cells) ================================
+        // warp = 32 consecutive variables x 32 frames: lane = frame packs its 32 symbols into a value word and an
+        // erasure word, two bit transposes turn them into the planes, lane = variable stores its half cell
+        {
+            uint32_t er0 = 0u, er1 = 0u;
+            const uint8_t *row0 = p.y + (size_t)(f0 + lane) * n, *row1 = row0 + (size_t)32 * n;
+            for (int g = warp; g * 32 < n; g += nwarps) {
+                uint32_t sa[8], sb[8];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t sy = (wv >> (8 * b)) & 0xffu;
-                    e[b] = __ballot_sync(kFull, sy >= 2u);
-                    o[b] = __ballot_sync(kFull, sy == 1u);
+                for (int i = 0; i < 8; ++i) { sa[i] = 0u; sb[i] = 0u; }
+                if (lane < nvalid[0]) bec_load32(row0, g, n, vec16, vec4, sa);
+                if (lane < nvalid[1]) bec_load32(row1, g, n, vec16, vec4, sb);
+                uint32_t V0 = 0u, E0 = 0u, V1 = 0u, E1 = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t v4, e4;
+                    sym4_to_nibbles(sa[i], v4, e4);
+                    V0 |= v4 << (4 * i); E0 |= e4 << (4 * i);
+                    sym4_to_nibbles(sb[i], v4, e4);
+                    V1 |= v4 << (4 * i); E1 |= e4 << (4 * i);
                 }
-                er_any |= e[0] | e[1] | e[2] | e[3];
-                if (lane < 4) {
-                    const uint32_t ee = lane == 0 ? e[0] : lane == 1 ? e[1] : lane == 2 ? e[2] : e[3];
-                    const uint32_t oo = lane == 0 ? o[0] : lane == 1 ? o[1] : lane == 2 ? o[2] : o[3];
-                    const uint32_t pos = s_vpos[4 * q + lane];
-                    reinterpret_cast<uint2 *>(xc + pos)[w] = make_uint2(ee, oo);      // (xe, xv) of this word
-                }
+                V0 = bit_transpose32(V0, lane); E0 = bit_transpose32(E0, lane);
+                V1 = bit_transpose32(V1, lane); E1 = bit_transpose32(E1, lane);
+                er0 |= E0; er1 |= E1;
+                const int v = g * 32 + lane;
+                if (v < n) xc[s_vpos[v]] = make_uint4(E0, V0, E1, V1);           // (xe, xv) of both words
             }
-            if (lane == 0 && er_any != 0u) atomicOr(&s_has[w], er_any);
+            er0 = __reduce_or_sync(kFull, er0);
+            er1 = __reduce_or_sync(kFull, er1);
+            if (lane == 0) {
+                if (er0 != 0u) atomicOr(&s_has[0], er0);
+                if (er1 != 0u) atomicOr(&s_has[1], er1);
+            }
         }
         __syncthreads();
         // priors = messages[y] (bec.py:85); v2c = priors[yy] (bec.py:86): the prior goes into every edge cell of the variable
 #pragma unroll
-        for (int ps = 0; ps < kResVnPasses; ++ps) {
+        for (int ps = 0; ps < VNP; ++ps) {
             const int item = tid + ps * T;
             if (item < np) {
                 int d = DV;
                 if (IRR) d = p.vdeg[item];
                 if (!IRR || d != 0xff) {
                     const uint4 x = xc[item];
-                    const uint4 pr = make_uint4(okw[0] & ~x.x, x.y, okw[1] & ~x.z, x.w);
-                    prior[item] = pr;
+                    const uint4 pr = make_uint4(okw[0] & ~x.x, x.y, okw[1] & ~x.z, x.w);       // (nz, pos) of both words
+                    // regular instance: the prior is kept as (is +1, is -1), the form bec_vn3_pn consumes
+                    prior[item] = IRR ? pr : make_uint4(pr.y, pr.x & ~pr.y, pr.w, pr.z & ~pr.w);
 #pragma unroll
                     for (int k = 0; k < DV; ++k) {
                         if (IRR && k >= d) break;
@@ -231,27 +298,50 @@ __global__ void __launch_bounds__(320, 2) resident_bec(const BecResParams p)
 
             // ---- check-node phase (bec.py:100-112)
 #pragma unroll
-            for (int ps = 0; ps < kResCnPasses; ++ps) {
+            for (int ps = 0; ps < CNP; ++ps) {
                 if (tid + ps * T < mp) {
-                    const int dcr = IRR ? (int)(cw[ps][0] & 15u) : DC;
                     uint4 m[DC];
-                    BecCnAccT<uint32_t> a0, a1;
-                    a0.init(); a1.init();
+                    if (!IRR) {
 #pragma unroll
-                    for (int k = 0; k < DC; ++k) {
-                        if (!IRR || k < dcr) {
-                            m[k] = *reinterpret_cast<const uint4 *>(smem + cell_off(ps, k));
-                            a0.push(m[k].x, m[k].y);
-                            a1.push(m[k].z, m[k].w);
+                        for (int k = 0; k < DC; ++k) m[k] = *reinterpret_cast<const uint4 *>(smem + cell_off(ps, k));
+                        BecCn6<uint32_t> t0, t1;
+                        {
+                            const uint32_t nz[6] = {m[0].x, m[1].x, m[2].x, m[3].x, m[4].x, m[5].x};
+                            const uint32_t ps6[6] = {m[0].y, m[1].y, m[2].y, m[3].y, m[4].y, m[5].y};
+                            t0.reduce(nz, ps6);
                         }
-                    }
+                        {
+                            const uint32_t nz[6] = {m[0].z, m[1].z, m[2].z, m[3].z, m[4].z, m[5].z};
+                            const uint32_t ps6[6] = {m[0].w, m[1].w, m[2].w, m[3].w, m[4].w, m[5].w};
+                            t1.reduce(nz, ps6);
+                        }
 #pragma unroll
-                    for (int k = 0; k < DC; ++k) {
-                        if (!IRR || k < dcr) {
+                        for (int k = 0; k < DC; ++k) {
                             uint4 o;
-                            a0.out(m[k].x, m[k].y, o.x, o.y);
-                            a1.out(m[k].z, m[k].w, o.z, o.w);
+                            t0.out(m[k].x, m[k].y, o.x, o.y);
+                            t1.out(m[k].z, m[k].w, o.z, o.w);
                             *reinterpret_cast<uint4 *>(smem + cell_off(ps, k)) = o;
+                        }
+                    } else {
+                        const int dcr = (int)(cw[ps][0] & 15u);
+                        BecCnAccT<uint32_t> a0, a1;
+                        a0.init(); a1.init();
+#pragma unroll
+                        for (int k = 0; k < DC; ++k) {
+                            if (k < dcr) {
+                                m[k] = *reinterpret_cast<const uint4 *>(smem + cell_off(ps, k));
+                                a0.push(m[k].x, m[k].y);
+                                a1.push(m[k].z, m[k].w);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < DC; ++k) {
+                            if (k < dcr) {
+                                uint4 o;
+                                a0.out(m[k].x, m[k].y, o.x, o.y);
+                                a1.out(m[k].z, m[k].w, o.z, o.w);
+                                *reinterpret_cast<uint4 *>(smem + cell_off(ps, k)) = o;
+                            }
                         }
                     }
                 }
@@ -263,7 +353,7 @@ __global__ void __launch_bounds__(320, 2) resident_bec(const BecResParams p)
             // ---- variable-node phase (bec.py:115-119)
             uint32_t chg0 = 0u, chg1 = 0u, has0 = 0u, has1 = 0u;
 #pragma unroll
-            for (int ps = 0; ps < kResVnPasses; ++ps) {
+            for (int ps = 0; ps < VNP; ++ps) {
                 const int item = tid + ps * T;
                 if (item >= np) continue;
                 uint32_t mnz0, mpos0, mnz1, mpos1;
@@ -271,18 +361,20 @@ __global__ void __launch_bounds__(320, 2) resident_bec(const BecResParams p)
                     uint4 c[3];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) c[k] = *reinterpret_cast<const uint4 *>(smem + (size_t)(k + 1) * S + (size_t)item * 16);
-                    const uint4 pr = prior[item];
+                    const uint4 pr = prior[item];                        // (is +1, is -1) of both words
                     {
-                        const uint32_t nz[4] = {pr.x, c[0].x, c[1].x, c[2].x}, ps4[4] = {pr.y, c[0].y, c[1].y, c[2].y};
+                        const uint32_t ps4[4] = {pr.x, c[0].y, c[1].y, c[2].y};
+                        const uint32_t ng4[4] = {pr.y, c[0].x & ~c[0].y, c[1].x & ~c[1].y, c[2].x & ~c[2].y};
                         uint32_t onz[3], opos[3];
-                        bec_vn3<uint32_t>(nz, ps4, onz, opos, mnz0, mpos0);
+                        bec_vn3_pn<uint32_t>(ps4, ng4, onz, opos, mnz0, mpos0);
 #pragma unroll
                         for (int k = 0; k < 3; ++k) { c[k].x = onz[k]; c[k].y = opos[k]; }
                     }
                     {
-                        const uint32_t nz[4] = {pr.z, c[0].z, c[1].z, c[2].z}, ps4[4] = {pr.w, c[0].w, c[1].w, c[2].w};
+                        const uint32_t ps4[4] = {pr.z, c[0].w, c[1].w, c[2].w};
+                        const uint32_t ng4[4] = {pr.w, c[0].z & ~c[0].w, c[1].z & ~c[1].w, c[2].z & ~c[2].w};
                         uint32_t onz[3], opos[3];
-                        bec_vn3<uint32_t>(nz, ps4, onz, opos, mnz1, mpos1);
+                        bec_vn3_pn<uint32_t>(ps4, ng4, onz, opos, mnz1, mpos1);
 #pragma unroll
                         for (int k = 0; k < 3; ++k) { c[k].z = onz[k]; c[k].w = opos[k]; }
                     }
@@ -320,14 +412,14 @@ __global__ void __launch_bounds__(320, 2) resident_bec(const BecResParams p)
                     s1.sign(mnz1, mpos1);
                 }
                 // x_new = symbols[sign(marginal)] (bec.py:119), merged under the run mask; changed / has-erasures flags
+                // (xv is a subset of ~xe on both sides, so "changed" is just a difference in either plane)
                 const uint4 xo = xc[item];
-                const uint32_t xe0 = ~mnz0, xe1 = ~mnz1;
-                chg0 |= ((xe0 ^ xo.x) | (~xe0 & (mpos0 ^ xo.y))) & run0;
-                chg1 |= ((xe1 ^ xo.z) | (~xe1 & (mpos1 ^ xo.w))) & run1;
-                has0 |= xe0 & run0;
-                has1 |= xe1 & run1;
-                xc[item] = make_uint4((xo.x & ~run0) | (xe0 & run0), (xo.y & ~run0) | (mpos0 & run0 & ~xe0),
-                                      (xo.z & ~run1) | (xe1 & run1), (xo.w & ~run1) | (mpos1 & run1 & ~xe1));
+                chg0 |= ((~mnz0 ^ xo.x) | (mpos0 ^ xo.y)) & run0;
+                chg1 |= ((~mnz1 ^ xo.z) | (mpos1 ^ xo.w)) & run1;
+                has0 |= ~mnz0 & run0;
+                has1 |= ~mnz1 & run1;
+                xc[item] = make_uint4((xo.x & ~run0) | (~mnz0 & run0), (xo.y & ~run0) | (mpos0 & run0),
+                                      (xo.z & ~run1) | (~mnz1 & run1), (xo.w & ~run1) | (mpos1 & run1));
             }
             chg0 = __reduce_or_sync(kFull, chg0); chg1 = __reduce_or_sync(kFull, chg1);
             has0 = __reduce_or_sync(kFull, has0); has1 = __reduce_or_sync(kFull, has1);
@@ -342,30 +434,33 @@ __global__ void __launch_bounds__(320, 2) resident_bec(const BecResParams p)
         }
 
         // ================================ words out: bit planes -> rows ================================
-#pragma unroll 1
-        for (int w = 0; w < 2; ++w) {
-            if (nvalid[w] == 0) break;
-            if (w) __syncthreads();                                      // the copy of word 0 has left the staging area
-            for (int q = warp; q < n4; q += nwarps) {
-                uint32_t packed = 0u;
+        {
+            uint8_t *row0 = p.x_hat + (size_t)(f0 + lane) * n, *row1 = row0 + (size_t)32 * n;
+            for (int g = warp; g * 32 < n; g += nwarps) {
+                const int v = g * 32 + lane;
+                uint4 xw = make_uint4(0u, 0u, 0u, 0u);
+                if (v < n) xw = xc[s_vpos[v]];
+                const uint32_t E0 = bit_transpose32(xw.x, lane), V0 = bit_transpose32(xw.y, lane);   // lane = frame again
+                const uint32_t E1 = bit_transpose32(xw.z, lane), V1 = bit_transpose32(xw.w, lane);
+                uint32_t sy[8];
+                if (lane < nvalid[0]) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t pos = s_vpos[4 * q + b];
-                    const uint2 xw = reinterpret_cast<const uint2 *>(xc + pos)[w];
-                    const uint32_t sy = ((xw.x >> lane) & 1u) ? 2u : ((xw.y >> lane) & 1u);
-                    packed |= sy << (8 * b);
+                    for (int i = 0; i < 8; ++i) sy[i] = nibbles_to_sym4((V0 >> (4 * i)) & 0xfu, (E0 >> (4 * i)) & 0xfu);
+                    bec_store32(row0, g, n, vec16, vec4, sy);
                 }
-                reinterpret_cast<uint32_t *>(stage)[(size_t)lane * n4 + q] = packed;
+                if (lane < nvalid[1]) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sy[i] = nibbles_to_sym4((V1 >> (4 * i)) & 0xfu, (E1 >> (4 * i)) & 0xfu);
+                    bec_store32(row1, g, n, vec16, vec4, sy);
+                }
             }
-            __syncthreads();
-            bec_copy(p.x_hat + (size_t)(f0 + 32 * w) * n, stage, (size_t)nvalid[w] * n, tid, T);
-            if (warp == w && lane < nvalid[w]) {
-                const long long f = f0 + 32 * w + lane;
-                p.iters[f] = s_iters[w * 32 + lane];
+            if (warp < 2 && lane < nvalid[warp]) {
+                const long long f = f0 + 32 * warp + lane;
+                p.iters[f] = s_iters[warp * 32 + lane];
                 if (p.reason != nullptr) {
                     uint8_t r = LDPC_REASON_DECODED;
-                    if ((s_stop[w] >> lane) & 1u) r = LDPC_REASON_STOPPING;
-                    else if ((s_act[w] >> lane) & 1u) r = (uint8_t)p.bound_reason;
+                    if ((s_stop[warp] >> lane) & 1u) r = LDPC_REASON_STOPPING;
+                    else if ((s_act[warp] >> lane) & 1u) r = (uint8_t)p.bound_reason;
                     p.reason[f] = r;
                 }
             }

@@ -116,6 +116,23 @@ void decode_bp(const G &g, int algo, const T *prior, const uint8_t *y_hard, int 
 
 extern "C" {
 
+// BecCn6 (tree reduction) against BecCnAccT (sequential), one word: nz/pos [6] in, out [12] = (onz, opos) per edge.
+void emu_bec_cn6(const uint32_t *nz, const uint32_t *pos, uint32_t *fast, uint32_t *ref)
+{
+    uint32_t a[6], b[6];
+    for (int k = 0; k < 6; ++k) { a[k] = nz[k]; b[k] = pos[k]; }
+    ldpc::BecCn6<uint32_t> t;
+    t.reduce(a, b);
+    ldpc::BecCnAccT<uint32_t> acc;
+    acc.init();
+    for (int k = 0; k < 6; ++k) acc.push(a[k], b[k]);
+    for (int k = 0; k < 6; ++k) {
+        t.out(a[k], b[k], fast[2 * k], fast[2 * k + 1]);
+        acc.out(a[k], b[k], ref[2 * k], ref[2 * k + 1]);
+    }
+}
+
+
 // bec_vn3 (degree-3 variable node as boolean functions) against the bit-sliced integer form, on caller-supplied planes:
 // nz/pos [4] words in, out[8] = {onz0, opos0, onz1, opos1, onz2, opos2, mnz, mpos} for both formulations.
 void emu_bec_vn3(const uint32_t *nz, const uint32_t *pos, uint32_t *fast, uint32_t *ref)

@@ -389,3 +389,21 @@ def test_bec_degree3_variable_rule_is_exhaustively_the_integer_form(emu):
             for e in range(3):
                 Se = S - c[e + 1]
                 assert ((int(fast[2 * e]) >> lane) & 1, (int(fast[2 * e + 1]) >> lane) & 1) == (int(Se != 0), int(Se > 0))
+
+
+def test_bec_degree6_check_tree_equals_sequential_accumulator(emu):
+    """ldpc::BecCn6 (erasure count / parity as reduction trees) == BecCnAccT (bec.py:100-112) on random ternary inputs,
+    including every erasure count 0..6 in some lane."""
+    rng = np.random.RandomState(1)
+    for rep in range(200):
+        pe = rng.choice([0.0, 0.1, 0.3, 0.6, 1.0])
+        er = rng.rand(6, 32) < pe
+        if rep < 7:                                         # lanes with exactly rep erasures
+            er[:] = False
+            er[:rep] = True
+        posb = (rng.rand(6, 32) < .5) & ~er
+        nz = np.array([sum((0 if er[k, l] else 1) << l for l in range(32)) for k in range(6)], np.uint32)
+        pos = np.array([sum(int(posb[k, l]) << l for l in range(32)) for k in range(6)], np.uint32)
+        fast = np.zeros(12, np.uint32); ref = np.zeros(12, np.uint32)
+        emu.emu_bec_cn6(ptr(nz), ptr(pos), ptr(fast), ptr(ref))
+        assert (fast == ref).all(), rep
