@@ -39,6 +39,34 @@ def bind_near_gpu(index):
         return None
 
 
+def bind_memory_near_gpu(index):
+    """Prefer the NUMA node of CUDA device `index` for every page this process allocates from now on — in particular the
+    pinned host buffers of decode_host, whose pages are placed when cudaHostAlloc pins them — via
+    set_mempolicy(MPOL_PREFERRED) (CPU affinity alone does not move memory).  Returns the node, or None when the
+    topology is not visible / the box is a single node / the syscall is refused (containers) / LDPC_NUMA_BIND=0."""
+    if os.environ.get("LDPC_NUMA_BIND", "1") == "0":
+        return None
+    try:
+        import ctypes
+        import platform
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fp:
+            node = int(fp.read().strip())
+        if node < 0 or not os.path.isdir("/sys/devices/system/node/node%d" % node):
+            return None
+        nr = {"x86_64": 238, "aarch64": 237}.get(platform.machine())
+        if nr is None:
+            return None
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED = 1
+        rc = ctypes.CDLL(None, use_errno=True).syscall(nr, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+        return node if rc == 0 else None
+    except Exception:
+        return None
+
+
 def parse_cpulist(text):
     """'0-3,8,10-11' -> {0,1,2,3,8,10,11} (the kernel's cpulist format)."""
     out = set()
@@ -69,6 +97,7 @@ class Comm:
                     quiet_nccl_stdout()
                     torch.cuda.set_device(self.local_rank)
                     bind_near_gpu(self.local_rank)
+                    bind_memory_near_gpu(self.local_rank)
                     dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
                 else:
                     dist.init_process_group(backend)

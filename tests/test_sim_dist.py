@@ -259,6 +259,7 @@ def test_parse_cpulist_and_bind_is_harmless_without_gpu():
     assert D.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
     assert D.parse_cpulist("") == set()
     assert D.bind_near_gpu(0) is None or isinstance(D.bind_near_gpu(0), set)     # no CUDA device here: a no-op
+    assert D.bind_memory_near_gpu(0) is None
 
 
 def test_random_irregular_sampler_follows_the_reference_construction():
