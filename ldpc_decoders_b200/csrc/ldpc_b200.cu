@@ -20,6 +20,7 @@
 #include "resident_bp.cuh"
 #include "resident_vp.cuh"
 #include "resident_vd.cuh"
+#include "resident_vq.cuh"
 #include "resident_bec.cuh"
 #include "stream_bec.cuh"
 #include "stream_bp.cuh"
@@ -610,6 +611,19 @@ int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_gri
     return LDPC_OK;
 }
 
+template <int ALGO, int TT, int NPC, int INMODE = -1, int INES = -1>
+int launch_resident_vq(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
+{
+    auto kern = resident_vq<ALGO, 6, 3, TT, NPC, INMODE, INES>;
+    int per_sm = 1;
+    int rc = resident_occupancy(h, kern, lc.threads, lc.smem, &per_sm);
+    if (rc) return rc;
+    const int grid = std::max(1, std::min(max_grid, h->sm_count * per_sm));
+    kern<<<grid, lc.threads, lc.smem, s>>>(rp);
+    h->launches++;
+    return LDPC_OK;
+}
+
 template <int TT, int NPC, bool IRR>
 int launch_resident_vd(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
@@ -690,6 +704,11 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
     int ring = 0;
     if (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(in.src) & 15u) == 0 && budget > state)
         ring = (int)std::min<size_t>(kResRingMax, (budget - state) / stride);
+    // regular codes, two-CTA geometry, float32, rows the bulk copy can stage, no separate hard input: the kernel with the
+    // frame hand-over fused into its variable phase (LDPC_RESIDENT_VP=1 keeps resident_vp, for A/B runs)
+    const bool use_vq = r.vp && !r.vp_big && dtype == LDPC_F32 && ring >= 2 && in.y_hard == nullptr && r.regular36 &&
+                        getenv("LDPC_RESIDENT_VP") == nullptr;
+    if (use_vq) ring = std::min(ring, kVqRing);
     rp.ring = ring;
     rp.stage_stride = (int)stride;
     ResLaunch lc;
@@ -717,6 +736,20 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
     } else if (r.vp_big) {
         rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 0, 0, false, kVpBigThreads>(h, rp, lc, max_grid, s)
                                 : launch_resident_vp<ALGO_SPA_PHI, 0, 0, false, kVpBigThreads>(h, rp, lc, max_grid, s);
+    } else if (r.vp && use_vq) {                                      // frame hand-over fused into the variable phase (resident_vq.cuh)
+        const bool ens = lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200;      // the reference's (1200,3,6) ensemble
+        if (ens && rp.in_mode == IN_BIAWGN && rp.in_es == 4)                                   // ... on float32 BIAWGN rows: the headline
+            rc = (algo == LDPC_MSA) ? launch_resident_vq<ALGO_MSA, 320, 1200, IN_BIAWGN, 4>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vq<ALGO_SPA_PHI, 320, 1200, IN_BIAWGN, 4>(h, rp, lc, max_grid, s);
+        else if (ens && rp.in_mode == IN_BSC)
+            rc = (algo == LDPC_MSA) ? launch_resident_vq<ALGO_MSA, 320, 1200, IN_BSC, 1>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vq<ALGO_SPA_PHI, 320, 1200, IN_BSC, 1>(h, rp, lc, max_grid, s);
+        else if (ens)
+            rc = (algo == LDPC_MSA) ? launch_resident_vq<ALGO_MSA, 320, 1200>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vq<ALGO_SPA_PHI, 320, 1200>(h, rp, lc, max_grid, s);
+        else
+            rc = (algo == LDPC_MSA) ? launch_resident_vq<ALGO_MSA, 0, 0>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vq<ALGO_SPA_PHI, 0, 0>(h, rp, lc, max_grid, s);
     } else if (r.vp) {
         if (lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200)      // the reference's (1200,3,6) ensemble
             rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320, 1200>(h, rp, lc, max_grid, s)

@@ -1,0 +1,300 @@
+// resident_vq.cuh — resident_vp with the frame hand-over FUSED INTO THE VARIABLE PHASE (regular codes, float32).
+//
+// In resident_vp a frame that leaves costs three CTA-wide barriers and a separate refill pass: every thread converts
+// four received values and scatters them into one lane of marg / prior as 4-byte stores that are 4-way bank-conflicted
+// by construction (19.9 M wavefronts for 5.4 M ideal), and the leaving frame's word is read back from shared memory.
+// ncu (profiles/, r1j): refill 16 % + output 11 % of the kernel's time; frames that never leave iterate 25 % faster.
+//
+// Here nothing of that exists as a phase:
+//   * every slot decision is CTA-UNIFORM and taken by every thread from the same shared flags right after the check
+//     phase's barrier: which frames decoded (syndrome zero), which complete their last iteration in THIS variable phase
+//     (the per-slot iteration counters live in registers of every thread), which ring entry each free slot takes (ring
+//     entries are consumed in order, so `head` is a register too).  No extra barrier, no thread-0 serial section;
+//   * the variable phase writes marg as whole 16-byte cells anyway.  A thread that owns position `item` writes the hard
+//     decision of a leaving frame straight from the cell it holds in registers (decoded frames: the cell as it was
+//     before this phase, one extra LDS.128), then overwrites that LANE of the cell with the new frame's prior, which it
+//     converts itself from the staged row (the value of variable imap[item]); the prior cell is rewritten the same way.
+//     All stores are the STS.128 of the phase: zero bank conflicts, zero extra wavefronts for marg;
+//   * the check phase zeroes the register-resident c2v of fresh lanes under a uniform branch.
+// Received rows land through cp.async.bulk + mbarrier (3 entries); thread 0 re-arms consumed entries after the phase's
+// barrier.  Arithmetic, exit rules and outputs are resident_vp's, bit for bit (tests/test_gpu_parity.py runs both).
+//
+// Handles: regular codes on resident_vp's tables in the two-CTA geometry, priors / BSC / BIAWGN input of any row type
+// the bulk copy can stage (16-byte aligned rows), no separate hard input (ldpc_decode with y_hard keeps resident_vp).
+#pragma once
+#include "resident_vp.cuh"
+
+namespace ldpc {
+
+constexpr int kVqRing = 3;
+
+// One received value -> prior.  INMODE / INES >= 0: the input mode and element size are compile-time (the headline
+// BIAWGN float32 rows and BSC bytes get their own instances); -1: read them from the parameters (res_llr's branches).
+template <int INMODE, int INES>
+__device__ __forceinline__ float vq_llr(const unsigned char *row, int v, int in_mode, int in_es, double param, double inv_param)
+{
+    uint32_t hbit;
+    if (INMODE < 0) return res_llr(row, v, in_mode, in_es, param, inv_param, &hbit);
+    return res_llr(row, v, INMODE, INES, param, inv_param, &hbit);
+}
+
+// INMODE / INES: see vq_llr.
+template <int ALGO, int DC, int DV, int TT, int NPC, int INMODE = -1, int INES = -1>
+__global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
+{
+    static_assert(DC >= 2 && DC <= 8 && DV >= 1 && DV <= 3, "regular codes: slot field is two bits");
+    constexpr int F = 4, CH = (DC + 1) / 2, VNP = kResVnPasses;
+    constexpr uint32_t ALL = 0xFu;
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int MPC = NPC * DV / DC;
+    const int np = NPC ? NPC : p.n, mp = NPC ? MPC : p.m;
+    const uint32_t S = (uint32_t)np * 16u;
+    const VpSmem L = vp_smem_layout(np, DV, p.ring, p.stage_stride, true);
+    float4 *marg = reinterpret_cast<float4 *>(smem + L.marg);
+    float4 *planes = reinterpret_cast<float4 *>(smem + L.planes);
+    float4 *prior = reinterpret_cast<float4 *>(smem + L.prior);
+    unsigned char *stage = smem + L.stage;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+    uint16_t *imap = reinterpret_cast<uint16_t *>(smem + L.imap);       // variable at a position
+
+    __shared__ int r_frame[kVqRing];
+    __shared__ uint32_t s_unsat[2];
+
+    const int tid = threadIdx.x, T = TT ? TT : (int)blockDim.x, lane = tid & 31;
+    const bool have_hard = (p.in_mode == IN_BSC);                        // iteration-0 exit on the received bits (bpa.py:29)
+    const int nref = NPC ? NPC : p.nref;
+    const size_t row_bytes = (size_t)nref * p.in_es;
+    const int R = p.ring;
+
+    // ---- per-thread graph indices -> registers (once per CTA), as resident_vp
+    uint32_t cw[kResCnPasses][CH];
+#pragma unroll
+    for (int ps = 0; ps < kResCnPasses; ++ps) {
+        const int c = tid + ps * T;
+#pragma unroll
+        for (int h = 0; h < CH; ++h) cw[ps][h] = 0u;
+        if (c < mp) {
+#pragma unroll
+            for (int k = 0; k < DC; ++k) {
+                const uint32_t e = p.cw[(size_t)c * 8 + k];              // (position << 4) | (slot + 1)
+                if (k & 1) cw[ps][k >> 1] |= (e & 0xfff0u) << 16 | (e & 3u) << 2;
+                else cw[ps][k >> 1] |= e & 0xfff3u;
+            }
+        }
+    }
+    auto goff = [&](int ps, int k) -> uint32_t {
+        const uint32_t w = cw[ps][k >> 1];
+        return (k & 1) ? vp_off1(w) : vp_off0(w);
+    };
+    float4 old[kResCnPasses][DC];                                        // c2v of the thread's own checks
+#pragma unroll
+    for (int ps = 0; ps < kResCnPasses; ++ps)
+#pragma unroll
+        for (int k = 0; k < DC; ++k) old[ps][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int i = tid; i < np; i += T) imap[i] = p.vinvmap[i];
+    auto issue = [&](int e) {                                            // thread 0: fetch the next frame into ring entry e
+        const int g = atomicAdd(p.counter, 1);
+        if (g < p.B) {
+            r_frame[e] = g;
+            mbar_expect_tx(&bars[e], (uint32_t)row_bytes);
+            bulk_g2s(stage + (size_t)e * p.stage_stride, (const char *)p.src + (size_t)g * row_bytes, (uint32_t)row_bytes, &bars[e]);
+        } else {
+            r_frame[e] = -1;
+        }
+    };
+    if (tid == 0) {
+        s_unsat[0] = s_unsat[1] = 0u;
+        for (int e = 0; e < R; ++e) mbar_init(&bars[e], 1u);
+        fence_mbar_init();
+        for (int e = 0; e < R; ++e) issue(e);
+    }
+    __syncthreads();
+
+    // CTA-uniform slot state, identical in every thread
+    uint32_t active = 0u, fresh = 0u;
+    int it_s[F] = {0, 0, 0, 0}, fr_s[F] = {0, 0, 0, 0};
+    int head_e = 0;                                                      // ring entry the next frame comes from ...
+    uint32_t head_par = 0u;                                              // ... and the phase parity of its mbarrier
+    bool more = true;                                                    // the ring may still deliver frames
+    int par = 0;
+
+    for (;;) {
+        // ======================================= check-node phase =======================================
+        uint32_t unsat = 0u;
+        if (active != 0u) {
+            if (fresh != 0u) {                                           // new frames start from c2v = 0
+#pragma unroll
+                for (int ps = 0; ps < kResCnPasses; ++ps)
+#pragma unroll
+                    for (int k = 0; k < DC; ++k) {
+                        if (fresh & 1u) old[ps][k].x = 0.f;
+                        if (fresh & 2u) old[ps][k].y = 0.f;
+                        if (fresh & 4u) old[ps][k].z = 0.f;
+                        if (fresh & 8u) old[ps][k].w = 0.f;
+                    }
+            }
+#pragma unroll
+            for (int ps = 0; ps < kResCnPasses; ++ps) {
+                if (tid + ps * T < mp) {
+                    float4 mg[DC];
+#pragma unroll
+                    for (int k = 0; k < DC; ++k) mg[k] = *reinterpret_cast<const float4 *>(smem + goff(ps, k));
+                    uint32_t sx[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int k = 0; k < DC; ++k) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float mv = (&mg[k].x)[j];
+                            sx[j] ^= f32_bits(mv);                       // sign bit == (marg < 0), see resident_vp
+                            (&mg[k].x)[j] = __fsub_rn(mv, (&old[ps][k].x)[j]);       // v2c = marg - c2v_old (bpa.py:37)
+                        }
+                    }
+                    const uint32_t syn = (sx[0] >> 31) | ((sx[1] >> 31) << 1) | ((sx[2] >> 31) << 2) | ((sx[3] >> 31) << 3);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float a[DC], o[DC];
+#pragma unroll
+                        for (int k = 0; k < DC; ++k) a[k] = (&mg[k].x)[j];
+                        if (ALGO == ALGO_MSA) cn_msa_lean<DC>(a, o);
+                        else cn_spa_sc<DC>(a, DC, o, p.sat_llr);
+#pragma unroll
+                        for (int k = 0; k < DC; ++k) (&old[ps][k].x)[j] = o[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < DC; ++k) {
+                        const uint32_t w = cw[ps][k >> 1];
+                        const uint32_t coff = (k & 1) ? vp_sl1x4(w) * (S >> 2) + vp_off1(w) : vp_sl0(w) * S + vp_off0(w);
+                        *reinterpret_cast<float4 *>(smem + coff) = old[ps][k];
+                    }
+                    unsat |= syn;
+                }
+            }
+            unsat = __reduce_or_sync(kFull, unsat);
+            if (lane == 0 && unsat != 0u) atomicOr(&s_unsat[par], unsat);
+        }
+        __syncthreads();
+
+        // ======================================= slot decisions (every thread, uniform) =======================================
+        uint32_t us = __reduce_or_sync(kFull, s_unsat[par]);
+        if (!have_hard) us |= fresh;                                     // a new frame's marg is its prior: no syndrome test yet
+        const uint32_t decoded = active & ~us;                           // leaves with its iteration count unchanged (bpa.py:29)
+        const uint32_t run = active & us;
+        uint32_t maxed = 0u;
+#pragma unroll
+        for (int s = 0; s < F; ++s)
+            if ((run >> s) & 1u) {
+                it_s[s] += 1;                                            // bpa.py:63
+                if (it_s[s] >= p.limit) maxed |= 1u << s;                // bpa.py:28 at the top of the next round
+            }
+        if (tid == 0) s_unsat[par ^ 1] = 0u;
+        const uint32_t leaving = decoded | maxed;
+        if (tid < F && ((leaving >> tid) & 1u)) {
+            int g = fr_s[0], itv = it_s[0];
+#pragma unroll
+            for (int s = 1; s < F; ++s)
+                if (tid == s) { g = fr_s[s]; itv = it_s[s]; }
+            p.iters[g] = itv;
+            if (p.reason != nullptr) p.reason[g] = (uint8_t)(((decoded >> tid) & 1u) ? LDPC_REASON_DECODED : p.bound_reason);
+        }
+        // free slots take the next landed rows, in slot order
+        uint32_t inst = 0u;
+        int ent[F] = {0, 0, 0, 0}, nfr[F] = {0, 0, 0, 0};
+        const uint32_t freem = (~active | leaving) & ALL;
+        if (freem != 0u && more) {
+            int taken = 0;
+#pragma unroll
+            for (int s = 0; s < F; ++s) {
+                if (((freem >> s) & 1u) && more && taken < R) {
+                    const int g = r_frame[head_e];
+                    if (g < 0) {
+                        more = false;
+                    } else {
+                        mbar_wait(&bars[head_e], head_par);
+                        ent[s] = head_e; nfr[s] = g;
+                        inst |= 1u << s;
+                        ++taken;
+                        if (++head_e == R) { head_e = 0; head_par ^= 1u; }
+                    }
+                }
+            }
+        }
+        if (active == 0u && inst == 0u) break;                           // nothing running, nothing left to start
+
+        // ======================================= variable-node phase =======================================
+        auto vn_item = [&](int item, float4 &pr, float4 &mgv) {
+            float4 c[DV];
+#pragma unroll
+            for (int k = 0; k < DV; ++k) c[k] = planes[(size_t)k * np + item];
+            pr = prior[item];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float s = (&c[0].x)[j];
+#pragma unroll
+                for (int k = 1; k < DV; ++k) s = __fadd_rn(s, (&c[k].x)[j]);
+                (&mgv.x)[j] = __fadd_rn((&pr.x)[j], s);                  // bpa.py:35
+            }
+        };
+        if ((leaving | inst) == 0u) {                                    // the common iteration: nothing but the sums
+#pragma unroll
+            for (int ps = 0; ps < VNP; ++ps) {
+                const int item = tid + ps * T;
+                if (item < np) {
+                    float4 pr, mgv;
+                    vn_item(item, pr, mgv);
+                    marg[item] = mgv;
+                }
+            }
+        } else {                                                         // a frame leaves and / or a new one moves in
+            uint8_t *dst[F];
+            const unsigned char *row[F];
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                dst[j] = p.x_hat + (size_t)fr_s[j] * nref;
+                row[j] = stage + (size_t)ent[j] * p.stage_stride;
+            }
+#pragma unroll 1
+            for (int ps = 0; ps < VNP; ++ps) {
+                const int item = tid + ps * T;
+                if (item >= np) break;
+                float4 pr, mgv;
+                vn_item(item, pr, mgv);
+                const uint32_t v = imap[item];
+                if (decoded != 0u) {                                     // word = the marginal this frame's last check phase saw
+                    const float4 om = marg[item];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((decoded >> j) & 1u) dst[j][v] = (uint8_t)(f32_bits((&om.x)[j]) >> 31);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((maxed >> j) & 1u) dst[j][v] = (uint8_t)(f32_bits((&mgv.x)[j]) >> 31);
+                if (inst != 0u) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((inst >> j) & 1u) {
+                            const float val = vq_llr<INMODE, INES>(row[j], (int)v, p.in_mode, p.in_es, p.param, p.inv_param);
+                            (&mgv.x)[j] = val;
+                            (&pr.x)[j] = val;
+                        }
+                    prior[item] = pr;
+                }
+                marg[item] = mgv;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && inst != 0u) {                                    // the staged rows are consumed: fetch the next frames
+#pragma unroll
+            for (int s = 0; s < F; ++s)
+                if ((inst >> s) & 1u) issue(ent[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < F; ++s)
+            if ((inst >> s) & 1u) { fr_s[s] = nfr[s]; it_s[s] = 0; }
+        active = (run & ~maxed) | inst;
+        fresh = inst;
+        par ^= 1;
+    }
+}
+
+}  // namespace ldpc
