@@ -25,9 +25,12 @@
  *     ldpc_debug_step are asynchronous on the given stream; ldpc_create /
  *     ldpc_destroy / ldpc_decode_host synchronise.  ONE exception: a decode on
  *     the streaming path whose iteration bound exceeds 32 (max_iter > 32, or
- *     max_iter <= 0 = "unlimited") reads one word back every 8 iterations
- *     (cudaStreamSynchronize on the given stream) to stop launching sweeps once
- *     every frame has left; such a call cannot be captured into a CUDA graph.
+ *     max_iter <= 0 = "unlimited") reads two words back every 2 - 4 iterations
+ *     (cudaStreamSynchronize on the given stream): whether any frame still runs
+ *     (to stop launching sweeps) and how many (active-frame compaction: once at
+ *     most 70 % of the frame columns are live they are packed to the front of
+ *     every row, LDPC_NO_COMPACTION=1 in the environment disables it); such a
+ *     call cannot be captured into a CUDA graph.
  *     The on-chip path (one launch per batch) never synchronises.
  *   - one handle per (process, device); a handle is not thread-safe.
  *   - there is NO CPU fallback: without a CUDA device ldpc_create fails.

@@ -187,8 +187,11 @@ __global__ void __launch_bounds__(256) ingest_bec_tiled(const uint8_t *__restric
 }
 
 // bit planes -> x_hat [B][n] bytes (symbol 2 where xer is set), same tile.
+// orig (optional): column f of the planes holds frame orig[f] (active-frame compaction, stream_bp.cuh); columns whose
+// frame index is >= B are padding.
 __global__ void __launch_bounds__(256) emit_words_tiled(const uint32_t *__restrict__ xval, const uint32_t *__restrict__ xer,
-                                                        uint8_t *__restrict__ x_hat, int B, int n, int wpr)
+                                                        uint8_t *__restrict__ x_hat, int B, int n, int wpr,
+                                                        const int *__restrict__ orig = nullptr, int extent = 0x7fffffff)
 {
     __shared__ uint32_t in_v[kTileVars][8], in_e[kTileVars][8];
     __shared__ uint32_t sym[kTileFrames][kTileRowWords];
@@ -220,7 +223,9 @@ __global__ void __launch_bounds__(256) emit_words_tiled(const uint32_t *__restri
 #pragma unroll
     for (int i = 0; i < kTileFrames * 8 / 256; ++i) {
         const int idx = tid + i * 256, r = idx >> 3, q = idx & 7;
-        const int f = f0 + r, v = v0 + 4 * q;
+        int f = f0 + r;
+        const int v = v0 + 4 * q;
+        if (orig != nullptr) f = (f < extent) ? orig[f] : B;
         if (f < B && v < n) *reinterpret_cast<uint32_t *>(x_hat + (size_t)f * n + v) = sym[r][q];
     }
 }
@@ -293,7 +298,8 @@ __global__ void init_flags(uint32_t *act, uint32_t *unsat, int *iters, int B, in
 
 // xbits [n][wpr] (and, for BEC, the erased plane) -> x_hat [B][n] uint8.  grid (ceil(n/32), wpr), block (32, 8).
 __global__ void emit_words(const uint32_t *__restrict__ xval, const uint32_t *__restrict__ xer,
-                           uint8_t *__restrict__ x_hat, int B, int n, int wpr)
+                           uint8_t *__restrict__ x_hat, int B, int n, int wpr,
+                           const int *__restrict__ orig = nullptr, int extent = 0x7fffffff)
 {
     const int v = blockIdx.x * 32 + threadIdx.x, w = blockIdx.y;
     uint32_t val = 0u, er = 0u;
@@ -302,24 +308,28 @@ __global__ void emit_words(const uint32_t *__restrict__ xval, const uint32_t *__
         if (xer != nullptr) er = xer[(size_t)v * wpr + w];
     }
     for (int l = threadIdx.y; l < 32; l += 8) {
-        const int f = w * 32 + l;
+        int f = w * 32 + l;
+        if (orig != nullptr) f = (f < extent) ? orig[f] : B;
         if (f < B && v < n) x_hat[(size_t)f * n + v] = ((er >> l) & 1u) ? (uint8_t)2 : (uint8_t)((val >> l) & 1u);
     }
 }
 
 // iters / exit reason per frame.  still-active frames hit the loop bound: MAXIMUM (or CAP when unlimited).
+// orig / extent: see emit_words_tiled (thread = column f, output index = the frame it holds).
 __global__ void emit_status(const int *__restrict__ iters_ws, const uint32_t *__restrict__ act,
                             const uint32_t *__restrict__ stopped, int *__restrict__ iters, uint8_t *__restrict__ reason,
-                            int B, int bound_reason)
+                            int B, int bound_reason, const int *__restrict__ orig = nullptr, int extent = 0x7fffffff)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= B) return;
-    iters[f] = iters_ws[f];
+    if (f >= extent) return;
+    const int o = (orig != nullptr) ? orig[f] : f;
+    if (o >= B) return;
+    iters[o] = iters_ws[f];
     if (reason != nullptr) {
         uint8_t r = LDPC_REASON_DECODED;
         if (stopped != nullptr && ((stopped[f >> 5] >> (f & 31)) & 1u)) r = LDPC_REASON_STOPPING;
         else if ((act[f >> 5] >> (f & 31)) & 1u) r = (uint8_t)bound_reason;
-        reason[f] = r;
+        reason[o] = r;
     }
 }
 

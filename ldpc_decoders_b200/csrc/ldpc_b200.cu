@@ -141,7 +141,8 @@ BpLayout bp_layout(const Tables &t, int dtype, int B, bool want_marg)
     b += align_up((size_t)t.n * L.wpr * 4, 256);                // xbits
     b += 2 * align_up((size_t)L.wpr * 4, 256);                  // act, unsat
     b += align_up((size_t)L.Bp * 4, 256);                       // iters
-    b += 256;                                                   // any_active
+    b += 256;                                                   // any_active, live count
+    b += 2 * align_up((size_t)L.Bp * 4, 256);                   // src_of, orig (active-frame compaction)
     L.bytes = b + 256;
     return L;
 }
@@ -210,12 +211,12 @@ template <typename KernelT> int resident_occupancy(ldpc_t *h, KernelT kern, int 
 
 // Check-node sweep: bulk-async staged kernel for check degrees <= 8, register kernel otherwise / on request.
 template <typename T, int ALGO>
-int launch_cn(ldpc_t *h, BpParams<T> p, bool tma, cudaStream_t s)
+int launch_cn(ldpc_t *h, BpParams<T> p, bool tma, cudaStream_t s, int extent)
 {
     constexpr int FPT = Fpt<T>::value;
     const Tables &t = h->t;
     if (tma && t.max_dc <= 8) {
-        const int gx = p.Bp / (kTmaThreads * FPT);
+        const int gx = extent / (kTmaThreads * FPT);                // frame tiles in the extent (p.Bp stays the row pitch)
         int gy = std::max(1, std::min(t.m, (h->sm_count * 8) / std::max(1, gx)));
         p.per_cta = (t.m + gy - 1) / gy;
         gy = (t.m + p.per_cta - 1) / p.per_cta;
@@ -265,16 +266,16 @@ int launch_vn(ldpc_t *h, const BpParams<T> &p, dim3 grid, cudaStream_t s)
 }
 
 template <typename T>
-int launch_cn_algo(ldpc_t *h, int algo, const BpParams<T> &p, bool tma, cudaStream_t s);
+int launch_cn_algo(ldpc_t *h, int algo, const BpParams<T> &p, bool tma, cudaStream_t s, int extent);
 template <>
-int launch_cn_algo<float>(ldpc_t *h, int algo, const BpParams<float> &p, bool tma, cudaStream_t s)
+int launch_cn_algo<float>(ldpc_t *h, int algo, const BpParams<float> &p, bool tma, cudaStream_t s, int extent)
 {
-    return algo == LDPC_MSA ? launch_cn<float, ALGO_MSA>(h, p, tma, s) : launch_cn<float, ALGO_SPA_PHI>(h, p, tma, s);
+    return algo == LDPC_MSA ? launch_cn<float, ALGO_MSA>(h, p, tma, s, extent) : launch_cn<float, ALGO_SPA_PHI>(h, p, tma, s, extent);
 }
 template <>
-int launch_cn_algo<double>(ldpc_t *h, int algo, const BpParams<double> &p, bool tma, cudaStream_t s)
+int launch_cn_algo<double>(ldpc_t *h, int algo, const BpParams<double> &p, bool tma, cudaStream_t s, int extent)
 {
-    return algo == LDPC_MSA ? launch_cn<double, ALGO_MSA>(h, p, tma, s) : launch_cn<double, ALGO_SPA_REF>(h, p, tma, s);
+    return algo == LDPC_MSA ? launch_cn<double, ALGO_MSA>(h, p, tma, s, extent) : launch_cn<double, ALGO_SPA_REF>(h, p, tma, s, extent);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -421,7 +422,9 @@ int decode_bp_stream(ldpc_t *h, int algo, const InSpec &in, int B, int max_iter,
     p.act = cv.take<uint32_t>(L.wpr);
     p.unsat = cv.take<uint32_t>(L.wpr);
     p.iters = cv.take<int>(L.Bp);
-    int *any_active = cv.take<int>(1);
+    int *any_active = cv.take<int>(2);                              // [0] some frame runs, [1] how many
+    int *src_of = cv.take<int>(L.Bp);
+    int *orig = cv.take<int>(L.Bp);
 
     bool have_hard = false;
     int rc = ingest_bp<T>(h, in, prior, p.xbits, B, L, s, &have_hard);
@@ -431,47 +434,80 @@ int decode_bp_stream(ldpc_t *h, int algo, const InSpec &in, int B, int max_iter,
     }
     LAUNCH(h, init_flags, (L.Bp + 255) / 256, 256, s, p.act, p.unsat, p.iters, B, L.Bp, L.wpr, have_hard ? 0 : 1);
 
-    int vpc = 1;
-    const dim3 vgrid = sweep_grid(h, L.ngroups, t.n, &vpc);
-    const int book_blocks = (L.wpr * 32 + 255) / 256;
+    // Long runs (iteration bound above 32, or "unlimited") read two words back every 4 iterations: whether any frame
+    // still runs (to stop launching sweeps) and how many (to compact the live columns once half of them are done).
+    const int TF = frames_per_tile(dtype), G = frames_per_group(dtype);
     const bool poll = (max_iter <= 0) || (limit > 32);
+    const bool may_compact = poll && marg_out == nullptr && getenv("LDPC_NO_COMPACTION") == nullptr;
+    // a read-back drains the stream (~20 us): every 2 iterations when an iteration moves >= 64 MB, every 4 otherwise
+    const int poll_every = ((size_t)t.E * L.Bp * sizeof(T) >= ((size_t)64 << 20)) ? 2 : 4;
+    int extent = L.Bp;                                              // frame columns the sweeps cover (a multiple of TF)
+    bool compacted = false;
     PollState ps{any_active, nullptr};
     if (poll) {
         rc = ensure_stage(h);
         if (rc) return rc;
         ps.h_flag = h->stage->h_flag;
     }
+    auto emit_all = [&]() -> int {                                  // words, iteration counts, reasons of the columns in `extent`
+        const int wx = extent / 32;
+        const int *og = compacted ? orig : nullptr;
+        const dim3 egrid((t.n + 31) / 32, wx), eblock(32, 8);
+        if (rows_word_aligned(x_hat, t.n)) LAUNCH(h, emit_words_tiled, tile_grid(t.n, wx), 256, s, p.xbits, (const uint32_t *)nullptr, x_hat, B, t.n, L.wpr, og, extent);
+        else LAUNCH(h, emit_words, egrid, eblock, s, p.xbits, (const uint32_t *)nullptr, x_hat, B, t.n, L.wpr, og, extent);
+        const int cols = compacted ? extent : B;
+        LAUNCH(h, emit_status, (cols + 255) / 256, 256, s, p.iters, p.act, (const uint32_t *)nullptr, iters, reason, B,
+               max_iter > 0 ? LDPC_REASON_MAXIMUM : LDPC_REASON_CAP, og, compacted ? extent : 0x7fffffff);
+        return LDPC_OK;
+    };
 
     for (int it = 0; it < limit; ++it) {
         p.first = (it == 0);
         p.skip_syn = (it == 0 && !have_hard);
+        p.Bp = L.Bp; p.wpr = L.wpr;                                 // pitches stay; the extent shrinks with compaction
+        p.ngroups = extent / G;
         ProfEvent *pe = prof_begin(h, 0, s);
-        rc = launch_cn_algo<T>(h, algo, p, tma, s);
+        rc = launch_cn_algo<T>(h, algo, p, tma, s, extent);
         prof_end(pe, s);
         if (rc) return rc;
-        const bool poll_now = poll && it >= 8 && (it % 8) == 0;
-        if (poll_now) CUDA_TRY(h, cudaMemsetAsync(any_active, 0, sizeof(int), s));
-        LAUNCH(h, bp_book, book_blocks, 256, s, p.act, p.unsat, p.iters, L.wpr, any_active);
+        const bool poll_now = poll && it >= 4 && (it % poll_every) == 0;
+        if (poll_now) CUDA_TRY(h, cudaMemsetAsync(any_active, 0, 2 * sizeof(int), s));
+        LAUNCH(h, bp_book, (extent + 255) / 256, 256, s, p.act, p.unsat, p.iters, extent / 32, any_active);
+        int live = -1;
         if (poll_now) {
-            bool active = true;
-            rc = poll_any_active(h, ps, s, &active);
-            if (rc) return rc;
-            if (!active) break;
+            CUDA_TRY(h, cudaMemcpyAsync(ps.h_flag, ps.d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            if (ps.h_flag[0] == 0) break;
+            live = ps.h_flag[1];
         }
+        int vpc = 1;
+        const dim3 vgrid = sweep_grid(h, p.ngroups, t.n, &vpc);
         p.per_cta = vpc;
         pe = prof_begin(h, 1, s);
         rc = launch_vn<T>(h, p, vgrid, s);
         prof_end(pe, s);
         if (rc) return rc;
+        // packing costs ~0.4 of an iteration's traffic and every later iteration saves 1 - live / extent of its own:
+        // worth it once <= 70 % of the columns are live (and the tile-rounded extent really shrinks)
+        if (may_compact && live > 0 && 10 * (long long)live <= 7 * (long long)extent && (live + TF - 1) / TF * TF < extent && it + 1 < limit) {
+            // ---- active-frame compaction: retire what is done, pack the live columns to the front of every row
+            if (!compacted) LAUNCH(h, iota_kernel, (L.Bp + 255) / 256, 256, s, orig, L.Bp);
+            compacted = true;
+            if ((rc = emit_all()) != 0) return rc;                  // finished frames leave now (live ones are rewritten at the end)
+            LAUNCH(h, compact_plan, 1, 1024, s, p.act, extent / 32, src_of);
+            LAUNCH(h, (compact_rows<T>), t.E, 256, s, p.msg, (size_t)L.Bp, src_of, live);
+            LAUNCH(h, (compact_rows<T>), t.n, 256, s, prior, (size_t)L.Bp, src_of, live);
+            LAUNCH(h, (compact_rows<int>), 1, 256, s, p.iters, (size_t)L.Bp, src_of, live);
+            LAUNCH(h, (compact_rows<int>), 1, 256, s, orig, (size_t)L.Bp, src_of, live);
+            LAUNCH(h, compact_bits, t.n, 128, s, p.xbits, L.wpr, src_of, live);
+            extent = (live + TF - 1) / TF * TF;
+            LAUNCH(h, compact_flags, (extent / 32 + 255) / 256, 256, s, p.act, p.unsat, orig, extent / 32, live);
+        }
     }
 
-    const dim3 egrid((t.n + 31) / 32, L.wpr), eblock(32, 8);
-    if (rows_word_aligned(x_hat, t.n)) LAUNCH(h, emit_words_tiled, tile_grid(t.n, L.wpr), 256, s, p.xbits, (const uint32_t *)nullptr, x_hat, B, t.n, L.wpr);
-    else LAUNCH(h, emit_words, egrid, eblock, s, p.xbits, (const uint32_t *)nullptr, x_hat, B, t.n, L.wpr);
-    LAUNCH(h, emit_status, (B + 255) / 256, 256, s, p.iters, p.act, (const uint32_t *)nullptr, iters, reason, B,
-           max_iter > 0 ? LDPC_REASON_MAXIMUM : LDPC_REASON_CAP);
+    if ((rc = emit_all()) != 0) return rc;
     if (marg_out) {
-        const dim3 tgrid((B + 31) / 32, (t.n + 31) / 32);
+        const dim3 tgrid((B + 31) / 32, (t.n + 31) / 32), eblock(32, 8);
         LAUNCH(h, (transpose_tile<T>), tgrid, eblock, s, p.marg, (T *)marg_out, t.n, B, L.Bp, t.n);
     }
     return check_launch(h, "decode_bp_stream");
@@ -1053,7 +1089,7 @@ static int debug_step_t(ldpc_t *h, int algo, int which, int B, const void *prior
     LAUNCH(h, init_flags, (L.Bp + 255) / 256, 256, s, p.act, p.unsat, p.iters, B, L.Bp, L.wpr, 1);
     int rc;
     if (which == 0) {
-        rc = launch_cn_algo<T>(h, algo, p, true, s);
+        rc = launch_cn_algo<T>(h, algo, p, true, s, L.Bp);
         if (rc) return rc;
     } else {
         if (!prior_in) return fail(h, LDPC_EINVAL, "variable-node step needs priors");

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
         }
         // free slots take the next landed rows, in slot order
         uint32_t inst = 0u;
-        int ent[F] = {0, 0, 0, 0}, nfr[F] = {0, 0, 0, 0};
+        int ent[F], nfr[F];                                              // only read under the matching bit of `inst`
         const uint32_t freem = (~active | leaving) & ALL;
         if (freem != 0u && more) {
             int taken = 0;

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kCtaThreads) cn_sweep(const BpParams<T> p)
 // ------------------------------------------------------------------------------------------------
 // Book-keeping between the two sweeps: one warp per flag word, lane = frame.
 // ------------------------------------------------------------------------------------------------
+// any_active[0] = some frame still runs; any_active[1] += number of running frames (the host's compaction decision).
 __global__ void bp_book(uint32_t *act, uint32_t *unsat, int *iters, int wpr, int *any_active)
 {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -123,8 +124,110 @@ __global__ void bp_book(uint32_t *act, uint32_t *unsat, int *iters, int wpr, int
     if (lane == 0) {
         act[w] = run;
         unsat[w] = 0u;
-        if (run != 0u) *any_active = 1;
+        if (run != 0u) {
+            any_active[0] = 1;
+            atomicAdd(any_active + 1, __popc(run));
+        }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Active-frame compaction (north star (4)): when at most half of the frame columns still run, the live columns are
+// packed to the front of every row, so that the sweeps touch [rows][live] instead of [rows][all] — converged frames stop
+// consuming bandwidth at FRAME granularity, not only when a whole 512-frame tile is done.  Frames are independent, so
+// the results are unchanged; `orig` remembers which frame a column holds.
+//   compact_plan   src_of[j] = column of the j-th live frame (ascending: src_of[j] >= j)
+//   compact_rows   row[j] = row[src_of[j]] for j < live, in place: one CTA owns a row and walks it in ascending chunks
+//                  (load a chunk's sources, barrier, store) - sources are never behind the write front
+//   compact_bits   the same for the bit-packed hard decisions
+//   compact_flags  act = the first `live` columns
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) compact_plan(const uint32_t *__restrict__ act, int wx, int *__restrict__ src_of)
+{
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int per = (wx + 1023) / 1024, w0 = tid * per, w1 = min(wx, w0 + per);
+    int cnt = 0;
+    for (int w = w0; w < w1; ++w) cnt += __popc(act[w]);
+    part[tid] = cnt;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {                             // inclusive scan
+        const int v = (tid >= d) ? part[tid - d] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int j = part[tid] - cnt;
+    for (int w = w0; w < w1; ++w) {
+        uint32_t a = act[w];
+        while (a) {
+            const int b = __ffs(a) - 1;
+            a &= a - 1u;
+            src_of[j++] = w * 32 + b;
+        }
+    }
+}
+
+constexpr int kCompactChunk = 1024;
+template <typename U>
+__global__ void __launch_bounds__(256) compact_rows(U *__restrict__ base, size_t pitch, const int *__restrict__ src_of, int live)
+{
+    U *row = base + (size_t)blockIdx.x * pitch;
+    for (int c = 0; c < live; c += kCompactChunk) {
+        U v[kCompactChunk / 256];
+#pragma unroll
+        for (int i = 0; i < kCompactChunk / 256; ++i) {
+            const int j = c + threadIdx.x + i * 256;
+            if (j < live) v[i] = row[__ldg(src_of + j)];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kCompactChunk / 256; ++i) {
+            const int j = c + threadIdx.x + i * 256;
+            if (j < live) row[j] = v[i];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128) compact_bits(uint32_t *__restrict__ base, int wpr, const int *__restrict__ src_of, int live)
+{
+    uint32_t *row = base + (size_t)blockIdx.x * wpr;
+    const int lw = (live + 31) / 32;
+    for (int c = 0; c < lw; c += 128) {
+        const int w = c + threadIdx.x;
+        uint32_t out = 0u;
+        if (w < lw) {
+            for (int b = 0; b < 32; ++b) {
+                const int j = w * 32 + b;
+                if (j < live) {
+                    const int sj = __ldg(src_of + j);
+                    out |= ((row[sj >> 5] >> (sj & 31)) & 1u) << b;
+                }
+            }
+        }
+        __syncthreads();
+        if (w < lw) row[w] = out;
+        __syncthreads();
+    }
+}
+
+// ... and the columns behind them (padding up to the tile size) hold no frame any more: orig = "none".
+__global__ void compact_flags(uint32_t *act, uint32_t *unsat, int *orig, int wx, int live)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= wx) return;
+    const int lo = w * 32;
+    act[w] = (live >= lo + 32) ? 0xffffffffu : (live <= lo ? 0u : ((1u << (live - lo)) - 1u));
+    unsat[w] = 0u;
+    for (int j = max(lo, live); j < lo + 32; ++j) orig[j] = 0x7fffffff;
+}
+
+// orig[j] = j for the identity start.
+__global__ void iota_kernel(int *a, int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) a[i] = i;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--streaming", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--iters-out", default=None, help="save the per-frame iteration counts (.npy)")
     ap.add_argument("--n", type=int, default=0, help="synthetic (3,6) code of this length instead of --code")
     args = ap.parse_args()
 
@@ -74,6 +75,8 @@ def main():
     ms = t0.elapsed_time(t1) / args.steps
     iters = res["o"]["iters"].cpu().numpy()
     x = res["o"]["x_hat"]
+    if args.iters_out:
+        np.save(args.iters_out, iters)
     print("%s %s %s %s=%g frames=%d: %.3f ms/step, %.3f M frames/s, mean iters %.2f, WER %.4f, %.3e edge updates/s"
           % (args.code if not args.n else "synthetic(3,6) n=%d" % args.n, args.algo, args.dtype, args.channel, args.snr,
              args.frames, ms, args.frames / ms / 1e3, iters.mean(), float((x != args.cw).any(dim=1).float().mean()),

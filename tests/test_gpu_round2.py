@@ -146,6 +146,41 @@ def test_frames_per_call_limit_is_reported(mods):
     assert int(out["iters"].sum().item()) >= 0
 
 
+# ------------------------------------------------------------------------------------------ streaming compaction
+@pytest.mark.parametrize("n,snr,dt,frames", [(4000, 2.5, np.float32, 6000), (4000, 2.6, np.float64, 3000), (2000, 2.2, np.float32, 5000)])
+def test_streaming_compaction_is_invisible(mods, monkeypatch, n, snr, dt, frames):
+    """Active-frame compaction (max_iter > 32: live columns are packed to the front of the rows once half of them are
+    done) changes which column a frame lives in, never its result: words, iteration counts and exit reasons equal the
+    run with LDPC_NO_COMPACTION=1 and the oracle's; mixed finish times, several compactions, ragged last tile."""
+    import os
+    from ldpc_decoders_b200 import codes
+    torch, lib = mods["torch"], mods["lib"]
+    code = codes.random_regular(n, 3, 6, seed=5)
+    tab = code.tables
+    eng = mods["engine"].engine_for(tab)
+    og = O.Graph(tab.m, tab.n, tab.edge_chk.astype(np.int64), tab.edge_var.astype(np.int64))
+    Y = G.channel_send("biawgn", snr, np.ones((frames, tab.n), np.int64), 808)
+    Y[7] = 1.0                                               # a noise-free frame: done at the first syndrome test
+    pri = O.llr_biawgn(snr, Y).astype(dt)
+    d = torch.from_numpy(pri).cuda()
+    ref = O.bp_decode(og, O.MSA, pri[:1500], max_iter=60, nthreads=8)
+    n0 = eng.launch_count
+    a = eng.decode_device(lib.MSA, d, max_iter=60, flags=lib.PATH_STREAMING)
+    a = {k: (v.clone() if v is not None else None) for k, v in a.items()}
+    la = eng.launch_count - n0
+    monkeypatch.setenv("LDPC_NO_COMPACTION", "1")
+    n0 = eng.launch_count
+    b = eng.decode_device(lib.MSA, d, max_iter=60, flags=lib.PATH_STREAMING)
+    lb = eng.launch_count - n0
+    monkeypatch.delenv("LDPC_NO_COMPACTION")
+    for k in ("x_hat", "iters", "reason"):
+        assert bool((a[k] == b[k]).all()), k
+    assert (a["iters"].cpu().numpy()[:1500] == ref["iters"]).all() and (a["x_hat"].cpu().numpy()[:1500] == ref["x_hat"]).all()
+    it = a["iters"].cpu().numpy()
+    assert it.max() >= np.median(it) + 4                     # the workload really has stragglers ...
+    assert la > lb                                           # ... and the compaction kernels really ran
+
+
 # ------------------------------------------------------------------------------------------ device-side counters
 @pytest.mark.parametrize("channel,algo,param,code", [("biawgn", "MSA", 2.0, "1200_3_6_rand_ldpc_1"),
                                                       ("bsc", "SPA", .05, "1200_rho_x5_rand_ldpc_1"),
