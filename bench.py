@@ -516,9 +516,14 @@ def main():
 
     streaming = None
     effective_hbm = None
+    # regular codes in the two-CTA geometry run resident_vq (resident_vp with the frame hand-over fused into the variable
+    # phase) unless LDPC_RESIDENT_VP=1 asks for the older kernel; ldpc_resident_kernel names the family
+    res_name = eng.resident_kernel
+    if res_name == "resident_vp" and os.environ.get("LDPC_RESIDENT_VP") is None:
+        res_name = "resident_vq"
     if resident:
-        roofline, effective_hbm = resident_roofline(main, eng.resident_kernel, 4,
-                                                    "ncu (profiles/): no pipe saturated - shared-memory wavefronts 64 %, issue 50 %, ALU 44 %; frame hand-over ~20 % of the kernel.")
+        roofline, effective_hbm = resident_roofline(main, res_name, 4,
+                                                    "ncu (profiles/, r2e): no pipe saturated - shared-memory wavefronts 64 %, issue 58 %, ALU 46 %, FMA 15 %.")
         roofline["shared_memory_plan"] = eng.resident_plan()
         sm = measure(args.flags | lib.PATH_STREAMING)
         assert (sm["iters"] == iters).all() and bool((sm["x_hat"] == x_hat).all()), "streaming and resident paths disagree"
@@ -553,7 +558,7 @@ def main():
            "mean_iters": sp_it / B, "edge_updates_per_s": 2 * tab.E * sp_it_all * args.steps / (sp["ms"] / 1e3),
            "wer": float((sp["x_hat"] != 0).any(dim=1).float().mean().item()), "gpu_launches": int(sp["launches"])}
     if sp["prof"]["vn_launches"] == 0:
-        spa["roofline"], spa["effective_hbm"] = resident_roofline(sp, eng.resident_kernel, 4, "Sum-product adds the MUFU pipe (18 ex2/lg2 per check and frame) to the limiters.")
+        spa["roofline"], spa["effective_hbm"] = resident_roofline(sp, res_name, 4, "Sum-product adds the MUFU pipe (18 ex2/lg2 per check and frame) to the limiters.")
     else:
         spa["roofline"] = streaming_roofline(sp)
     del y_spa
