@@ -647,10 +647,10 @@ int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_gri
     return LDPC_OK;
 }
 
-template <int ALGO, int TT, int NPC, int INMODE = -1, int INES = -1>
+template <int ALGO, int TT, int NPC, int INMODE = -1, int INES = -1, bool IRR = false>
 int launch_resident_vq(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
-    auto kern = resident_vq<ALGO, 6, 3, TT, NPC, INMODE, INES>;
+    auto kern = resident_vq<ALGO, 6, IRR ? 8 : 3, TT, NPC, INMODE, INES, IRR>;
     int per_sm = 1;
     int rc = resident_occupancy(h, kern, lc.threads, lc.smem, &per_sm);
     if (rc) return rc;
@@ -742,7 +742,7 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
         ring = (int)std::min<size_t>(kResRingMax, (budget - state) / stride);
     // regular codes, two-CTA geometry, float32, rows the bulk copy can stage, no separate hard input: the kernel with the
     // frame hand-over fused into its variable phase (LDPC_RESIDENT_VP=1 keeps resident_vp, for A/B runs)
-    const bool use_vq = r.vp && !r.vp_big && dtype == LDPC_F32 && ring >= 2 && in.y_hard == nullptr && r.regular36 &&
+    const bool use_vq = ((r.vp && !r.vp_big && r.regular36) || r.vx) && dtype == LDPC_F32 && ring >= 2 && in.y_hard == nullptr &&
                         getenv("LDPC_RESIDENT_VP") == nullptr;
     if (use_vq) ring = std::min(ring, kVqRing);
     rp.ring = ring;
@@ -762,6 +762,17 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
         const bool ens = lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200;
         if (r.vx) rc = ens ? launch_resident_vd<320, 1200, true>(h, rp, lc, max_grid, s) : launch_resident_vd<0, 0, true>(h, rp, lc, max_grid, s);
         else rc = ens ? launch_resident_vd<320, 1200, false>(h, rp, lc, max_grid, s) : launch_resident_vd<0, 0, false>(h, rp, lc, max_grid, s);
+    } else if (r.vx && use_vq) {                                      // irregular instance, hand-over fused (resident_vq.cuh)
+        const bool ens = lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200;
+        if (ens && rp.in_mode == IN_BSC)                                           // config 4: the irregular ensemble on the BSC
+            rc = (algo == LDPC_MSA) ? launch_resident_vq<ALGO_MSA, 320, 1200, IN_BSC, 1, true>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vq<ALGO_SPA_PHI, 320, 1200, IN_BSC, 1, true>(h, rp, lc, max_grid, s);
+        else if (ens)
+            rc = (algo == LDPC_MSA) ? launch_resident_vq<ALGO_MSA, 320, 1200, -1, -1, true>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vq<ALGO_SPA_PHI, 320, 1200, -1, -1, true>(h, rp, lc, max_grid, s);
+        else
+            rc = (algo == LDPC_MSA) ? launch_resident_vq<ALGO_MSA, 0, 0, -1, -1, true>(h, rp, lc, max_grid, s)
+                                    : launch_resident_vq<ALGO_SPA_PHI, 0, 0, -1, -1, true>(h, rp, lc, max_grid, s);
     } else if (r.vx) {
         if (lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200)      // the reference's irregular n = 1200 ensemble
             rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 320, 1200, true>(h, rp, lc, max_grid, s)
@@ -1420,21 +1431,25 @@ int ldpc_decode_host(ldpc_t *h, int channel, int algo, int dtype, double param,
     if (in_packed && channel != LDPC_CH_BSC && channel != LDPC_CH_BEC)
         return fail(h, LDPC_EINVAL, "LDPC_IN_PACKED is for BSC / BEC symbol input");
     const unsigned dflags = flags & ~(LDPC_IN_PACKED | LDPC_OUT_PACKED | LDPC_HOST_ASYNC);
-    if (chunk <= 0) {
-        // Enough chunks to overlap H2D / decode / D2H on the 3 slot streams and keep the pipeline's ramp and tail short
-        // (B / 16; scripts/e2e_probe.py: 2048-frame chunks of the n = 1200 code reach 0.90 of a plain pinned H2D copy,
-        // 5461-frame chunks 0.87, one chunk 0.63), each chunk still filling the GPU (>= 2048 frames) and its message
-        // workspace bounded (~1 GiB per slot).
-        const size_t per_frame = (size_t)t.E * elem_size(dtype) + (size_t)t.n * elem_size(dtype) * 2;
-        size_t cap = ((size_t)1 << 30) / std::max<size_t>(per_frame, 1);
-        cap = std::max<size_t>(256, std::min<size_t>(cap, 16384));
-        size_t c = std::max<size_t>((size_t)B / 16, 2048);
-        c = std::min(c, cap);
-        chunk = (int)std::max<size_t>(128, c / 128 * 128);
-    }
-    chunk = std::min(chunk, B);
     const size_t in_row = in_packed ? planes * pstride : (size_t)t.n * in_es;      // bytes of one frame on the host side
     const size_t out_row = out_packed ? planes * pstride : (size_t)t.n;
+    if (chunk <= 0) {
+        // Enough chunks to overlap H2D / decode / D2H on the 3 slot streams and keep the pipeline's ramp and tail short,
+        // each chunk big enough that its copies (>= ~4 MiB in) outweigh the ~40 us of launches and copy set-up it costs:
+        // float32 rows of the n = 1200 code -> B / 16 (scripts/e2e_probe.py: 2048-frame chunks reach 0.90 of a plain
+        // pinned H2D copy, 5461-frame chunks 0.87, one chunk 0.63); bit-packed symbols are 30 x smaller per frame and want
+        // few, large chunks (round 2: BSC packed 26 -> 33 M frames/s, BEC packed 99 -> 150 M).  The chunk's message
+        // workspace stays bounded (~1 GiB per slot).
+        const size_t per_frame = (size_t)t.E * elem_size(dtype) + (size_t)t.n * elem_size(dtype) * 2;
+        size_t cap = ((size_t)1 << 30) / std::max<size_t>(per_frame, 1);
+        cap = std::max<size_t>(256, std::min<size_t>(cap, 65536));
+        const size_t total_in = (size_t)B * in_row;
+        size_t chunks = std::min<size_t>(16, std::max<size_t>(3, (total_in + ((size_t)4 << 20) - 1) / ((size_t)4 << 20)));
+        size_t c = std::max<size_t>(((size_t)B + chunks - 1) / chunks, 2048);
+        c = std::min(c, cap);
+        chunk = (int)std::max<size_t>(128, (c + 127) / 128 * 128);
+    }
+    chunk = std::min(chunk, B);
 
     HostStage *st = h->stage;
     int idx = st->next;

@@ -38,18 +38,19 @@ __device__ __forceinline__ float vq_llr(const unsigned char *row, int v, int in_
     return res_llr(row, v, INMODE, INES, param, inv_param, &hbit);
 }
 
-// INMODE / INES: see vq_llr.
-template <int ALGO, int DC, int DV, int TT, int NPC, int INMODE = -1, int INES = -1>
+// INMODE / INES: see vq_llr.  IRR: the irregular instance of resident_vp (check degrees 2..DC <= 6, variable degrees
+// 0..8, holes; one index word per edge, planes are prefixes of the positions, short checks padded with +inf cells).
+template <int ALGO, int DC, int DV, int TT, int NPC, int INMODE = -1, int INES = -1, bool IRR = false>
 __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
 {
-    static_assert(DC >= 2 && DC <= 8 && DV >= 1 && DV <= 3, "regular codes: slot field is two bits");
-    constexpr int F = 4, CH = (DC + 1) / 2, VNP = kResVnPasses;
+    static_assert(DC >= 2 && DC <= 8 && DV >= 1 && (IRR ? (DV <= 8 && DC <= 6) : DV <= 3), "see resident_vp");
+    constexpr int F = 4, CH = IRR ? DC : (DC + 1) / 2, VNP = kResVnPasses;
     constexpr uint32_t ALL = 0xFu;
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int MPC = NPC * DV / DC;
+    constexpr int MPC = IRR ? NPC / 2 : NPC * DV / DC;
     const int np = NPC ? NPC : p.n, mp = NPC ? MPC : p.m;
     const uint32_t S = (uint32_t)np * 16u;
-    const VpSmem L = vp_smem_layout(np, DV, p.ring, p.stage_stride, true);
+    const VpSmem L = IRR ? vx_smem_layout(np, p.plane_cells, p.ring, p.stage_stride) : vp_smem_layout(np, DV, p.ring, p.stage_stride, true);
     float4 *marg = reinterpret_cast<float4 *>(smem + L.marg);
     float4 *planes = reinterpret_cast<float4 *>(smem + L.planes);
     float4 *prior = reinterpret_cast<float4 *>(smem + L.prior);
@@ -74,15 +75,21 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
 #pragma unroll
         for (int h = 0; h < CH; ++h) cw[ps][h] = 0u;
         if (c < mp) {
+            if (IRR) {
 #pragma unroll
-            for (int k = 0; k < DC; ++k) {
-                const uint32_t e = p.cw[(size_t)c * 8 + k];              // (position << 4) | (slot + 1)
-                if (k & 1) cw[ps][k >> 1] |= (e & 0xfff0u) << 16 | (e & 3u) << 2;
-                else cw[ps][k >> 1] |= e & 0xfff3u;
+                for (int k = 0; k < DC; ++k) cw[ps][k] = p.cwx[(size_t)c * 8 + k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < DC; ++k) {
+                    const uint32_t e = p.cw[(size_t)c * 8 + k];          // (position << 4) | (slot + 1)
+                    if (k & 1) cw[ps][k >> 1] |= (e & 0xfff0u) << 16 | (e & 3u) << 2;
+                    else cw[ps][k >> 1] |= e & 0xfff3u;
+                }
             }
         }
     }
     auto goff = [&](int ps, int k) -> uint32_t {
+        if (IRR) return vx_goff(cw[ps][k]);
         const uint32_t w = cw[ps][k >> 1];
         return (k & 1) ? vp_off1(w) : vp_off0(w);
     };
@@ -93,6 +100,13 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
         for (int k = 0; k < DC; ++k) old[ps][k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int i = tid; i < np; i += T) imap[i] = p.vinvmap[i];
+    if (IRR) {
+        // cells nobody writes must read as +0.0 (short planes, holes), the padding cells behind marg as +inf
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f), i4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+        for (int i = tid; i < (int)(L.stage / 16); i += T) reinterpret_cast<float4 *>(smem)[i] = z4;
+        __syncthreads();
+        if (tid < 8) marg[np + tid] = i4;
+    }
     auto issue = [&](int e) {                                            // thread 0: fetch the next frame into ring entry e
         const int g = atomicAdd(p.counter, 1);
         if (g < p.B) {
@@ -151,6 +165,8 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
                         }
                     }
                     const uint32_t syn = (sx[0] >> 31) | ((sx[1] >> 31) << 1) | ((sx[2] >> 31) << 2) | ((sx[3] >> 31) << 3);
+                    // irregular, sum-product: a padding edge reads +inf (neutral), its own output is forced to 0 (resident_vp)
+                    const int dcr = (IRR && ALGO != ALGO_MSA) ? (int)(cw[ps][0] & 15u) : DC;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float a[DC], o[DC];
@@ -159,12 +175,17 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
                         if (ALGO == ALGO_MSA) cn_msa_lean<DC>(a, o);
                         else cn_spa_sc<DC>(a, DC, o, p.sat_llr);
 #pragma unroll
-                        for (int k = 0; k < DC; ++k) (&old[ps][k].x)[j] = o[k];
+                        for (int k = 0; k < DC; ++k) (&old[ps][k].x)[j] = (IRR && ALGO != ALGO_MSA && k >= 2 && k >= dcr) ? 0.f : o[k];
                     }
 #pragma unroll
                     for (int k = 0; k < DC; ++k) {
-                        const uint32_t w = cw[ps][k >> 1];
-                        const uint32_t coff = (k & 1) ? vp_sl1x4(w) * (S >> 2) + vp_off1(w) : vp_sl0(w) * S + vp_off0(w);
+                        uint32_t coff;
+                        if (IRR) {
+                            coff = vx_soff(cw[ps][k]);
+                        } else {
+                            const uint32_t w = cw[ps][k >> 1];
+                            coff = (k & 1) ? vp_sl1x4(w) * (S >> 2) + vp_off1(w) : vp_sl0(w) * S + vp_off0(w);
+                        }
                         *reinterpret_cast<float4 *>(smem + coff) = old[ps][k];
                     }
                     unsat |= syn;
@@ -223,15 +244,30 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
 
         // ======================================= variable-node phase =======================================
         auto vn_item = [&](int item, float4 &pr, float4 &mgv) {
-            float4 c[DV];
+            if (IRR) {
+                // plane k = a prefix of the positions (descending degree): ascending edge order, bpa.py:35
+                float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (item < p.pcnt[0]) sm = *reinterpret_cast<const float4 *>(smem + p.pbase[0] + (size_t)item * 16);
 #pragma unroll
-            for (int k = 0; k < DV; ++k) c[k] = planes[(size_t)k * np + item];
+                for (int k = 1; k < DV; ++k) {
+                    if (item >= p.pcnt[k]) break;
+                    const float4 c = *reinterpret_cast<const float4 *>(smem + p.pbase[k] + (size_t)item * 16);
+                    sm.x = __fadd_rn(sm.x, c.x); sm.y = __fadd_rn(sm.y, c.y);
+                    sm.z = __fadd_rn(sm.z, c.z); sm.w = __fadd_rn(sm.w, c.w);
+                }
+                pr = prior[item];
+                mgv = make_float4(__fadd_rn(pr.x, sm.x), __fadd_rn(pr.y, sm.y), __fadd_rn(pr.z, sm.z), __fadd_rn(pr.w, sm.w));
+                return;
+            }
+            float4 c[IRR ? 1 : DV];
+#pragma unroll
+            for (int k = 0; k < (IRR ? 1 : DV); ++k) c[k] = planes[(size_t)k * np + item];
             pr = prior[item];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float s = (&c[0].x)[j];
 #pragma unroll
-                for (int k = 1; k < DV; ++k) s = __fadd_rn(s, (&c[k].x)[j]);
+                for (int k = 1; k < (IRR ? 1 : DV); ++k) s = __fadd_rn(s, (&c[k].x)[j]);
                 (&mgv.x)[j] = __fadd_rn((&pr.x)[j], s);                  // bpa.py:35
             }
         };
@@ -260,6 +296,10 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
                 float4 pr, mgv;
                 vn_item(item, pr, mgv);
                 const uint32_t v = imap[item];
+                if (IRR && v == 0xffffu) {                               // a position without a variable: nothing leaves, nothing moves in
+                    marg[item] = mgv;
+                    continue;
+                }
                 if (decoded != 0u) {                                     // word = the marginal this frame's last check phase saw
                     const float4 om = marg[item];
 #pragma unroll
