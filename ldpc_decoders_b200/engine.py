@@ -388,6 +388,12 @@ class Engine:
         """One CN (which=0) or VN (which=1) sweep on messages [B, E] in np.where(H) edge order."""
         torch = _torch()
         t = self.tables
+        if msg_in.dim() != 2 or msg_in.shape[1] != t.E or not msg_in.is_cuda or not msg_in.is_contiguous():
+            raise ValueError("msg_in must be a contiguous CUDA tensor [B, E]")
+        if msg_in.dtype not in (torch.float32, torch.float64):
+            raise TypeError("messages must be float32 or float64")
+        if prior is not None and (tuple(prior.shape) != (msg_in.shape[0], t.n) or prior.dtype != msg_in.dtype or not prior.is_contiguous()):
+            raise ValueError("prior must be a contiguous [B, n] tensor of the message dtype")
         B = int(msg_in.shape[0])
         dtype = _lib.F32 if msg_in.dtype == torch.float32 else _lib.F64
         msg_out = torch.empty_like(msg_in)

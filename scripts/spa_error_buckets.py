@@ -22,8 +22,8 @@ def main():
         tab = Tables(*G.code_tables(rec["code"]))
         eng = engine.engine_for(tab)
         for dt, tdt in (("f64", torch.float64), ("f32", torch.float32)):
-            out, _ = eng.debug_step(lib.SPA, 0, torch.from_numpy(np.ascontiguousarray(v2c)).to("cuda", tdt))
-            got = out.double().cpu().numpy()
+            out, _ = eng.debug_step(lib.SPA, 0, torch.from_numpy(np.ascontiguousarray(v2c)[None, :]).to("cuda", tdt))
+            got = out.double().cpu().numpy()[0]
             ok = np.isfinite(c2v) & np.isfinite(got)
             d = np.abs(got - c2v)[ok]
             a = np.abs(c2v)[ok]
