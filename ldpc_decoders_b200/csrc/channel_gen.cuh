@@ -81,8 +81,12 @@ __global__ void channel_generate(void *__restrict__ y, const uint8_t *__restrict
     const long long total = (long long)B * groups;
     const uint32_t thr = (param >= 1.0) ? 0xffffffffu : (uint32_t)(param * 4294967296.0);   // u < p  <=>  r < p * 2^32
     const float sigma = (float)param;
+    const bool small = total < 0x7fffffffLL;                     // 32-bit index arithmetic (the 64-bit division costs ~40 instructions)
+    const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0;             // one 128-bit / 32-bit store per thread
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int f = (int)(i / groups), g = (int)(i % groups);
+        int f, g;
+        if (small) { f = (int)((uint32_t)i / (uint32_t)groups); g = (int)((uint32_t)i - (uint32_t)f * (uint32_t)groups); }
+        else { f = (int)(i / groups); g = (int)(i % groups); }
         const Philox4 r = channel_words(seed, frame0 + (unsigned long long)f, (uint32_t)g);
         const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
         float z[4] = {0.f, 0.f, 0.f, 0.f};
@@ -90,21 +94,60 @@ __global__ void channel_generate(void *__restrict__ y, const uint8_t *__restrict
             box_muller(r.x, r.y, &z[0], &z[1]);
             box_muller(r.z, r.w, &z[2], &z[3]);
         }
+        uint32_t xw = 0u;                                        // the four transmitted bits of the group, one per byte
+        if (x != nullptr) {
+            if ((n & 3) == 0) xw = __ldg(reinterpret_cast<const uint32_t *>(x) + g);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (4 * g + j < n) xw |= (uint32_t)x[4 * g + j] << (8 * j);
+            }
+        }
+        float out_f[4];
+        uint32_t out_b = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int v = 4 * g + j;
-            if (v >= n) break;
-            const uint32_t xb = (x != nullptr) ? (uint32_t)(x[v] != 0) : 0u;
-            const size_t o = (size_t)f * n + v;
+            const uint32_t xb = ((xw >> (8 * j)) & 0xffu) != 0u ? 1u : 0u;
             if (MODE == GEN_BIAWGN) {
-                reinterpret_cast<float *>(y)[o] = fmaf(sigma, z[j], xb ? 1.0f : -1.0f);
+                out_f[j] = fmaf(sigma, z[j], xb ? 1.0f : -1.0f);
             } else {
                 const bool hit = (param >= 1.0) || (rr[j] < thr);
-                if (MODE == GEN_BSC) reinterpret_cast<uint8_t *>(y)[o] = (uint8_t)(xb ^ (hit ? 1u : 0u));
-                else reinterpret_cast<uint8_t *>(y)[o] = (uint8_t)(hit ? 2u : xb);
+                out_b |= ((MODE == GEN_BSC) ? (xb ^ (hit ? 1u : 0u)) : (hit ? 2u : xb)) << (8 * j);
+            }
+        }
+        const size_t o = (size_t)f * n + (size_t)4 * g;
+        if (vec) {
+            if (MODE == GEN_BIAWGN) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + o) = make_float4(out_f[0], out_f[1], out_f[2], out_f[3]);
+            else *reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(y) + o) = out_b;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (4 * g + j >= n) break;
+                if (MODE == GEN_BIAWGN) reinterpret_cast<float *>(y)[o + j] = out_f[j];
+                else reinterpret_cast<uint8_t *>(y)[o + j] = (uint8_t)(out_b >> (8 * j));
             }
         }
     }
+}
+
+// Number of bytes that differ between two words of four symbols in {0, 1, 2}.
+__device__ __forceinline__ int sym4_diff(uint32_t a, uint32_t b)
+{
+    const uint32_t t = a ^ b;
+    return __popc((t | (t >> 1)) & 0x01010101u);
+}
+
+// One lane's share of #{v : row[v] != x[v]} (x NULL = the all-zero word); 4 symbols per load when the rows are word-aligned.
+__device__ __forceinline__ int row_errors(const uint8_t *__restrict__ row, const uint8_t *__restrict__ x, int n, int lane)
+{
+    int e = 0;
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(x)) & 3u) == 0) {
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(row), *xw = reinterpret_cast<const uint32_t *>(x);
+        for (int q = lane; q < (n >> 2); q += 32) e += sym4_diff(rw[q], (x != nullptr) ? __ldg(xw + q) : 0u);
+    } else {
+        for (int v = lane; v < n; v += 32) e += (row[v] != ((x != nullptr) ? x[v] : (uint8_t)0)) ? 1 : 0;
+    }
+    return e;
 }
 
 // bit_errs[b] = #{v : x_hat[b][v] != x[v]} (src/main.py:41; an undecoded BEC symbol 2 counts as an error).  One warp per frame.
@@ -114,8 +157,7 @@ __global__ void count_errors(const uint8_t *__restrict__ x_hat, const uint8_t *_
     const int f = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (f >= B) return;
     const uint8_t *row = x_hat + (size_t)f * n;
-    int e = 0;
-    for (int v = lane; v < n; v += 32) e += (row[v] != ((x != nullptr) ? x[v] : (uint8_t)0)) ? 1 : 0;
+    int e = row_errors(row, x, n, lane);
     e = __reduce_add_sync(kFull, e);
     if (lane == 0) bit_errs[f] = e;
 }
@@ -134,8 +176,7 @@ __global__ void __launch_bounds__(256) count_accumulate(const uint8_t *__restric
     const int f = blockIdx.x * 8 + warp;
     int e = 0, it = -1;
     if (f < B) {
-        const uint8_t *row = x_hat + (size_t)f * n;
-        for (int v = lane; v < n; v += 32) e += (row[v] != ((x != nullptr) ? x[v] : (uint8_t)0)) ? 1 : 0;
+        e = row_errors(x_hat + (size_t)f * n, x, n, lane);
         e = __reduce_add_sync(kFull, e);
         it = iters[f];
         if (lane == 0 && bit_errs != nullptr) bit_errs[f] = e;
