@@ -647,10 +647,10 @@ int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_gri
     return LDPC_OK;
 }
 
-template <int ALGO, int TT, int NPC, int INMODE = -1, int INES = -1, bool IRR = false>
+template <int ALGO, int TT, int NPC, int INMODE = -1, int INES = -1, bool IRR = false, typename T = float>
 int launch_resident_vq(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
-    auto kern = resident_vq<ALGO, 6, IRR ? 8 : 3, TT, NPC, INMODE, INES, IRR>;
+    auto kern = resident_vq<ALGO, 6, IRR ? 8 : 3, TT, NPC, INMODE, INES, IRR, T>;
     int per_sm = 1;
     int rc = resident_occupancy(h, kern, lc.threads, lc.smem, &per_sm);
     if (rc) return rc;
@@ -742,7 +742,9 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
         ring = (int)std::min<size_t>(kResRingMax, (budget - state) / stride);
     // regular codes, two-CTA geometry, float32, rows the bulk copy can stage, no separate hard input: the kernel with the
     // frame hand-over fused into its variable phase (LDPC_RESIDENT_VP=1 keeps resident_vp, for A/B runs)
-    const bool use_vq = ((r.vp && !r.vp_big && r.regular36) || r.vx) && dtype == LDPC_F32 && ring >= 2 && in.y_hard == nullptr &&
+    // (float64 min-sum runs the same kernel on double2 cells; float64 ROWS leave room for one ring entry only, which is
+    // enough as long as one frame leaves per iteration - a second one waits for the next variable phase)
+    const bool use_vq = ((r.vp && !r.vp_big && r.regular36) || r.vx) && ring >= (dtype == LDPC_F64 ? 1 : 2) && in.y_hard == nullptr &&
                         getenv("LDPC_RESIDENT_VP") == nullptr;
     if (use_vq) ring = std::min(ring, kVqRing);
     rp.ring = ring;
@@ -758,7 +760,15 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
     CUDA_TRY(h, cudaMemsetAsync(rp.counter, 0, sizeof(int), s));
     ProfEvent *pe = prof_begin(h, 0, s);
     int rc;
-    if (dtype == LDPC_F64) {                                        // resident_eligible: min-sum, r.vp, two CTAs per SM
+    if (dtype == LDPC_F64 && use_vq) {                              // float64 min-sum with the fused hand-over
+        const bool ens = lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200;
+        if (r.vx) rc = ens ? launch_resident_vq<ALGO_MSA, 320, 1200, -1, -1, true, double>(h, rp, lc, max_grid, s)
+                           : launch_resident_vq<ALGO_MSA, 0, 0, -1, -1, true, double>(h, rp, lc, max_grid, s);
+        else if (ens && rp.in_mode == IN_BIAWGN && rp.in_es == 8) rc = launch_resident_vq<ALGO_MSA, 320, 1200, IN_BIAWGN, 8, false, double>(h, rp, lc, max_grid, s);
+        else if (ens && rp.in_mode == IN_BIAWGN && rp.in_es == 4) rc = launch_resident_vq<ALGO_MSA, 320, 1200, IN_BIAWGN, 4, false, double>(h, rp, lc, max_grid, s);
+        else rc = ens ? launch_resident_vq<ALGO_MSA, 320, 1200, -1, -1, false, double>(h, rp, lc, max_grid, s)
+                      : launch_resident_vq<ALGO_MSA, 0, 0, -1, -1, false, double>(h, rp, lc, max_grid, s);
+    } else if (dtype == LDPC_F64) {                                 // resident_eligible: min-sum, r.vp, two CTAs per SM
         const bool ens = lc.threads == 320 && r.np == 1200 && r.mp == 600 && t.n == 1200;
         if (r.vx) rc = ens ? launch_resident_vd<320, 1200, true>(h, rp, lc, max_grid, s) : launch_resident_vd<0, 0, true>(h, rp, lc, max_grid, s);
         else rc = ens ? launch_resident_vd<320, 1200, false>(h, rp, lc, max_grid, s) : launch_resident_vd<0, 0, false>(h, rp, lc, max_grid, s);

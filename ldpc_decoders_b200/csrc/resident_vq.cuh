@@ -22,38 +22,76 @@
 // Handles: regular codes on resident_vp's tables in the two-CTA geometry, priors / BSC / BIAWGN input of any row type
 // the bulk copy can stage (16-byte aligned rows), no separate hard input (ldpc_decode with y_hard keeps resident_vp).
 #pragma once
+#include "resident_vd.cuh"
 #include "resident_vp.cuh"
 
 namespace ldpc {
 
 constexpr int kVqRing = 3;
 
+// The scalar type of the messages: float (4 frames per 16-byte cell) or double (2 frames per cell, the reference's own
+// arithmetic — min-sum only, resident_vd's node rule).  A cell is a cell: layout, tables and placement do not change.
+template <typename T> struct VqType;
+template <> struct VqType<float> {
+    using Cell = float4;
+    static constexpr int F = 4;
+    static __device__ __forceinline__ uint32_t signword(float v) { return f32_bits(v); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+};
+template <> struct VqType<double> {
+    using Cell = double2;
+    static constexpr int F = 2;
+    static __device__ __forceinline__ uint32_t signword(double v) { return f64_hi(v); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+};
+template <typename C, typename T> __device__ __forceinline__ T &lane_of(C &c, int j) { return (&c.x)[j]; }
+
 // One received value -> prior.  INMODE / INES >= 0: the input mode and element size are compile-time (the headline
 // BIAWGN float32 rows and BSC bytes get their own instances); -1: read them from the parameters (res_llr's branches).
-template <int INMODE, int INES>
-__device__ __forceinline__ float vq_llr(const unsigned char *row, int v, int in_mode, int in_es, double param, double inv_param)
+template <typename T, int INMODE, int INES>
+__device__ __forceinline__ T vq_llr(const unsigned char *row, int v, int in_mode, int in_es, double param, double inv_param)
 {
     uint32_t hbit;
-    if (INMODE < 0) return res_llr(row, v, in_mode, in_es, param, inv_param, &hbit);
-    return res_llr(row, v, INMODE, INES, param, inv_param, &hbit);
+    if (sizeof(T) == 8) {                                                // float64: the reference's expression with its division
+        if (INMODE < 0) return (T)vd_llr(row, v, in_mode, in_es, param, &hbit);
+        return (T)vd_llr(row, v, INMODE, INES, param, &hbit);
+    }
+    if (INMODE < 0) return (T)res_llr(row, v, in_mode, in_es, param, inv_param, &hbit);
+    return (T)res_llr(row, v, INMODE, INES, param, inv_param, &hbit);
+}
+
+// The check rule at the message type: float32 min-sum / sum-product (ldpc_math.cuh), float64 min-sum (resident_vd.cuh).
+template <int ALGO, int DC> __device__ __forceinline__ void vq_check(const float (&a)[DC], float (&o)[DC], float sat)
+{
+    if (ALGO == ALGO_MSA) cn_msa_lean<DC>(a, o);
+    else cn_spa_sc<DC>(a, DC, o, sat);
+}
+template <int ALGO, int DC> __device__ __forceinline__ void vq_check(const double (&a)[DC], double (&o)[DC], float)
+{
+    cn_msa_lean_f64<DC>(a, o);
 }
 
 // INMODE / INES: see vq_llr.  IRR: the irregular instance of resident_vp (check degrees 2..DC <= 6, variable degrees
 // 0..8, holes; one index word per edge, planes are prefixes of the positions, short checks padded with +inf cells).
-template <int ALGO, int DC, int DV, int TT, int NPC, int INMODE = -1, int INES = -1, bool IRR = false>
+template <int ALGO, int DC, int DV, int TT, int NPC, int INMODE = -1, int INES = -1, bool IRR = false, typename TS = float>
 __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
 {
     static_assert(DC >= 2 && DC <= 8 && DV >= 1 && (IRR ? (DV <= 8 && DC <= 6) : DV <= 3), "see resident_vp");
-    constexpr int F = 4, CH = IRR ? DC : (DC + 1) / 2, VNP = kResVnPasses;
-    constexpr uint32_t ALL = 0xFu;
+    static_assert(sizeof(TS) == 4 || ALGO == ALGO_MSA, "float64 on chip is min-sum only");
+    using VT = VqType<TS>;
+    using Cell = typename VT::Cell;
+    constexpr int F = VT::F, CH = IRR ? DC : (DC + 1) / 2, VNP = kResVnPasses;
+    constexpr uint32_t ALL = (1u << F) - 1u;
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int MPC = IRR ? NPC / 2 : NPC * DV / DC;
     const int np = NPC ? NPC : p.n, mp = NPC ? MPC : p.m;
     const uint32_t S = (uint32_t)np * 16u;
     const VpSmem L = IRR ? vx_smem_layout(np, p.plane_cells, p.ring, p.stage_stride) : vp_smem_layout(np, DV, p.ring, p.stage_stride, true);
-    float4 *marg = reinterpret_cast<float4 *>(smem + L.marg);
-    float4 *planes = reinterpret_cast<float4 *>(smem + L.planes);
-    float4 *prior = reinterpret_cast<float4 *>(smem + L.prior);
+    Cell *marg = reinterpret_cast<Cell *>(smem + L.marg);
+    Cell *planes = reinterpret_cast<Cell *>(smem + L.planes);
+    Cell *prior = reinterpret_cast<Cell *>(smem + L.prior);
     unsigned char *stage = smem + L.stage;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
     uint16_t *imap = reinterpret_cast<uint16_t *>(smem + L.imap);       // variable at a position
@@ -93,17 +131,21 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
         const uint32_t w = cw[ps][k >> 1];
         return (k & 1) ? vp_off1(w) : vp_off0(w);
     };
-    float4 old[kResCnPasses][DC];                                        // c2v of the thread's own checks
+    Cell old[kResCnPasses][DC];                                          // c2v of the thread's own checks
 #pragma unroll
     for (int ps = 0; ps < kResCnPasses; ++ps)
 #pragma unroll
-        for (int k = 0; k < DC; ++k) old[ps][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < DC; ++k)
+#pragma unroll
+            for (int j = 0; j < F; ++j) (&old[ps][k].x)[j] = (TS)0;
 
     for (int i = tid; i < np; i += T) imap[i] = p.vinvmap[i];
     if (IRR) {
         // cells nobody writes must read as +0.0 (short planes, holes), the padding cells behind marg as +inf
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f), i4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-        for (int i = tid; i < (int)(L.stage / 16); i += T) reinterpret_cast<float4 *>(smem)[i] = z4;
+        Cell i4;
+#pragma unroll
+        for (int j = 0; j < F; ++j) (&i4.x)[j] = (TS)INFINITY;
+        for (int i = tid; i < (int)(L.stage / 16); i += T) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         if (tid < 8) marg[np + tid] = i4;
     }
@@ -127,7 +169,9 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
 
     // CTA-uniform slot state, identical in every thread
     uint32_t active = 0u, fresh = 0u;
-    int it_s[F] = {0, 0, 0, 0}, fr_s[F] = {0, 0, 0, 0};
+    int it_s[F], fr_s[F];
+#pragma unroll
+    for (int j = 0; j < F; ++j) { it_s[j] = 0; fr_s[j] = 0; }
     int head_e = 0;                                                      // ring entry the next frame comes from ...
     uint32_t head_par = 0u;                                              // ... and the phase parity of its mbarrier
     bool more = true;                                                    // the ring may still deliver frames
@@ -141,41 +185,42 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
 #pragma unroll
                 for (int ps = 0; ps < kResCnPasses; ++ps)
 #pragma unroll
-                    for (int k = 0; k < DC; ++k) {
-                        if (fresh & 1u) old[ps][k].x = 0.f;
-                        if (fresh & 2u) old[ps][k].y = 0.f;
-                        if (fresh & 4u) old[ps][k].z = 0.f;
-                        if (fresh & 8u) old[ps][k].w = 0.f;
-                    }
+                    for (int k = 0; k < DC; ++k)
+#pragma unroll
+                        for (int j = 0; j < F; ++j)
+                            if ((fresh >> j) & 1u) (&old[ps][k].x)[j] = (TS)0;
             }
 #pragma unroll
             for (int ps = 0; ps < kResCnPasses; ++ps) {
                 if (tid + ps * T < mp) {
-                    float4 mg[DC];
+                    Cell mg[DC];
 #pragma unroll
-                    for (int k = 0; k < DC; ++k) mg[k] = *reinterpret_cast<const float4 *>(smem + goff(ps, k));
-                    uint32_t sx[4] = {0u, 0u, 0u, 0u};
+                    for (int k = 0; k < DC; ++k) mg[k] = *reinterpret_cast<const Cell *>(smem + goff(ps, k));
+                    uint32_t sx[F];
+#pragma unroll
+                    for (int j = 0; j < F; ++j) sx[j] = 0u;
 #pragma unroll
                     for (int k = 0; k < DC; ++k) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float mv = (&mg[k].x)[j];
-                            sx[j] ^= f32_bits(mv);                       // sign bit == (marg < 0), see resident_vp
-                            (&mg[k].x)[j] = __fsub_rn(mv, (&old[ps][k].x)[j]);       // v2c = marg - c2v_old (bpa.py:37)
+                        for (int j = 0; j < F; ++j) {
+                            const TS mv = (&mg[k].x)[j];
+                            sx[j] ^= VT::signword(mv);                   // sign bit == (marg < 0), see resident_vp
+                            (&mg[k].x)[j] = VT::sub(mv, (&old[ps][k].x)[j]);         // v2c = marg - c2v_old (bpa.py:37)
                         }
                     }
-                    const uint32_t syn = (sx[0] >> 31) | ((sx[1] >> 31) << 1) | ((sx[2] >> 31) << 2) | ((sx[3] >> 31) << 3);
+                    uint32_t syn = 0u;
+#pragma unroll
+                    for (int j = 0; j < F; ++j) syn |= (sx[j] >> 31) << j;
                     // irregular, sum-product: a padding edge reads +inf (neutral), its own output is forced to 0 (resident_vp)
                     const int dcr = (IRR && ALGO != ALGO_MSA) ? (int)(cw[ps][0] & 15u) : DC;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float a[DC], o[DC];
+                    for (int j = 0; j < F; ++j) {
+                        TS a[DC], o[DC];
 #pragma unroll
                         for (int k = 0; k < DC; ++k) a[k] = (&mg[k].x)[j];
-                        if (ALGO == ALGO_MSA) cn_msa_lean<DC>(a, o);
-                        else cn_spa_sc<DC>(a, DC, o, p.sat_llr);
+                        vq_check<ALGO, DC>(a, o, p.sat_llr);
 #pragma unroll
-                        for (int k = 0; k < DC; ++k) (&old[ps][k].x)[j] = (IRR && ALGO != ALGO_MSA && k >= 2 && k >= dcr) ? 0.f : o[k];
+                        for (int k = 0; k < DC; ++k) (&old[ps][k].x)[j] = (IRR && ALGO != ALGO_MSA && k >= 2 && k >= dcr) ? (TS)0 : o[k];
                     }
 #pragma unroll
                     for (int k = 0; k < DC; ++k) {
@@ -186,7 +231,7 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
                             const uint32_t w = cw[ps][k >> 1];
                             coff = (k & 1) ? vp_sl1x4(w) * (S >> 2) + vp_off1(w) : vp_sl0(w) * S + vp_off0(w);
                         }
-                        *reinterpret_cast<float4 *>(smem + coff) = old[ps][k];
+                        *reinterpret_cast<Cell *>(smem + coff) = old[ps][k];
                     }
                     unsat |= syn;
                 }
@@ -243,40 +288,42 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
         if (active == 0u && inst == 0u) break;                           // nothing running, nothing left to start
 
         // ======================================= variable-node phase =======================================
-        auto vn_item = [&](int item, float4 &pr, float4 &mgv) {
+        auto vn_item = [&](int item, Cell &pr, Cell &mgv) {
+            Cell sm;
             if (IRR) {
                 // plane k = a prefix of the positions (descending degree): ascending edge order, bpa.py:35
-                float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (item < p.pcnt[0]) sm = *reinterpret_cast<const float4 *>(smem + p.pbase[0] + (size_t)item * 16);
+#pragma unroll
+                for (int j = 0; j < F; ++j) (&sm.x)[j] = (TS)0;
+                if (item < p.pcnt[0]) sm = *reinterpret_cast<const Cell *>(smem + p.pbase[0] + (size_t)item * 16);
 #pragma unroll
                 for (int k = 1; k < DV; ++k) {
                     if (item >= p.pcnt[k]) break;
-                    const float4 c = *reinterpret_cast<const float4 *>(smem + p.pbase[k] + (size_t)item * 16);
-                    sm.x = __fadd_rn(sm.x, c.x); sm.y = __fadd_rn(sm.y, c.y);
-                    sm.z = __fadd_rn(sm.z, c.z); sm.w = __fadd_rn(sm.w, c.w);
-                }
-                pr = prior[item];
-                mgv = make_float4(__fadd_rn(pr.x, sm.x), __fadd_rn(pr.y, sm.y), __fadd_rn(pr.z, sm.z), __fadd_rn(pr.w, sm.w));
-                return;
-            }
-            float4 c[IRR ? 1 : DV];
+                    const Cell c = *reinterpret_cast<const Cell *>(smem + p.pbase[k] + (size_t)item * 16);
 #pragma unroll
-            for (int k = 0; k < (IRR ? 1 : DV); ++k) c[k] = planes[(size_t)k * np + item];
+                    for (int j = 0; j < F; ++j) (&sm.x)[j] = VT::add((&sm.x)[j], (&c.x)[j]);
+                }
+            } else {
+                Cell c[DV];
+#pragma unroll
+                for (int k = 0; k < DV; ++k) c[k] = planes[(size_t)k * np + item];
+#pragma unroll
+                for (int j = 0; j < F; ++j) {
+                    TS s = (&c[0].x)[j];
+#pragma unroll
+                    for (int k = 1; k < DV; ++k) s = VT::add(s, (&c[k].x)[j]);
+                    (&sm.x)[j] = s;
+                }
+            }
             pr = prior[item];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float s = (&c[0].x)[j];
-#pragma unroll
-                for (int k = 1; k < (IRR ? 1 : DV); ++k) s = __fadd_rn(s, (&c[k].x)[j]);
-                (&mgv.x)[j] = __fadd_rn((&pr.x)[j], s);                  // bpa.py:35
-            }
+            for (int j = 0; j < F; ++j) (&mgv.x)[j] = VT::add((&pr.x)[j], (&sm.x)[j]);      // bpa.py:35
         };
         if ((leaving | inst) == 0u) {                                    // the common iteration: nothing but the sums
 #pragma unroll
             for (int ps = 0; ps < VNP; ++ps) {
                 const int item = tid + ps * T;
                 if (item < np) {
-                    float4 pr, mgv;
+                    Cell pr, mgv;
                     vn_item(item, pr, mgv);
                     marg[item] = mgv;
                 }
@@ -293,7 +340,7 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
             for (int ps = 0; ps < VNP; ++ps) {
                 const int item = tid + ps * T;
                 if (item >= np) break;
-                float4 pr, mgv;
+                Cell pr, mgv;
                 vn_item(item, pr, mgv);
                 const uint32_t v = imap[item];
                 if (IRR && v == 0xffffu) {                               // a position without a variable: nothing leaves, nothing moves in
@@ -301,19 +348,19 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
                     continue;
                 }
                 if (decoded != 0u) {                                     // word = the marginal this frame's last check phase saw
-                    const float4 om = marg[item];
+                    const Cell om = marg[item];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if ((decoded >> j) & 1u) dst[j][v] = (uint8_t)(f32_bits((&om.x)[j]) >> 31);
+                    for (int j = 0; j < F; ++j)
+                        if ((decoded >> j) & 1u) dst[j][v] = (uint8_t)(VT::signword((&om.x)[j]) >> 31);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((maxed >> j) & 1u) dst[j][v] = (uint8_t)(f32_bits((&mgv.x)[j]) >> 31);
+                for (int j = 0; j < F; ++j)
+                    if ((maxed >> j) & 1u) dst[j][v] = (uint8_t)(VT::signword((&mgv.x)[j]) >> 31);
                 if (inst != 0u) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < F; ++j)
                         if ((inst >> j) & 1u) {
-                            const float val = vq_llr<INMODE, INES>(row[j], (int)v, p.in_mode, p.in_es, p.param, p.inv_param);
+                            const TS val = vq_llr<TS, INMODE, INES>(row[j], (int)v, p.in_mode, p.in_es, p.param, p.inv_param);
                             (&mgv.x)[j] = val;
                             (&pr.x)[j] = val;
                         }
