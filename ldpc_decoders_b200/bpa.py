@@ -69,6 +69,9 @@ class BPA:
         if Y.shape != priors.shape or Y.ndim != 2 or Y.shape[1] != self.tables.n:
             raise ValueError("Y and priors must both be [B, n]")
         dtype = _lib.F32 if priors.dtype == np.float32 else _lib.F64
+        if Y.shape[0] == 0:                                 # an empty batch decodes to empty results
+            empty = (np.empty((0, self.tables.n), np.int64), np.empty(0, np.int32), np.empty(0, np.uint8))
+            return empty if return_reason else empty[:2]
         hard = np.issubdtype(Y.dtype, np.integer) or Y.dtype == np.bool_
         import torch
         dev = self.engine._dev()

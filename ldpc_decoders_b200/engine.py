@@ -343,6 +343,8 @@ class Engine:
             if y.dtype not in _NP2DT:
                 raise TypeError("input must be float16, float32 or float64")
             y_dtype = _NP2DT[y.dtype]
+        if B == 0:                                          # an empty batch decodes to empty results (the C ABI wants B > 0)
+            return (np.empty((0, prow if packed_out else t.n), np.uint8), np.empty(0, np.int32), np.empty(0, np.uint8))
         if packed_out:
             flags |= _lib.OUT_PACKED
         xshape = (B, prow) if packed_out else (B, t.n)

@@ -130,6 +130,20 @@ def test_bec_config2_1e5_frames_bit_exact(mods, cw, mi):
     assert total >= 100000
 
 
+def test_empty_batches_decode_to_empty_results(mods):
+    tab = tables(mods, "7_4_hamming")
+    n = tab.n
+    x, it = mods["biawgn"].MSA(2.0, tab, max_iter=10).decode_batch(np.zeros((0, n)))
+    assert x.shape == (0, n) and it.shape == (0,)
+    x, it, rs = mods["bsc"].SPA(.1, tab, max_iter=10, dtype=np.float32).decode_batch(np.zeros((0, n), np.uint8), return_reason=True)
+    assert x.shape == (0, n) and it.shape == (0,) and rs.shape == (0,)
+    x, it = mods["bec"].SPA(.3, tab, max_iter=10).decode_batch(np.zeros((0, n), np.uint8))
+    assert x.shape == (0, n) and it.shape == (0,)
+    from ldpc_decoders_b200 import bpa
+    x, it = bpa.MSA(tab, max_iter=10).decode_batch(np.zeros((0, n)), np.zeros((0, n)))
+    assert x.shape == (0, n) and it.shape == (0,)
+
+
 def test_frames_per_call_limit_is_reported(mods):
     lib = mods["lib"]
     tab = tables(mods, "7_4_hamming")
