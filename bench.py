@@ -283,7 +283,7 @@ def extra_workloads(torch, lib, eng_mod, Tables, peak):
         frac = (cn_b + vn_b) * 3 / (ms / 1e3) / 1e9 / peak
         rec = {"workload": label, "value": fps, "unit": UNIT, "mean_iters": float(iters.mean()),
                "edge_updates_per_s": 2 * tab.E * float(iters.sum()) * 3 / (ms / 1e3),
-               "path": ("on-chip (%s)" % ("resident_vd" if dtype == lib.F64 else eng.resident_kernel)) if on_chip else "streaming"}
+               "path": ("on-chip (%s)" % ("resident_vq<double> / resident_vd" if dtype == lib.F64 else eng.resident_kernel)) if on_chip else "streaming"}
         # streaming: fraction of the measured HBM peak the whole step reaches; on-chip: the same algorithmic bytes never
         # touch HBM, so the figure is an EFFECTIVE one (see roofline.note)
         rec["effective_hbm_frac" if on_chip else "step_hbm_frac"] = frac
@@ -535,15 +535,16 @@ def main():
     # ---- the reference's own arithmetic: float64 messages (bpa.py computes in the dtype of its priors, and its front
     # ends produce float64), float64 received rows; same code / SNR / frames, min-sum
     y64 = y.double()
+    f64_name = "resident_vq<double>" if res_name == "resident_vq" else "resident_vd"     # the float64 instance of the same kernel
     f64 = measure(args.flags, y=y64, dtype=lib.F64)
     f64_res = f64["prof"]["vn_launches"] == 0
     msa_f64 = {"workload": "same code / SNR / frames, min-sum with float64 messages and float64 rows (the reference's arithmetic, bit-exact with the float64 oracle)",
                "value": total_frames / (f64["ms"] / 1e3), "unit": UNIT, "ms_per_step": f64["ms"] / args.steps, "dtype": "f64",
                "mean_iters": float(f64["iters"].mean()), "gpu_launches": int(f64["launches"]),
                "edge_updates_per_s": 2 * tab.E * sum_over_ranks(float(f64["iters"].sum())) * args.steps / (f64["ms"] / 1e3),
-               "path": "on-chip (resident_vd)" if f64_res else "streaming"}
+               "path": ("on-chip (%s)" % f64_name) if f64_res else "streaming"}
     if f64_res:
-        msa_f64["roofline"], msa_f64["effective_hbm"] = resident_roofline(f64, "resident_vd", 8, "Two frames per 16-byte cell; DSETP/select minima.")
+        msa_f64["roofline"], msa_f64["effective_hbm"] = resident_roofline(f64, f64_name, 8, "Two frames per 16-byte cell; DSETP/select minima.")
     else:
         msa_f64["roofline"] = streaming_roofline(f64, 8)
 
