@@ -671,6 +671,7 @@ def main():
             Y64[...] = Yh.astype(np.float64)
             e2e_variants.append(e2e_leg("float64 rows in, float64 messages (the reference's own types end to end), MSA f64",
                                         lib.CH_BIAWGN, lib.MSA, lib.F64, nv, Y64, ref=(f64["iters"], f64["x_hat"])))
+            msa_f64["e2e"] = {k: e2e_variants[-1][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step", "h2d_GBps_by_rank")}
             del Y16, Y64
             pflip = 0.05
             gb = torch.Generator(device="cuda").manual_seed(5 + rank)

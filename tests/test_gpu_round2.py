@@ -412,3 +412,18 @@ def test_monte_carlo_on_two_gpus_under_nccl_equals_one_gpu(mods, tmp_path):
             assert one[key] == two[key], (extra, key)
         if "--frames" in extra:
             assert all(v == 100000 for v in two["tot"].values())
+        if "host" in extra:
+            # ... and the numpy-noise run equals the oracle-driven SEQUENTIAL loop of the reference (main.py:37-45): one
+            # frame at a time, the same legacy RNG stream, stop at the min_wec-th word error
+            from ldpc_decoders_b200 import dist, sim
+            og = O.Graph(*G.code_tables("512_3_6_rand_ldpc_1"))
+            x = np.ones(og.n, np.int64)
+            for snr in (1.5, 2.5):
+                def decode_batch(Y, snr=snr):
+                    r = O.bp_decode(og, O.MSA, O.llr_biawgn(snr, Y).astype(np.float32), max_iter=10)
+                    return r["x_hat"], r["iters"]
+                std = np.sqrt(10 ** (-snr / 10))
+                np.random.seed(5)
+                ref = sim.run_param(decode_batch, lambda X: (2 * X - 1) + np.random.normal(0, std, X.shape), x, dist.Comm("gloo"), 1, 12)
+                key = str(float(snr))
+                assert (two["tot"][key], two["wec"][key], two["bec"][key]) == (ref["tot"], ref["wec"], ref["bec"]), snr
