@@ -169,9 +169,14 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
 
     // CTA-uniform slot state, identical in every thread
     uint32_t active = 0u, fresh = 0u;
-    int it_s[F], fr_s[F];
+    // A slot is in `run` in every round between moving in and leaving, so its iteration count is the number of rounds
+    // since then: start_s = the round at which the frame moved in, gi = the current round.  next_max = the first round at
+    // which some active slot reaches the iteration bound: until then, and while every syndrome stays non-zero, a round
+    // needs no per-slot book-keeping at all.
+    int start_s[F], fr_s[F];
 #pragma unroll
-    for (int j = 0; j < F; ++j) { it_s[j] = 0; fr_s[j] = 0; }
+    for (int j = 0; j < F; ++j) { start_s[j] = 0; fr_s[j] = 0; }
+    int gi = 0, next_max = 0x7fffffff;
     int head_e = 0;                                                      // ring entry the next frame comes from ...
     uint32_t head_par = 0u;                                              // ... and the phase parity of its mbarrier
     bool more = true;                                                    // the ring may still deliver frames
@@ -241,53 +246,6 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
         }
         __syncthreads();
 
-        // ======================================= slot decisions (every thread, uniform) =======================================
-        uint32_t us = __reduce_or_sync(kFull, s_unsat[par]);
-        if (!have_hard) us |= fresh;                                     // a new frame's marg is its prior: no syndrome test yet
-        const uint32_t decoded = active & ~us;                           // leaves with its iteration count unchanged (bpa.py:29)
-        const uint32_t run = active & us;
-        uint32_t maxed = 0u;
-#pragma unroll
-        for (int s = 0; s < F; ++s)
-            if ((run >> s) & 1u) {
-                it_s[s] += 1;                                            // bpa.py:63
-                if (it_s[s] >= p.limit) maxed |= 1u << s;                // bpa.py:28 at the top of the next round
-            }
-        if (tid == 0) s_unsat[par ^ 1] = 0u;
-        const uint32_t leaving = decoded | maxed;
-        if (tid < F && ((leaving >> tid) & 1u)) {
-            int g = fr_s[0], itv = it_s[0];
-#pragma unroll
-            for (int s = 1; s < F; ++s)
-                if (tid == s) { g = fr_s[s]; itv = it_s[s]; }
-            p.iters[g] = itv;
-            if (p.reason != nullptr) p.reason[g] = (uint8_t)(((decoded >> tid) & 1u) ? LDPC_REASON_DECODED : p.bound_reason);
-        }
-        // free slots take the next landed rows, in slot order
-        uint32_t inst = 0u;
-        int ent[F], nfr[F];                                              // only read under the matching bit of `inst`
-        const uint32_t freem = (~active | leaving) & ALL;
-        if (freem != 0u && more) {
-            int taken = 0;
-#pragma unroll
-            for (int s = 0; s < F; ++s) {
-                if (((freem >> s) & 1u) && more && taken < R) {
-                    const int g = r_frame[head_e];
-                    if (g < 0) {
-                        more = false;
-                    } else {
-                        mbar_wait(&bars[head_e], head_par);
-                        ent[s] = head_e; nfr[s] = g;
-                        inst |= 1u << s;
-                        ++taken;
-                        if (++head_e == R) { head_e = 0; head_par ^= 1u; }
-                    }
-                }
-            }
-        }
-        if (active == 0u && inst == 0u) break;                           // nothing running, nothing left to start
-
-        // ======================================= variable-node phase =======================================
         auto vn_item = [&](int item, Cell &pr, Cell &mgv) {
             Cell sm;
             if (IRR) {
@@ -318,6 +276,68 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
 #pragma unroll
             for (int j = 0; j < F; ++j) (&mgv.x)[j] = VT::add((&pr.x)[j], (&sm.x)[j]);      // bpa.py:35
         };
+        // ======================================= slot decisions (every thread, uniform) =======================================
+        ++gi;
+        uint32_t us = __reduce_or_sync(kFull, s_unsat[par]);
+        if (!have_hard) us |= fresh;                                     // a new frame's marg is its prior: no syndrome test yet
+        if (tid == 0) s_unsat[par ^ 1] = 0u;
+        if (active != 0u && (active & ~us) == 0u && gi < next_max && (active == ALL || !more)) {
+            // ---- the quiet round (two out of three): nobody decoded, nobody at the bound, no free slot to fill
+#pragma unroll
+            for (int ps = 0; ps < VNP; ++ps) {
+                const int item = tid + ps * T;
+                if (item < np) {
+                    Cell pr, mgv;
+                    vn_item(item, pr, mgv);
+                    marg[item] = mgv;
+                }
+            }
+            __syncthreads();
+            fresh = 0u;
+            par ^= 1;
+            continue;
+        }
+        const uint32_t decoded = active & ~us;                           // leaves with its iteration count unchanged (bpa.py:29)
+        const uint32_t run = active & us;
+        uint32_t maxed = 0u;
+#pragma unroll
+        for (int s = 0; s < F; ++s)
+            if (((run >> s) & 1u) && gi - start_s[s] >= p.limit) maxed |= 1u << s;   // bpa.py:63, then bpa.py:28 at the top of the next round
+        const uint32_t leaving = decoded | maxed;
+        if (tid < F && ((leaving >> tid) & 1u)) {
+            int g = fr_s[0], st = start_s[0];
+#pragma unroll
+            for (int s = 1; s < F; ++s)
+                if (tid == s) { g = fr_s[s]; st = start_s[s]; }
+            const bool dec = ((decoded >> tid) & 1u) != 0u;
+            p.iters[g] = gi - st - (dec ? 1 : 0);                        // a decoded frame did not run this round
+            if (p.reason != nullptr) p.reason[g] = (uint8_t)(dec ? LDPC_REASON_DECODED : p.bound_reason);
+        }
+        // free slots take the next landed rows, in slot order
+        uint32_t inst = 0u;
+        int ent[F], nfr[F];                                              // only read under the matching bit of `inst`
+        const uint32_t freem = (~active | leaving) & ALL;
+        if (freem != 0u && more) {
+            int taken = 0;
+#pragma unroll
+            for (int s = 0; s < F; ++s) {
+                if (((freem >> s) & 1u) && more && taken < R) {
+                    const int g = r_frame[head_e];
+                    if (g < 0) {
+                        more = false;
+                    } else {
+                        mbar_wait(&bars[head_e], head_par);
+                        ent[s] = head_e; nfr[s] = g;
+                        inst |= 1u << s;
+                        ++taken;
+                        if (++head_e == R) { head_e = 0; head_par ^= 1u; }
+                    }
+                }
+            }
+        }
+        if (active == 0u && inst == 0u) break;                           // nothing running, nothing left to start
+
+        // ======================================= variable-node phase =======================================
         if ((leaving | inst) == 0u) {                                    // the common iteration: nothing but the sums
 #pragma unroll
             for (int ps = 0; ps < VNP; ++ps) {
@@ -377,9 +397,13 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
         }
 #pragma unroll
         for (int s = 0; s < F; ++s)
-            if ((inst >> s) & 1u) { fr_s[s] = nfr[s]; it_s[s] = 0; }
+            if ((inst >> s) & 1u) { fr_s[s] = nfr[s]; start_s[s] = gi; }
         active = (run & ~maxed) | inst;
         fresh = inst;
+        next_max = 0x7fffffff;
+#pragma unroll
+        for (int s = 0; s < F; ++s)
+            if ((active >> s) & 1u) next_max = min(next_max, start_s[s] + p.limit);
         par ^= 1;
     }
 }
