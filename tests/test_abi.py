@@ -87,3 +87,30 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"(from|import)\s+oracle|libldpc_oracle|oracle[/.]\w", src), f
+
+
+def test_bit_packed_row_helpers_round_trip(lib):
+    """Host-side packing for LDPC_IN_PACKED / LDPC_OUT_PACKED: the layout ldpc_packed_row_bytes promises (rows padded to
+    16 bytes, bit v = bit (v & 7) of byte (v >> 3)), value plane then erasure plane for BEC symbols."""
+    from ldpc_decoders_b200 import engine as E
+    rng = np.random.RandomState(0)
+    for n in (1, 7, 8, 9, 127, 128, 129, 1200, 2640):
+        assert E.packed_row_bytes(n) == lib.ldpc_packed_row_bytes(n) and E.packed_row_bytes(n) % 16 == 0
+        assert E.packed_row_bytes(n) * 8 >= n
+        Y = rng.randint(0, 2, size=(5, n)).astype(np.uint8)
+        P = E.pack_bits(Y)
+        assert P.shape == (5, E.packed_row_bytes(n)) and (E.unpack_bits(P, n) == Y).all()
+        for v in (0, n // 2, n - 1):
+            assert (((P[:, v >> 3] >> (v & 7)) & 1) == Y[:, v]).all()
+        S = rng.randint(0, 3, size=(5, n)).astype(np.uint8)
+        Q = E.pack_symbols(S)
+        s = E.packed_row_bytes(n)
+        assert Q.shape == (5, 2 * s) and (E.unpack_symbols(Q, n) == S).all()
+        assert (E.unpack_bits(Q[:, :s], n) == (S == 1)).all() and (E.unpack_bits(Q[:, s:], n) == (S == 2)).all()
+    assert lib.ldpc_packed_row_bytes(0) == 0
+
+
+def test_monte_carlo_entry_points_validate_arguments(lib):
+    assert lib.ldpc_mc_scratch_bytes(None, 2, 0, 0, 128) == 0
+    assert lib.ldpc_count_accumulate(None, None, None, None, 1, None, None, 0, None) == -1
+    assert lib.ldpc_mc_round(None, 2, 0, 0, 1.0, 1.0, None, 0, 0, 1, 10, 0, None, 0, None, 0, 0, None) == -1
