@@ -647,10 +647,10 @@ int launch_resident_vp(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_gri
     return LDPC_OK;
 }
 
-template <int ALGO, int TT, int NPC, int INMODE = -1, int INES = -1, bool IRR = false, typename T = float>
+template <int ALGO, int TT, int NPC, int INMODE = -1, int INES = -1, bool IRR = false, typename T = float, int MAXT = 320>
 int launch_resident_vq(ldpc_t *h, const ResParams &rp, ResLaunch lc, int max_grid, cudaStream_t s)
 {
-    auto kern = resident_vq<ALGO, 6, IRR ? 8 : 3, TT, NPC, INMODE, INES, IRR, T>;
+    auto kern = resident_vq<ALGO, 6, IRR ? 8 : 3, TT, NPC, INMODE, INES, IRR, T, MAXT>;
     int per_sm = 1;
     int rc = resident_occupancy(h, kern, lc.threads, lc.smem, &per_sm);
     if (rc) return rc;
@@ -744,8 +744,9 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
     // frame hand-over fused into its variable phase (LDPC_RESIDENT_VP=1 keeps resident_vp, for A/B runs)
     // (float64 min-sum runs the same kernel on double2 cells; float64 ROWS leave room for one ring entry only, which is
     // enough as long as one frame leaves per iteration - a second one waits for the next variable phase)
-    const bool use_vq = ((r.vp && !r.vp_big && r.regular36) || r.vx) && ring >= (dtype == LDPC_F64 ? 1 : 2) && in.y_hard == nullptr &&
-                        getenv("LDPC_RESIDENT_VP") == nullptr;
+    // (the one-CTA-per-SM geometry of codes up to n ~ 2850 has room for one ring entry too)
+    const bool use_vq = ((r.vp && r.regular36 && (!r.vp_big || dtype == LDPC_F32)) || r.vx) &&
+                        ring >= ((dtype == LDPC_F64 || r.vp_big) ? 1 : 2) && in.y_hard == nullptr && getenv("LDPC_RESIDENT_VP") == nullptr;
     if (use_vq) ring = std::min(ring, kVqRing);
     rp.ring = ring;
     rp.stage_stride = (int)stride;
@@ -790,6 +791,9 @@ int decode_bp_resident(ldpc_t *h, int algo, int dtype, const InSpec &in, int B, 
         else
             rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 0, 0, true>(h, rp, lc, max_grid, s)
                                     : launch_resident_vp<ALGO_SPA_PHI, 0, 0, true>(h, rp, lc, max_grid, s);
+    } else if (r.vp_big && use_vq) {
+        rc = (algo == LDPC_MSA) ? launch_resident_vq<ALGO_MSA, 0, 0, -1, -1, false, float, kVpBigThreads>(h, rp, lc, max_grid, s)
+                                : launch_resident_vq<ALGO_SPA_PHI, 0, 0, -1, -1, false, float, kVpBigThreads>(h, rp, lc, max_grid, s);
     } else if (r.vp_big) {
         rc = (algo == LDPC_MSA) ? launch_resident_vp<ALGO_MSA, 0, 0, false, kVpBigThreads>(h, rp, lc, max_grid, s)
                                 : launch_resident_vp<ALGO_SPA_PHI, 0, 0, false, kVpBigThreads>(h, rp, lc, max_grid, s);

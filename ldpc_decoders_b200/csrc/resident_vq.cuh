@@ -75,26 +75,31 @@ template <int ALGO, int DC> __device__ __forceinline__ void vq_check(const doubl
 
 // INMODE / INES: see vq_llr.  IRR: the irregular instance of resident_vp (check degrees 2..DC <= 6, variable degrees
 // 0..8, holes; one index word per edge, planes are prefixes of the positions, short checks padded with +inf cells).
-template <int ALGO, int DC, int DV, int TT, int NPC, int INMODE = -1, int INES = -1, bool IRR = false, typename TS = float>
-__global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
+// MAXT: 320 = two CTAs per SM; kVpBigThreads = ONE CTA per SM for regular codes whose 4 frames need the whole shared memory
+// (n up to ~2850, the Margulis code: resident_vp's geometry — five variable passes, a third check pass whose c2v_old lives
+// in the planes, the position -> variable map in global memory, one ring entry).
+template <int ALGO, int DC, int DV, int TT, int NPC, int INMODE = -1, int INES = -1, bool IRR = false, typename TS = float, int MAXT = 320>
+__global__ void __launch_bounds__(MAXT, MAXT > 320 ? 1 : 2) resident_vq(const ResParams p)
 {
+    static_assert(MAXT == 320 || (MAXT == kVpBigThreads && !IRR && TT == 0 && NPC == 0 && sizeof(TS) == 4), "two geometries");
+    constexpr bool BIG = MAXT > 320;
     static_assert(DC >= 2 && DC <= 8 && DV >= 1 && (IRR ? (DV <= 8 && DC <= 6) : DV <= 3), "see resident_vp");
     static_assert(sizeof(TS) == 4 || ALGO == ALGO_MSA, "float64 on chip is min-sum only");
     using VT = VqType<TS>;
     using Cell = typename VT::Cell;
-    constexpr int F = VT::F, CH = IRR ? DC : (DC + 1) / 2, VNP = kResVnPasses;
+    constexpr int F = VT::F, CH = IRR ? DC : (DC + 1) / 2, VNP = BIG ? kVpBigVnPasses : kResVnPasses;
     constexpr uint32_t ALL = (1u << F) - 1u;
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int MPC = IRR ? NPC / 2 : NPC * DV / DC;
     const int np = NPC ? NPC : p.n, mp = NPC ? MPC : p.m;
     const uint32_t S = (uint32_t)np * 16u;
-    const VpSmem L = IRR ? vx_smem_layout(np, p.plane_cells, p.ring, p.stage_stride) : vp_smem_layout(np, DV, p.ring, p.stage_stride, true);
+    const VpSmem L = IRR ? vx_smem_layout(np, p.plane_cells, p.ring, p.stage_stride) : vp_smem_layout(np, DV, p.ring, p.stage_stride, !BIG);
     Cell *marg = reinterpret_cast<Cell *>(smem + L.marg);
     Cell *planes = reinterpret_cast<Cell *>(smem + L.planes);
     Cell *prior = reinterpret_cast<Cell *>(smem + L.prior);
     unsigned char *stage = smem + L.stage;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
-    uint16_t *imap = reinterpret_cast<uint16_t *>(smem + L.imap);       // variable at a position
+    const uint16_t *imap = BIG ? p.vinvmap : reinterpret_cast<const uint16_t *>(smem + L.imap);       // variable at a position
 
     __shared__ int r_frame[kVqRing];
     __shared__ uint32_t s_unsat[2];
@@ -139,7 +144,18 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
 #pragma unroll
             for (int j = 0; j < F; ++j) (&old[ps][k].x)[j] = (TS)0;
 
-    for (int i = tid; i < np; i += T) imap[i] = p.vinvmap[i];
+    if (!BIG)
+        for (int i = tid; i < np; i += T) reinterpret_cast<uint16_t *>(smem + L.imap)[i] = p.vinvmap[i];
+    // BIG: the check of the third pass (position tid + 2 T), its gather / scatter byte offsets straight from the table
+    const int ctail = tid + kResCnPasses * T;
+    auto tail_offsets = [&](uint32_t (&g)[DC], uint32_t (&sc)[DC]) {
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+            const uint32_t e = p.cw[(size_t)ctail * 8 + k];              // (position << 4) | (slot + 1)
+            g[k] = e & 0xfff0u;
+            sc[k] = (e & 3u) * S + g[k];
+        }
+    };
     if (IRR) {
         // cells nobody writes must read as +0.0 (short planes, holes), the padding cells behind marg as +inf
         Cell i4;
@@ -194,6 +210,15 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
 #pragma unroll
                         for (int j = 0; j < F; ++j)
                             if ((fresh >> j) & 1u) (&old[ps][k].x)[j] = (TS)0;
+                if (BIG && ctail < mp) {                                 // third-pass checks keep their c2v in the planes only
+                    uint32_t g[DC], sc[DC];
+                    tail_offsets(g, sc);
+#pragma unroll
+                    for (int k = 0; k < DC; ++k)
+#pragma unroll
+                        for (int j = 0; j < F; ++j)
+                            if ((fresh >> j) & 1u) reinterpret_cast<TS *>(smem + sc[k])[j] = (TS)0;
+                }
             }
 #pragma unroll
             for (int ps = 0; ps < kResCnPasses; ++ps) {
@@ -240,6 +265,40 @@ __global__ void __launch_bounds__(320, 2) resident_vq(const ResParams p)
                     }
                     unsat |= syn;
                 }
+            }
+            if (BIG && ctail < mp) {                                     // third pass: c2v_old comes back from the planes
+                uint32_t g[DC], sc[DC];
+                tail_offsets(g, sc);
+                Cell mg[DC], ol[DC];
+#pragma unroll
+                for (int k = 0; k < DC; ++k) {
+                    mg[k] = *reinterpret_cast<const Cell *>(smem + g[k]);
+                    ol[k] = *reinterpret_cast<const Cell *>(smem + sc[k]);
+                }
+                uint32_t sx[F];
+#pragma unroll
+                for (int j = 0; j < F; ++j) sx[j] = 0u;
+#pragma unroll
+                for (int k = 0; k < DC; ++k)
+#pragma unroll
+                    for (int j = 0; j < F; ++j) {
+                        const TS mv = (&mg[k].x)[j];
+                        sx[j] ^= VT::signword(mv);
+                        (&mg[k].x)[j] = VT::sub(mv, (&ol[k].x)[j]);
+                    }
+#pragma unroll
+                for (int j = 0; j < F; ++j) {
+                    TS a[DC], o[DC];
+#pragma unroll
+                    for (int k = 0; k < DC; ++k) a[k] = (&mg[k].x)[j];
+                    vq_check<ALGO, DC>(a, o, p.sat_llr);
+#pragma unroll
+                    for (int k = 0; k < DC; ++k) (&ol[k].x)[j] = o[k];
+                }
+#pragma unroll
+                for (int k = 0; k < DC; ++k) *reinterpret_cast<Cell *>(smem + sc[k]) = ol[k];
+#pragma unroll
+                for (int j = 0; j < F; ++j) unsat |= (sx[j] >> 31) << j;
             }
             unsat = __reduce_or_sync(kFull, unsat);
             if (lane == 0 && unsat != 0u) atomicOr(&s_unsat[par], unsat);
