@@ -596,16 +596,16 @@ def main():
 
     mc = {}
     if not args.no_mc:
-      try:
-        mc["n1200"] = mc_leg("Monte-Carlo: Philox BIAWGN %.1f dB noise + MSA f32 decode + error counters on the device, LDPC(1200,3,6) %s, cw=1"
-                             % (SNR_DB, CODE), tab, SNR_DB, B, args.mc_rounds)
-        big = gcodes.random_regular(64800, 3, 6, seed=0).tables
-        mc["n64800"] = mc_leg("Monte-Carlo (config 5): synthetic (3,6) n=64800 (seed 0), BIAWGN 2.5 dB, MSA f32, cw=1, streaming path",
-                              big, 2.5, 2048, max(2, args.mc_rounds // 8))
-        mc["n64800"]["step_hbm_frac"] = (mc["n64800"]["value"] / world) * mc["n64800"]["mean_iters"] * 3402000.0 / 1e9 / peak
-        del big
-      except Exception as exc:                  # a side leg must not lose the headline line (every rank fails alike: no hang)
-        mc["error"] = repr(exc)
+        try:
+            mc["n1200"] = mc_leg("Monte-Carlo: Philox BIAWGN %.1f dB noise + MSA f32 decode + error counters on the device, LDPC(1200,3,6) %s, cw=1"
+                                 % (SNR_DB, CODE), tab, SNR_DB, B, args.mc_rounds)
+            big = gcodes.random_regular(64800, 3, 6, seed=0).tables
+            mc["n64800"] = mc_leg("Monte-Carlo (config 5): synthetic (3,6) n=64800 (seed 0), BIAWGN 2.5 dB, MSA f32, cw=1, streaming path",
+                                  big, 2.5, 2048, max(2, args.mc_rounds // 8))
+            mc["n64800"]["step_hbm_frac"] = (mc["n64800"]["value"] / world) * mc["n64800"]["mean_iters"] * 3402000.0 / 1e9 / peak
+            del big
+        except Exception as exc:                # a side leg must not lose the headline line (every rank fails alike: no hang)
+            mc["error"] = repr(exc)
 
     # ---- e2e: host buffers through the host entry point (what decode_batch calls), copies inside the timed region
     def e2e_leg(label, channel, algo, dtype, param, Yh_, packed_in=False, packed_out=True, ref=None):
