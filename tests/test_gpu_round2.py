@@ -130,6 +130,32 @@ def test_bec_config2_1e5_frames_bit_exact(mods, cw, mi):
     assert total >= 100000
 
 
+@pytest.mark.parametrize("code", ["1200_3_6_rand_ldpc_1", "1200_rho_x5_rand_ldpc_10", "512_3_6_rand_ldpc_2", "12_3_4_ldpc", "7_4_hamming"])
+def test_bec_on_chip_and_streaming_paths_agree(mods, code):
+    """resident_bec (64-frame tiles on chip, boolean node rules, in-kernel bit transposes) and the streaming bit-plane
+    sweeps are the same decoder: words, iteration counts and exit reasons identical, and equal to the oracle's, for
+    ragged batch sizes (partial tiles, a partial second word), every iteration bound, channel and arbitrary symbols."""
+    torch, lib = mods["torch"], mods["lib"]
+    tab = tables(mods, code)
+    og = O.Graph(*G.code_tables(code))
+    eng = mods["engine"].engine_for(tab)
+    rng = np.random.RandomState(17)
+    for B, mi in ((1, 10), (31, 3), (33, 0), (64, 10), (97, 100), (1000, 1), (2049, 10)):
+        Y = G.channel_send("bec", .42, np.ones((B, tab.n), np.int64), 200 + B).astype(np.uint8)
+        if B >= 97:
+            Y[::7] = rng.choice(3, size=Y[::7].shape, p=[.35, .35, .3]).astype(np.uint8)        # inconsistent words too
+        d = torch.from_numpy(Y).cuda()
+        n0 = eng.launch_count
+        a = eng.decode_device_channel(lib.CH_BEC, lib.BEC, lib.F32, 0.0, d, max_iter=mi, flags=lib.PATH_RESIDENT)
+        assert eng.launch_count - n0 == 1                         # one kernel for the whole decode
+        a = {k: v.clone() for k, v in a.items() if v is not None}
+        b = eng.decode_device_channel(lib.CH_BEC, lib.BEC, lib.F32, 0.0, d, max_iter=mi, flags=lib.PATH_STREAMING)
+        ref = O.bec_decode(og, Y, max_iter=mi, nthreads=4)
+        for k in ("x_hat", "iters", "reason"):
+            assert bool((a[k] == b[k]).all()), (B, mi, k)
+            assert (a[k].cpu().numpy() == ref[k]).all(), (B, mi, k)
+
+
 def test_empty_batches_decode_to_empty_results(mods):
     tab = tables(mods, "7_4_hamming")
     n = tab.n
