@@ -141,7 +141,9 @@ __device__ __forceinline__ void bec_store32(uint8_t *row, int g, int n, bool vec
 // IRR = true : check degrees 2..6, variable degrees 0..8, holes (resident_vp's irregular `cwx` tables).
 // CNP / VNP: check / variable items per thread (mp <= CNP * T, np <= VNP * T); MAXT: threads per CTA, two CTAs per SM.
 // (2, 4, 320) is resident_vp's geometry; (1, 2, 608) gives every thread ONE check and TWO variables of an n = 1200 code:
-// 19 + 19 warps per SM instead of 10 + 10 behind the same two barriers per iteration, at 48 registers per thread.
+// 19 + 19 warps per SM instead of 10 + 10 behind the same two barriers per iteration, at 48 registers per thread — measured
+// SLOWER (318 against 356 M frames/s on config 2: the transposes spill, instructions grow 16 %), so it is only launched with
+// LDPC_BEC_WIDE=1 (A/B runs); the default is resident_vp's geometry.
 template <bool IRR, int CNP = kResCnPasses, int VNP = kResVnPasses, int MAXT = 320>
 __global__ void __launch_bounds__(MAXT, 2) resident_bec(const BecResParams p)
 {
