@@ -53,16 +53,21 @@ LDPC_HD Philox4 channel_words(unsigned long long seed, unsigned long long frame,
 }
 
 // Box-Muller on two words: u1 in (0, 1) with 32 bits of resolution (|z| up to 6.7 sigma), u2 in [0, 1).
+// On the device the logarithm and the sine / cosine are the SFU approximations (__logf: 1 ulp-of-2^-21.4 absolute on the
+// result's scale, __sincosf on an angle folded into [-pi, pi): 2^-21.4 absolute): the noise changes by ~1e-6 sigma, far
+// below anything a Monte-Carlo estimate resolves, and the generator kernel gets ~40 % shorter.  The angle is drawn from
+// [-pi, pi) instead of [0, 2 pi): the same uniform distribution on the circle.
 LDPC_HD void box_muller(uint32_t r1, uint32_t r2, float *z0, float *z1)
 {
     const float u1 = fmaf((float)r1, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     const float u2 = (float)r2 * 2.3283064365386963e-10f;
-    const float rad = sqrtf(-2.0f * logf(u1));
     float s, c;
 #if defined(__CUDA_ARCH__)
-    sincospif(2.0f * u2, &s, &c);
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    __sincosf(6.283185307179586f * (u2 - 0.5f), &s, &c);
 #else
-    s = sinf(6.283185307179586f * u2); c = cosf(6.283185307179586f * u2);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    s = sinf(6.283185307179586f * (u2 - 0.5f)); c = cosf(6.283185307179586f * (u2 - 0.5f));
 #endif
     *z0 = rad * c;
     *z1 = rad * s;
