@@ -364,54 +364,76 @@ __global__ void __launch_bounds__(MAXT, 2) resident_bec(const BecResParams p)
 #pragma unroll
                     for (int k = 0; k < 3; ++k) c[k] = *reinterpret_cast<const uint4 *>(smem + (size_t)(k + 1) * S + (size_t)item * 16);
                     const uint4 pr = prior[item];                        // (is +1, is -1) of both words
-                    {
-                        const uint32_t ps4[4] = {pr.x, c[0].y, c[1].y, c[2].y};
-                        const uint32_t ng4[4] = {pr.y, c[0].x & ~c[0].y, c[1].x & ~c[1].y, c[2].x & ~c[2].y};
-                        uint32_t onz[3], opos[3];
-                        bec_vn3_pn<uint32_t>(ps4, ng4, onz, opos, mnz0, mpos0);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) { c[k].x = onz[k]; c[k].y = opos[k]; }
+                    const uint32_t pa[4] = {pr.x, c[0].y, c[1].y, c[2].y}, na[4] = {pr.y, c[0].x & ~c[0].y, c[1].x & ~c[1].y, c[2].x & ~c[2].y};
+                    const uint32_t pb[4] = {pr.z, c[0].w, c[1].w, c[2].w}, nb[4] = {pr.w, c[0].z & ~c[0].w, c[1].z & ~c[1].w, c[2].z & ~c[2].w};
+                    uint32_t onz0[3], opos0[3], onz1[3], opos1[3];
+                    if ((bec_conflict<uint32_t>(pa, na) | bec_conflict<uint32_t>(pb, nb)) == 0u) {
+                        // no frame has votes of both signs at this variable (always so for symbols of an erasure channel
+                        // on a codeword): the sums' signs are ORs of the other inputs
+                        bec_vn3_or<uint32_t>(pa, na, onz0, opos0, mnz0, mpos0);
+                        bec_vn3_or<uint32_t>(pb, nb, onz1, opos1, mnz1, mpos1);
+                    } else {                                             // inconsistent input: the literal rule
+                        bec_vn3_pn<uint32_t>(pa, na, onz0, opos0, mnz0, mpos0);
+                        bec_vn3_pn<uint32_t>(pb, nb, onz1, opos1, mnz1, mpos1);
                     }
-                    {
-                        const uint32_t ps4[4] = {pr.z, c[0].w, c[1].w, c[2].w};
-                        const uint32_t ng4[4] = {pr.w, c[0].z & ~c[0].w, c[1].z & ~c[1].w, c[2].z & ~c[2].w};
-                        uint32_t onz[3], opos[3];
-                        bec_vn3_pn<uint32_t>(ps4, ng4, onz, opos, mnz1, mpos1);
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) { c[k].z = onz[k]; c[k].w = opos[k]; }
-                    }
+                    for (int k = 0; k < 3; ++k) c[k] = make_uint4(onz0[k], opos0[k], onz1[k], opos1[k]);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) *reinterpret_cast<uint4 *>(smem + (size_t)(k + 1) * S + (size_t)item * 16) = c[k];
                 } else {
                     const int d = p.vdeg[item];
                     if (d == 0xff) continue;                             // a position without a variable
                     const uint4 pr = prior[item];
-                    BsInt<5, uint32_t> s0, s1;
-                    s0.set_ternary(pr.x, pr.y);
-                    s1.set_ternary(pr.z, pr.w);
                     uint4 c[DV];
+                    BecVnOr<uint32_t> g0, g1;
+                    g0.init(pr.x, pr.y);
+                    g1.init(pr.z, pr.w);
 #pragma unroll
                     for (int k = 0; k < DV; ++k) {
                         if (k < d) {
                             c[k] = *reinterpret_cast<const uint4 *>(smem + p.pbase[k] + (size_t)item * 16);
-                            s0.add_ternary(c[k].x, c[k].y);
-                            s1.add_ternary(c[k].z, c[k].w);
+                            g0.push(c[k].x, c[k].y);
+                            g1.push(c[k].z, c[k].w);
                         }
                     }
+                    if ((g0.conflict() | g1.conflict()) == 0u) {         // no conflicting votes: ORs of the other inputs
 #pragma unroll
-                    for (int k = 0; k < DV; ++k) {
-                        if (k < d) {
-                            BsInt<5, uint32_t> t0 = s0, t1 = s1;
-                            t0.sub_ternary(c[k].x, c[k].y);
-                            t1.sub_ternary(c[k].z, c[k].w);
-                            uint4 o;
-                            t0.sign(o.x, o.y);
-                            t1.sign(o.z, o.w);
-                            *reinterpret_cast<uint4 *>(smem + p.pbase[k] + (size_t)item * 16) = o;
+                        for (int k = 0; k < DV; ++k) {
+                            if (k < d) {
+                                uint4 o;
+                                g0.out(c[k].x, c[k].y, o.x, o.y);
+                                g1.out(c[k].z, c[k].w, o.z, o.w);
+                                *reinterpret_cast<uint4 *>(smem + p.pbase[k] + (size_t)item * 16) = o;
+                            }
                         }
+                        g0.marg(mnz0, mpos0);
+                        g1.marg(mnz1, mpos1);
+                    } else {                                             // inconsistent input: bit-sliced integers, any degree <= 8
+                        BsInt<5, uint32_t> s0, s1;
+                        s0.set_ternary(pr.x, pr.y);
+                        s1.set_ternary(pr.z, pr.w);
+#pragma unroll
+                        for (int k = 0; k < DV; ++k) {
+                            if (k < d) {
+                                s0.add_ternary(c[k].x, c[k].y);
+                                s1.add_ternary(c[k].z, c[k].w);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < DV; ++k) {
+                            if (k < d) {
+                                BsInt<5, uint32_t> t0 = s0, t1 = s1;
+                                t0.sub_ternary(c[k].x, c[k].y);
+                                t1.sub_ternary(c[k].z, c[k].w);
+                                uint4 o;
+                                t0.sign(o.x, o.y);
+                                t1.sign(o.z, o.w);
+                                *reinterpret_cast<uint4 *>(smem + p.pbase[k] + (size_t)item * 16) = o;
+                            }
+                        }
+                        s0.sign(mnz0, mpos0);
+                        s1.sign(mnz1, mpos1);
                     }
-                    s0.sign(mnz0, mpos0);
-                    s1.sign(mnz1, mpos1);
                 }
                 // x_new = symbols[sign(marginal)] (bec.py:119), merged under the run mask; changed / has-erasures flags
                 // (xv is a subset of ~xe on both sides, so "changed" is just a difference in either plane)

@@ -116,6 +116,37 @@ void decode_bp(const G &g, int algo, const T *prior, const uint8_t *y_hard, int 
 
 extern "C" {
 
+// Conflict-free variable rules (bec_vn3_or, BecVnOr) against the literal ones, on lanes WITHOUT conflicting votes:
+// nz/pos [1 + d] words in (index 0 = prior); out = (onz, opos) per edge then (mnz, mpos); returns the conflict word.
+uint32_t emu_bec_vn_or(int d, const uint32_t *nz, const uint32_t *pos, uint32_t *fast3, uint32_t *fastg, uint32_t *ref)
+{
+    ldpc::BsInt<5, uint32_t> acc;
+    acc.set_ternary(nz[0], pos[0]);
+    for (int k = 1; k <= d; ++k) acc.add_ternary(nz[k], pos[k]);
+    for (int k = 1; k <= d; ++k) {
+        ldpc::BsInt<5, uint32_t> t = acc;
+        t.sub_ternary(nz[k], pos[k]);
+        t.sign(ref[2 * (k - 1)], ref[2 * (k - 1) + 1]);
+    }
+    acc.sign(ref[2 * d], ref[2 * d + 1]);
+    ldpc::BecVnOr<uint32_t> g;
+    g.init(nz[0], pos[0]);
+    for (int k = 1; k <= d; ++k) g.push(nz[k], pos[k]);
+    for (int k = 1; k <= d; ++k) g.out(nz[k], pos[k], fastg[2 * (k - 1)], fastg[2 * (k - 1) + 1]);
+    g.marg(fastg[2 * d], fastg[2 * d + 1]);
+    uint32_t conflict = g.conflict();
+    if (d == 3) {
+        uint32_t p4[4], n4[4], onz[3], opos[3], mnz, mpos;
+        for (int i = 0; i < 4; ++i) { p4[i] = pos[i]; n4[i] = nz[i] & ~pos[i]; }
+        ldpc::bec_vn3_or<uint32_t>(p4, n4, onz, opos, mnz, mpos);
+        for (int k = 0; k < 3; ++k) { fast3[2 * k] = onz[k]; fast3[2 * k + 1] = opos[k]; }
+        fast3[6] = mnz; fast3[7] = mpos;
+        if (ldpc::bec_conflict<uint32_t>(p4, n4) != conflict) return 0xdeadbeefu;
+    }
+    return conflict;
+}
+
+
 // BecCn6 (tree reduction) against BecCnAccT (sequential), one word: nz/pos [6] in, out [12] = (onz, opos) per edge.
 void emu_bec_cn6(const uint32_t *nz, const uint32_t *pos, uint32_t *fast, uint32_t *ref)
 {

@@ -407,3 +407,40 @@ def test_bec_degree6_check_tree_equals_sequential_accumulator(emu):
         fast = np.zeros(12, np.uint32); ref = np.zeros(12, np.uint32)
         emu.emu_bec_cn6(ptr(nz), ptr(pos), ptr(fast), ptr(ref))
         assert (fast == ref).all(), rep
+
+
+def test_bec_conflict_free_variable_rules_equal_the_literal_ones(emu):
+    """bec_vn3_or / BecVnOr (ORs of the other inputs) == the bit-sliced integer rule of bec.py:115-119 on every lane
+    whose inputs carry no conflicting votes, for every degree 0..8; lanes WITH conflicts are flagged by the conflict
+    word (the kernel then takes the literal rule).  Exhaustive for degree 3."""
+    import itertools
+    emu.emu_bec_vn_or.restype = ctypes.c_uint32
+    rng = np.random.RandomState(2)
+    for d in range(0, 9):
+        combos = list(itertools.product((-1, 0, 1), repeat=d + 1)) if d <= 3 else None
+        reps = (len(combos) + 31) // 32 if combos else 40
+        for rep in range(reps):
+            if combos:
+                pick = combos[32 * rep:32 * rep + 32]
+            else:
+                pick = [tuple(rng.choice([-1, 0, 1], p=[.3, .4, .3]) if rng.rand() < .5 else abs(rng.choice([-1, 0, 1])) * rng.choice([-1, 1])
+                              for _ in range(d + 1)) for _ in range(32)]
+                pick = [tuple(int(abs(t)) * (1 if rng.rand() < .5 else -1) for t in c) if l % 4 == 0 else
+                        tuple(int(abs(t)) * s0 for t in c) for l, (c, s0) in enumerate(zip(pick, rng.choice([-1, 1], size=32)))]
+            nz = np.zeros(9, np.uint32); pos = np.zeros(9, np.uint32)
+            for lane, c in enumerate(pick):
+                for i, t in enumerate(c):
+                    if t != 0:
+                        nz[i] |= np.uint32(1 << lane)
+                    if t > 0:
+                        pos[i] |= np.uint32(1 << lane)
+            f3 = np.zeros(20, np.uint32); fg = np.zeros(20, np.uint32); ref = np.zeros(20, np.uint32)
+            conflict = emu.emu_bec_vn_or(d, ptr(nz), ptr(pos), ptr(f3), ptr(fg), ptr(ref))
+            assert conflict != 0xdeadbeef
+            for lane, c in enumerate(pick):
+                has_conflict = any(t > 0 for t in c) and any(t < 0 for t in c)
+                assert ((conflict >> lane) & 1) == int(has_conflict)
+            ok = np.uint32(~np.uint32(conflict) & np.uint32((1 << len(pick)) - 1 if len(pick) < 32 else 0xffffffff))
+            assert ((fg[:2 * d + 2] ^ ref[:2 * d + 2]) & ok).max() == 0, (d, rep)
+            if d == 3:
+                assert ((f3[:8] ^ ref[:8]) & ok).max() == 0, rep
