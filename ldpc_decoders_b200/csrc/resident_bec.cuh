@@ -27,7 +27,7 @@
 // operating points (max_iter 10) nearly every frame runs every iteration.  Symbols are transposed into bit planes
 // inside the kernel: a warp takes 32 variables x 32 frames, every lane reads the 32 bytes of its own row straight from
 // global memory (whole 32-byte sectors: no staging, no barrier), packs them into a value and an erasure word, and five
-// shuffle stages transpose the 32 x 32 bit tile (bit_transpose32); the words leave the same way in reverse.
+// shuffle stages transpose the 32 x 32 bit tile (BecTr); the words leave the same way in reverse.
 #pragma once
 #include "resident_vp.cuh"
 
@@ -66,33 +66,60 @@ __host__ __device__ inline BecSmem bec_smem_layout(int np, int plane_cells, bool
 }
 
 // 32 x 32 bit transpose across a warp: lane i holds row i in, column i out (bit j of the result = bit i of lane j's
-// input).  Five butterfly stages of one shuffle and two logic operations each — against 64 ballots plus 64 compares for
-// the same tile, which made the symbol transposes 46 % of the kernel's instructions (profiles/, r2a).
-__device__ __forceinline__ uint32_t bit_transpose32(uint32_t x, int lane)
-{
+// input).  Five butterfly stages; in each the lane ROTATES its word so that the half its partner wants sits where the
+// partner keeps it (rotate amount and keep-mask depend on the lane only: loop invariants), one shuffle, one bit-select
+// — against 64 ballots plus 64 compares for the same tile, which made the symbol transposes 46 % of the kernel's
+// instructions (profiles/, r2a).
+struct BecTr {
+    uint32_t amt[5], keep[5];
+    __device__ __forceinline__ explicit BecTr(int lane)
+    {
 #pragma unroll
-    for (int s = 0; s < 5; ++s) {
-        const int w = 16 >> s;
-        const uint32_t m = (s == 0) ? 0x0000ffffu : (s == 1) ? 0x00ff00ffu : (s == 2) ? 0x0f0f0f0fu : (s == 3) ? 0x33333333u : 0x55555555u;
-        const uint32_t y = __shfl_xor_sync(kFull, x, w);
-        x = (lane & w) ? ((x & ~m) | ((y >> w) & m)) : ((x & m) | ((y << w) & ~m));
+        for (int s = 0; s < 5; ++s) {
+            const int w = 16 >> s;
+            const uint32_t m = (s == 0) ? 0x0000ffffu : (s == 1) ? 0x00ff00ffu : (s == 2) ? 0x0f0f0f0fu : (s == 3) ? 0x33333333u : 0x55555555u;
+            const bool up = (lane & w) != 0;
+            amt[s] = up ? (uint32_t)w : (uint32_t)(32 - w);          // upper lane: its low half moves up; lower lane: high half down
+            keep[s] = up ? ~m : m;
+            // opaque to the optimiser: otherwise it re-derives both per use from (constant ^ lane bit), three LOP3 per stage
+            asm("" : "+r"(amt[s]), "+r"(keep[s]));
+        }
     }
-    return x;
-}
+    __device__ __forceinline__ uint32_t operator()(uint32_t x) const
+    {
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const uint32_t y = __shfl_xor_sync(kFull, __funnelshift_l(x, x, amt[s]), 16 >> s);
+            x = (x & keep[s]) | (y & ~keep[s]);
+        }
+        return x;
+    }
+};
 
-// Four symbol bytes {0, 1, >= 2 = erased} -> 4-bit (value, erased) nibbles.  0x00204081 = 1 | 1<<7 | 1<<14 | 1<<21
-// gathers the low bits of the four bytes into bits 21..24 of the product (all partial products land on distinct bits).
-__device__ __forceinline__ void sym4_to_nibbles(uint32_t w, uint32_t &val, uint32_t &er)
+// Symbol bytes {0, 1, >= 2 = erased} <-> bit words.  Eight 32-bit loads hold symbols 4 i + b (word i, byte b) of a
+// 32-symbol block; the words below keep symbol 4 i + b at bit 8 b + i, a fixed permutation of the block that the lane
+// <-> variable map of the transposed tile absorbs (bec_tile_var), so packing is one mask + one multiply-add per word
+// and plane (the multiplies run on the FMA pipe, which the kernel leaves idle; its limiter is the ALU pipe).
+__device__ __forceinline__ int bec_tile_var(int lane) { return 4 * (lane & 7) + (lane >> 3); }
+__device__ __forceinline__ void sym32_to_words(const uint32_t (&sy)[8], uint32_t &val, uint32_t &er)
 {
-    const uint32_t e = ((((w & 0x7f7f7f7fu) + 0x7e7e7e7eu) | w) >> 7) & 0x01010101u;     // byte >= 2
-    const uint32_t v = w & 0x01010101u & ~e;
-    val = ((v * 0x00204081u) >> 21) & 0xfu;
-    er = ((e * 0x00204081u) >> 21) & 0xfu;
+    uint32_t v = 0u, e = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t w = sy[i];
+        v = (w & 0x01010101u) * (1u << i) + v;                                  // bit 0 of byte b -> bit 8 b + i (disjoint: + is |)
+        const uint32_t f = (((w & 0x7e7e7e7eu) + 0x7e7e7e7eu) | w) & 0x80808080u;   // bit 7 of byte b: byte >= 2
+        e = (i == 7) ? (e + f) : (__umulhi(f, 1u << (25 + i)) + e);             // >> (7 - i): bit 8 b + 7 -> bit 8 b + i
+    }
+    val = v & ~e;
+    er = e;
 }
-// ... and back: nibbles -> four symbol bytes (value and erased are disjoint).
-__device__ __forceinline__ uint32_t nibbles_to_sym4(uint32_t val, uint32_t er)
+// ... and back (value and erased are disjoint): word i of the block
+__device__ __forceinline__ uint32_t words_to_sym4(uint32_t val, uint32_t er, int i)
 {
-    return ((val * 0x00204081u) & 0x01010101u) | (((er * 0x00204081u) & 0x01010101u) << 1);
+    const uint32_t v = (val >> i) & 0x01010101u;
+    const uint32_t e = (i == 0) ? ((er & 0x01010101u) << 1) : ((er >> (i - 1)) & 0x02020202u);
+    return v | e;
 }
 
 // 32 consecutive symbols (variables 32 g ..) of one frame's row, straight from / to global memory.  A lane touches whole
@@ -164,6 +191,7 @@ __global__ void __launch_bounds__(MAXT, 2) resident_bec(const BecResParams p)
     __shared__ int s_tile;
 
     const int tid = threadIdx.x, T = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int tvar = bec_tile_var(lane);
 
     // ---- per-thread graph indices -> registers (once per CTA), packed exactly as in resident_vp
     uint32_t cw[CNP][CH];
@@ -215,6 +243,7 @@ __global__ void __launch_bounds__(MAXT, 2) resident_bec(const BecResParams p)
         // warp = 32 consecutive variables x 32 frames: lane = frame packs its 32 symbols into a value word and an
         // erasure word, two bit transposes turn them into the planes, lane = variable stores its half cell
         {
+            const BecTr tr(lane);
             uint32_t er0 = 0u, er1 = 0u;
             const uint8_t *row0 = p.y + (size_t)(f0 + lane) * n, *row1 = row0 + (size_t)32 * n;
             for (int g = warp; g * 32 < n; g += nwarps) {
@@ -223,19 +252,13 @@ __global__ void __launch_bounds__(MAXT, 2) resident_bec(const BecResParams p)
                 for (int i = 0; i < 8; ++i) { sa[i] = 0u; sb[i] = 0u; }
                 if (lane < nvalid[0]) bec_load32(row0, g, n, vec16, vec4, sa);
                 if (lane < nvalid[1]) bec_load32(row1, g, n, vec16, vec4, sb);
-                uint32_t V0 = 0u, E0 = 0u, V1 = 0u, E1 = 0u;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    uint32_t v4, e4;
-                    sym4_to_nibbles(sa[i], v4, e4);
-                    V0 |= v4 << (4 * i); E0 |= e4 << (4 * i);
-                    sym4_to_nibbles(sb[i], v4, e4);
-                    V1 |= v4 << (4 * i); E1 |= e4 << (4 * i);
-                }
-                V0 = bit_transpose32(V0, lane); E0 = bit_transpose32(E0, lane);
-                V1 = bit_transpose32(V1, lane); E1 = bit_transpose32(E1, lane);
+                uint32_t V0, E0, V1, E1;
+                sym32_to_words(sa, V0, E0);
+                sym32_to_words(sb, V1, E1);
+                V0 = tr(V0); E0 = tr(E0);
+                V1 = tr(V1); E1 = tr(E1);
                 er0 |= E0; er1 |= E1;
-                const int v = g * 32 + lane;
+                const int v = g * 32 + tvar;                                      // the variable this lane holds after the transposes
                 if (v < n) xc[s_vpos[v]] = make_uint4(E0, V0, E1, V1);           // (xe, xv) of both words
             }
             er0 = __reduce_or_sync(kFull, er0);
@@ -459,22 +482,23 @@ __global__ void __launch_bounds__(MAXT, 2) resident_bec(const BecResParams p)
 
         // ================================ words out: bit planes -> rows ================================
         {
+            const BecTr tr(lane);
             uint8_t *row0 = p.x_hat + (size_t)(f0 + lane) * n, *row1 = row0 + (size_t)32 * n;
             for (int g = warp; g * 32 < n; g += nwarps) {
-                const int v = g * 32 + lane;
+                const int v = g * 32 + tvar;
                 uint4 xw = make_uint4(0u, 0u, 0u, 0u);
                 if (v < n) xw = xc[s_vpos[v]];
-                const uint32_t E0 = bit_transpose32(xw.x, lane), V0 = bit_transpose32(xw.y, lane);   // lane = frame again
-                const uint32_t E1 = bit_transpose32(xw.z, lane), V1 = bit_transpose32(xw.w, lane);
+                const uint32_t E0 = tr(xw.x), V0 = tr(xw.y);                      // lane = frame again
+                const uint32_t E1 = tr(xw.z), V1 = tr(xw.w);
                 uint32_t sy[8];
                 if (lane < nvalid[0]) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) sy[i] = nibbles_to_sym4((V0 >> (4 * i)) & 0xfu, (E0 >> (4 * i)) & 0xfu);
+                    for (int i = 0; i < 8; ++i) sy[i] = words_to_sym4(V0, E0, i);
                     bec_store32(row0, g, n, vec16, vec4, sy);
                 }
                 if (lane < nvalid[1]) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) sy[i] = nibbles_to_sym4((V1 >> (4 * i)) & 0xfu, (E1 >> (4 * i)) & 0xfu);
+                    for (int i = 0; i < 8; ++i) sy[i] = words_to_sym4(V1, E1, i);
                     bec_store32(row1, g, n, vec16, vec4, sy);
                 }
             }
