@@ -50,6 +50,15 @@ METRIC = "decoded_frames_per_s"
 UNIT = "frames/s"
 
 
+def kernel_label(eng):
+    """The on-chip kernel LDPC_PATH_AUTO launches in float32: ldpc_resident_kernel names the LAYOUT family
+    ("resident_vp" = variable planes, regular or irregular); its kernel is resident_vq unless LDPC_RESIDENT_VP is set."""
+    name = eng.resident_kernel
+    if name == "resident_vp" and os.environ.get("LDPC_RESIDENT_VP") is None:
+        return "resident_vq"
+    return name
+
+
 def load_code(name=CODE):
     import _golden as G
     return G.code_tables(name)
@@ -283,7 +292,7 @@ def extra_workloads(torch, lib, eng_mod, Tables, peak):
         frac = (cn_b + vn_b) * 3 / (ms / 1e3) / 1e9 / peak
         rec = {"workload": label, "value": fps, "unit": UNIT, "mean_iters": float(iters.mean()),
                "edge_updates_per_s": 2 * tab.E * float(iters.sum()) * 3 / (ms / 1e3),
-               "path": ("on-chip (%s)" % ("resident_vq<double> / resident_vd" if dtype == lib.F64 else eng.resident_kernel)) if on_chip else "streaming"}
+               "path": ("on-chip (%s)" % ("resident_vq<double> / resident_vd" if dtype == lib.F64 else kernel_label(eng))) if on_chip else "streaming"}
         # streaming: fraction of the measured HBM peak the whole step reaches; on-chip: the same algorithmic bytes never
         # touch HBM, so the figure is an EFFECTIVE one (see roofline.note)
         rec["effective_hbm_frac" if on_chip else "step_hbm_frac"] = frac
@@ -310,10 +319,10 @@ def extra_workloads(torch, lib, eng_mod, Tables, peak):
         ms = timed_steps(torch, fi, 3, 2, None)
         iters = res["o"]["iters"].cpu().numpy()
         out.append({"workload": "irregular LDPC n=1200 (1200_rho_x5_rand_ldpc_1) BSC p=0.06 %s f32, max_iter 10, cw=0 (%s)"
-                                % (nm, eng.resident_kernel or "streaming"),
+                                % (nm, kernel_label(eng) or "streaming"),
                     "value": frames * 3 / (ms / 1e3), "unit": UNIT, "mean_iters": float(iters.mean()),
                     "edge_updates_per_s": 2 * irr.E * float(iters.sum()) * 3 / (ms / 1e3),
-                    "path": ("on-chip (%s)" % eng.resident_kernel) if eng.resident_kernel else "streaming"})
+                    "path": ("on-chip (%s)" % kernel_label(eng)) if eng.resident_kernel else "streaming"})
     # Monte-Carlo round entirely on the GPU (on-device Philox channel + decode + error count): what sim.py --noise device runs
     eng = eng_mod.engine_for(tab)
     frames = 32768
@@ -518,9 +527,7 @@ def main():
     effective_hbm = None
     # regular codes in the two-CTA geometry run resident_vq (resident_vp with the frame hand-over fused into the variable
     # phase) unless LDPC_RESIDENT_VP=1 asks for the older kernel; ldpc_resident_kernel names the family
-    res_name = eng.resident_kernel
-    if res_name == "resident_vp" and os.environ.get("LDPC_RESIDENT_VP") is None:
-        res_name = "resident_vq"
+    res_name = kernel_label(eng)
     if resident:
         roofline, effective_hbm = resident_roofline(main, res_name, 4,
                                                     "ncu (profiles/, r2e): no pipe saturated - shared-memory wavefronts 64 %, issue 58 %, ALU 46 %, FMA 15 %.")

@@ -252,9 +252,10 @@ int ldpc_resident_frames(const ldpc_t *h);
  * (default 0.4; 0 keeps file order) before ldpc_create. */
 int ldpc_resident_plan(const ldpc_t *h, long *out);
 
-/* Name of the on-chip kernel LDPC_PATH_RESIDENT launches for this code: "resident_vp" (regular codes, variable-plane
- * message layout, csrc/resident_vp.cuh), "resident_bp" (any degree profile <= 8, csrc/resident_bp.cuh) or "" when the
- * code has no on-chip path.  The string is static. */
+/* Layout family of the on-chip path of this code: "resident_vp" (variable-plane message layout, regular and irregular
+ * codes: csrc/resident_vp.cuh and the kernel that runs on it by default, resident_vq, csrc/resident_vq.cuh),
+ * "resident_bp" (check-major layout, any degree profile <= 8, csrc/resident_bp.cuh) or "" when the code has no on-chip
+ * path.  The string is static. */
 const char *ldpc_resident_kernel(const ldpc_t *h);
 
 /* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
