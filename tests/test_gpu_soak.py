@@ -1,0 +1,68 @@
+"""Randomised soak of the on-chip kernels against the oracle at batch sizes that force frame hand-overs.
+
+The fuzz tests of test_gpu_parity.py use batches that fit the kernels' slots (no frame ever follows another one into a
+slot); the 1e4-frame tests exercise the hand-over on two codes at fixed parameters.  Here every case draws a code, a
+channel, an operating point, an iteration bound, an arithmetic type and a batch size of a few thousand frames
+(several frames per slot, ragged last tile), and the words, iteration counts and exit reasons must equal the oracle's.
+LDPC_SOAK_CASES (default 6) sets the number of cases; profiles/r2/soak.log holds a run with 150.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import _golden as G
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = int(os.environ.get("LDPC_SOAK_CASES", "6"))
+CODES = ["1200_3_6_rand_ldpc_1", "1200_3_6_rand_ldpc_7", "1200_rho_x5_rand_ldpc_2", "1200_rho_x5_rand_ldpc_9",
+         "512_3_6_rand_ldpc_1", "margulis", "12_3_4_ldpc", "7_4_hamming"]
+
+
+@pytest.fixture(scope="module")
+def mods():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ldpc_decoders_b200 as pkg
+    from ldpc_decoders_b200 import _lib, bec, biawgn, bsc, engine
+    return dict(torch=torch, pkg=pkg, lib=_lib, bec=bec, biawgn=biawgn, bsc=bsc, engine=engine)
+
+
+@pytest.mark.parametrize("case", list(range(CASES)))
+def test_soak_case(mods, case):
+    rng = np.random.RandomState(31000 + case)
+    code = CODES[rng.randint(len(CODES))]
+    m, n, rows, cols = G.code_tables(code)
+    tab = mods["pkg"].Tables(m, n, rows, cols)
+    og = O.Graph(m, n, rows, cols)
+    small = n < 100
+    # several frames per slot: 296 CTAs x 4 frames (148 x 4 for the one-CTA geometry, 64-frame tiles for erasures)
+    B = int(rng.randint(2500, 7000)) if not small else int(rng.randint(40000, 90000))
+    mi = int(rng.choice([1, 2, 5, 10, 10, 10, 25, 100]))
+    cw = int(rng.randint(2)) if code.startswith("1200_3_6") else 0        # all-ones is a codeword of the (3,6) codes (even checks)
+    x = np.zeros((B, n), np.int64) + cw
+    kind = rng.choice(["biawgn", "bsc", "bec"])
+    dt = np.float32 if rng.rand() < .6 else np.float64
+    if kind == "bec":
+        p = float(rng.uniform(.3, .5)) if not small else float(rng.uniform(.1, .4))
+        Y = G.channel_send("bec", p, x, 100 + case).astype(np.uint8)
+        ref = O.bec_decode(og, Y, max_iter=mi, nthreads=8)
+        x_hat, iters, reason = mods["bec"].SPA(p, tab, max_iter=mi).decode_batch(Y, return_reason=True)
+    elif kind == "bsc":
+        p = float(rng.uniform(.02, .09))
+        Yh = G.channel_send("bsc", p, x, 200 + case).astype(np.uint8)
+        ref = O.bp_decode(og, O.MSA, O.llr_bsc(p, Yh).astype(dt), y_hard=Yh, max_iter=mi, nthreads=8)
+        x_hat, iters, reason = mods["bsc"].MSA(p, tab, max_iter=mi, dtype=dt).decode_batch(Yh, return_reason=True)
+    else:
+        snr = float(rng.uniform(.5, 3.5))
+        Y = G.channel_send("biawgn", snr, x, 300 + case)
+        ref = O.bp_decode(og, O.MSA, O.llr_biawgn(snr, Y).astype(dt), max_iter=mi, nthreads=8)
+        x_hat, iters, reason = mods["biawgn"].MSA(snr, tab, max_iter=mi, dtype=dt).decode_batch(Y, return_reason=True)
+    what = "%s %s %s B=%d max_iter=%d cw=%d" % (code, kind, dt.__name__, B, mi, cw)
+    assert (iters == ref["iters"]).all(), what
+    assert (reason == ref["reason"]).all(), what
+    assert (x_hat == ref["x_hat"]).all(), what
+    print("soak ok:", what, "mean iters %.2f" % iters.mean())
