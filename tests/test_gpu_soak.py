@@ -66,3 +66,34 @@ def test_soak_case(mods, case):
     assert (reason == ref["reason"]).all(), what
     assert (x_hat == ref["x_hat"]).all(), what
     print("soak ok:", what, "mean iters %.2f" % iters.mean())
+
+
+@pytest.mark.parametrize("case", list(range(max(2, CASES // 3))))
+def test_soak_sum_product_on_chip_equals_streaming(mods, case):
+    """Sum-product float32 has no bit-exact CPU counterpart (tolerance tests hold it to the reference); the on-chip kernel
+    and the streaming sweeps run the same arithmetic, so at hand-over batch sizes they must agree bit for bit."""
+    torch, lib = mods["torch"], mods["lib"]
+    rng = np.random.RandomState(47000 + case)
+    code = CODES[rng.randint(len(CODES) - 2)]                             # the 1200 / 512 / Margulis codes
+    m, n, rows, cols = G.code_tables(code)
+    eng = mods["engine"].engine_for(mods["pkg"].Tables(m, n, rows, cols))
+    B = int(rng.randint(2500, 6000))
+    mi = int(rng.choice([2, 5, 10, 10, 25, 100]))
+    x = np.zeros((B, n), np.int64)
+    if rng.rand() < .5:
+        snr = float(rng.uniform(.5, 3.5))
+        ch, prm = lib.CH_BIAWGN, 10 ** (-snr / 10)
+        y = torch.from_numpy(G.channel_send("biawgn", snr, x, 400 + case).astype(np.float32)).cuda()
+    else:
+        p = float(rng.uniform(.02, .09))
+        ch, prm = lib.CH_BSC, float(np.log(1 - p) - np.log(p))
+        y = torch.from_numpy(G.channel_send("bsc", p, x, 500 + case).astype(np.uint8)).cuda()
+    a = eng.decode_device_channel(ch, lib.SPA, lib.F32, prm, y, max_iter=mi, flags=lib.PATH_STREAMING)
+    a = {k: (v.clone() if v is not None else None) for k, v in a.items()}
+    n0 = eng.launch_count
+    b = eng.decode_device_channel(ch, lib.SPA, lib.F32, prm, y, max_iter=mi)
+    assert eng.launch_count - n0 == 1                                     # the on-chip kernel: one launch
+    what = "%s SPA f32 B=%d max_iter=%d" % (code, B, mi)
+    for k in ("iters", "reason", "x_hat"):
+        assert bool((a[k] == b[k]).all()), (what, k)
+    print("soak ok:", what, "mean iters %.2f" % float(b["iters"].float().mean()))
