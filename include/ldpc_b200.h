@@ -34,6 +34,14 @@
  *     The on-chip path (one launch per batch) never synchronises.
  *   - one handle per (process, device); a handle is not thread-safe.
  *   - there is NO CPU fallback: without a CUDA device ldpc_create fails.
+ *   - environment variables, read by the library for A/B measurements only
+ *     (results are identical with and without them; scripts/r2_*.sh use them):
+ *     LDPC_NO_COMPACTION=1 (streaming path without active-frame compaction),
+ *     LDPC_RESIDENT_VP=1 (the round-1 on-chip kernels resident_vp / resident_vd
+ *     instead of resident_vq), LDPC_RESIDENT_LAYOUT=check (check-major on-chip
+ *     layout, resident_bp), LDPC_BEC_WIDE=1 (608-thread geometry of the on-chip
+ *     erasure kernel), LDPC_PLAN_EFFORT=<float> (placement annealing effort,
+ *     read at ldpc_create).
  */
 #ifndef LDPC_B200_H
 #define LDPC_B200_H
