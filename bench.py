@@ -299,6 +299,9 @@ def extra_workloads(torch, lib, eng_mod, Tables, peak):
         out.append(rec)
 
     tab = Tables(*load_code())
+    # the headline workload in a four times larger batch: the launch's fixed cost (first rows in, last frames out: ~29 us) is
+    # 3.5 % of a 32768-frame step and 0.9 % of this one
+    bp_case("headline workload at 131072 frames per step: LDPC(1200,3,6) BIAWGN 2.0 dB MSA f32, max_iter 10", tab, lib.MSA, lib.F32, 2.0, 131072)
     bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB MSA f64 (the reference's arithmetic), max_iter 10", tab, lib.MSA, lib.F64, 2.0, 32768)
     bp_case("LDPC(1200,3,6) BIAWGN 2.0 dB SPA f64 (formula mirror), max_iter 10, cw=0", tab, lib.SPA, lib.F64, 2.0, 16384, cw=0)
     big = codes.random_regular(64800, 3, 6, seed=0).tables
